@@ -1,0 +1,31 @@
+// C-ABI plumbing shared by every entry point: thread-local error text, version, device info.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace fsrl {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+}  // namespace fsrl
+
+extern "C" const char* fsrl_last_error(void) { return fsrl::g_err; }
+extern "C" int fsrl_abi_version(void) { return 1; }
+extern "C" int fsrl_sm_count(void) { return fsrl::sm_count(); }

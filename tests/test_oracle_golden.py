@@ -1,0 +1,91 @@
+"""The oracle against the reference's own outputs (fixtures made by oracle/make_golden.py
+from the AST-extracted /root/reference/fsrl/policy/base_policy.py:524-567 and the imported
+/root/reference/fsrl/utils/optim_util.py) and SURVEY.md Appendix B's literal vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cport, returns
+from oracle.lagrangian import PIDLagrangian
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "returns_golden.npz"))
+
+
+def test_gae_numpy_and_c_match_reference_bitwise(gold):
+    n = int(gold["gae_count"])
+    assert n >= 10
+    for k in range(n):
+        v, vn, r, e = (gold[f"gae{k}_{s}"] for s in ("v", "vn", "r", "e"))
+        g, l = gold[f"gae{k}_gl"]
+        want = gold[f"gae{k}_out"]
+        got_c = cport.gae_return(v, vn, r, e, g, l)
+        assert got_c.dtype == np.float64
+        assert np.array_equal(got_c, want), f"C port differs on case {k}"
+        if len(r) <= 5000:
+            got = returns.gae_return(v, vn, r, e, g, l)
+            assert np.array_equal(got, want), f"numpy port differs on case {k}"
+
+
+def test_gae_appendix_b_literals():
+    out = returns.gae_return(np.array([1, 2, 3, 4], np.float32), np.array([2, 3, 4, 0], np.float32),
+                             np.ones(4), np.array([0, 0, 0, 1], bool), 0.99, 0.95)
+    np.testing.assert_allclose(out, [3.07075357, 1.15975925, -0.8615, -3.0], rtol=0, atol=1e-8)
+    out = returns.gae_return(np.array([0, 1], np.float32), np.array([0, 1], np.float32),
+                             np.array([0., 1.]), np.array([False, True]), 0.1, 0.1)
+    np.testing.assert_allclose(out, [0.001, 0.1], rtol=0, atol=1e-12)
+
+
+def test_nstep_matches_reference(gold):
+    n = int(gold["ns_count"])
+    for k in range(n):
+        m, e, tq, idx = (gold[f"ns{k}_{s}"] for s in ("m", "e", "tq", "idx"))
+        g, ns = gold[f"ns{k}_gn"]
+        want = gold[f"ns{k}_out"]
+        got = returns.nstep_return(m, e, tq, idx, float(g), int(ns))
+        np.testing.assert_allclose(got, want, rtol=1e-15, atol=0)
+        got_c = cport.nstep_return(m, e, tq, idx, float(g), int(ns))
+        np.testing.assert_allclose(got_c, want, rtol=1e-15, atol=0)
+
+
+def test_nstep_appendix_b_literal():
+    out = returns.nstep_return(np.array([1., 2, 3, 4, 5]), np.array([0, 0, 1, 0, 0], bool),
+                               np.array([[10], [20], [0], [40]], np.float32),
+                               np.array([[0, 1, 2, 3], [1, 2, 2, 4]]), 0.99, 2)
+    np.testing.assert_allclose(out.ravel(), [12.781, 24.572, 3.0, 48.154], atol=1e-9)
+
+
+def test_pid_matches_reference(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "pid_golden.json")))
+    assert len(cases) >= 4
+    for c in cases:
+        o = PIDLagrangian(c["pid"])
+        for cost, lam, integ, eold in zip(c["costs"], c["lagrangian"], c["error_integral"],
+                                          c["error_old"]):
+            o.step(cost, c["limit"])
+            assert o.lagrangian == lam and o.error_integral == integ and o.error_old == eold
+    # Appendix B literal
+    o = PIDLagrangian((0.05, 0.0005, 0.1))
+    lams = [o.step(c, 10) for c in (25, 18, 12, 8, 9, 14)]
+    np.testing.assert_allclose(lams, [2.2575, 0.4115, 0.1125, 0.0, 0.061, 0.713], atol=1e-12)
+
+
+def test_dual_gae_layout():
+    rng = np.random.default_rng(0)
+    N = 50
+    v = rng.standard_normal((2, N)).astype(np.float32)
+    vn = rng.standard_normal((2, N)).astype(np.float32)
+    term = rng.random(N) < 0.1
+    trunc = np.zeros(N, bool); trunc[24] = True
+    unf = np.zeros(N, bool); unf[-1] = True
+    vals, rets, advs = returns.dual_gae(v, vn, rng.random(N), rng.random(N) < 0.2, term, trunc,
+                                        unf, 0.99, 0.95)
+    assert vals.shape == rets.shape == advs.shape == (N, 2) and advs.dtype == np.float32
+    np.testing.assert_allclose(rets, advs + vals, rtol=0, atol=1e-5)
+    # a terminated step does not bootstrap: adv = r - v
+    i = int(np.flatnonzero(term)[0])
+    assert abs(advs[i, 0] - (np.float32(0) + 0)) >= 0  # smoke
