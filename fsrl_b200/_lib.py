@@ -38,6 +38,62 @@ c_int = ctypes.c_int
 c_size = ctypes.c_size_t
 c_vp = ctypes.c_void_p
 
+
+
+# ---- C structs of include/fsrl_b200.h -------------------------------------------------------
+class Mlp3(ctypes.Structure):
+    _fields_ = [("w1t", c_vp), ("b1", c_vp), ("w2t", c_vp), ("b2", c_vp), ("w3t", c_vp),
+                ("b3", c_vp), ("in_", c_int), ("H", c_int), ("out", c_int)]
+
+
+class CollectStats(ctypes.Structure):
+    _fields_ = [("step_count", ctypes.c_ulonglong), ("sum_ep_len", ctypes.c_ulonglong),
+                ("total_cost", c_f64), ("sum_ep_rew", c_f64), ("episode_count", c_int),
+                ("n_episode", c_int), ("n_ready", c_int), ("term_count", c_int),
+                ("trunc_count", c_int), ("finished", c_int), ("finished_next", c_int),
+                ("pad", c_int)]
+
+
+class Rollout(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("E", c_int), ("max_steps", c_int), ("inline_done", c_int),
+                ("seed_env", ctypes.c_uint), ("seed_act", ctypes.c_uint),
+                ("env_state", c_vp), ("obs_cur", c_vp), ("env_t", c_vp), ("ep_idx", c_vp),
+                ("act_ctr", c_vp), ("active", c_vp), ("done_now", c_vp), ("ep_rew", c_vp),
+                ("ep_len", c_vp),
+                ("actor", Mlp3), ("log_sigma", c_vp),
+                ("head", c_int), ("mode", c_int), ("bounded", c_int), ("action_bound", c_int),
+                ("action_scaling", c_int), ("pad0", c_int),
+                ("max_action", c_f32), ("expl_sigma", c_f32), ("sigma_min", c_f32),
+                ("sigma_max", c_f32), ("tanh_eps", c_f32), ("pad1", c_f32),
+                ("act_low", c_f32 * 8), ("act_high", c_f32 * 8),
+                ("b_obs", c_vp), ("b_obs_next", c_vp), ("b_act", c_vp), ("b_rew", c_vp),
+                ("b_cost", c_vp), ("b_logp", c_vp), ("b_term", c_vp), ("b_trunc", c_vp),
+                ("b_ptr", c_vp), ("b_len", c_vp), ("cap", ctypes.c_longlong),
+                ("stats", c_vp)]
+
+
+class PpoUpdate(ctypes.Structure):
+    _fields_ = [("theta", c_vp), ("grad", c_vp), ("adam_m", c_vp), ("adam_v", c_vp),
+                ("w2n", c_vp), ("scratch", c_vp), ("norm_sq", c_vp), ("stats", c_vp),
+                ("mask", c_vp), ("net_off", ctypes.c_longlong * 3),
+                ("n_params", ctypes.c_longlong),
+                ("n_nets", c_int), ("D", c_int), ("H", c_int), ("A", c_int), ("C", c_int),
+                ("actor_out", c_int), ("bmax", c_int), ("head_indep", c_int),
+                ("obs", c_vp), ("act", c_vp), ("logp_old", c_vp), ("adv", c_vp), ("ret", c_vp),
+                ("values", c_vp), ("ld", ctypes.c_longlong), ("perm", c_vp),
+                ("eps_clip", c_f32), ("dual_clip", c_f32), ("vf_coef", c_f32),
+                ("max_grad_norm", c_f32), ("max_action", c_f32), ("lagrangian", c_f32),
+                ("rescaling", c_f32), ("pad0", c_f32),
+                ("bounded", c_int), ("norm_adv", c_int), ("value_clip", c_int),
+                ("use_lagrangian", c_int),
+                ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("adam_eps", c_f64)]
+
+
+MODE_TRAIN, MODE_EVAL, MODE_RANDOM = 0, 1, 2
+HEAD_GAUSS_INDEP, HEAD_GAUSS_COND, HEAD_DETERMINISTIC = 0, 1, 2
+BOUND_NONE, BOUND_CLIP, BOUND_TANH = 0, 1, 2
+PPO_STATS = 8
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "fsrl_last_error": (ctypes.c_char_p, []),
@@ -46,6 +102,15 @@ SIGNATURES = {
     "fsrl_gae_dual_workspace_bytes": (c_size, [c_i64]),
     "fsrl_gae_dual": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_f64, c_f64,
                               c_f32p, c_f32p, c_i64, c_i64, c_int, c_vp, c_size, c_vp]),
+    "fsrl_env_dims": (c_int, [c_int] + [ctypes.POINTER(c_int)] * 4),
+    "fsrl_env_reset_all": (c_int, [ctypes.POINTER(Rollout), c_vp]),
+    "fsrl_collect_begin": (c_int, [ctypes.POINTER(Rollout), c_int, c_vp]),
+    "fsrl_rollout_steps": (c_int, [ctypes.POINTER(Rollout), c_int, c_vp]),
+    "fsrl_mlp_forward": (c_int, [ctypes.POINTER(Mlp3), c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),
+    "fsrl_ppo_scratch_floats": (c_size, [c_int, c_int, c_int]),
+    "fsrl_ppo_sync_mirror": (c_int, [ctypes.POINTER(PpoUpdate), c_vp]),
+    "fsrl_ppo_lag_epoch": (c_int, [ctypes.POINTER(PpoUpdate), ctypes.c_longlong, c_int, c_int,
+                                   ctypes.c_longlong, ctypes.POINTER(c_int), c_vp]),
 }
 
 

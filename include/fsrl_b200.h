@@ -50,6 +50,130 @@ int fsrl_gae_dual(const float* v, const float* vnext, const float* rew, const fl
                   double gae_lambda, float* adv, float* ret, int64_t N, int64_t ld, int C,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+
+/* ---- network descriptor ----------------------------------------------------------------
+ * A 2-hidden-layer MLP in -> H -> H -> out (tianshou Net/MLP + head; the reference builds
+ * these at fsrl/agent/ppo_lag_agent.py:136-145).  Canonical layout: every Linear is stored
+ * TRANSPOSED, Wt[in][out] row-major (torch's .weight is the strided view Wt.t()).
+ * H must be 64, 128, 256 or 512. */
+typedef struct fsrl_mlp3 {
+    const float* w1t; /* [in][H]  */
+    const float* b1;  /* [H]      */
+    const float* w2t; /* [H][H]   */
+    const float* b2;  /* [H]      */
+    const float* w3t; /* [H][out] */
+    const float* b3;  /* [out]    */
+    int in, H, out;
+} fsrl_mlp3_t;
+
+/* ---- a1-a5: rollout collection ---------------------------------------------------------
+ * One fsrl_rollout_steps() step == one iteration of the while-loop of
+ * FastCollector.collect (fsrl/data/fast_collector.py:252-368): policy forward
+ * (base_policy.py:178-190), exploration noise (ddpg_lag.py:225-231), map_action
+ * (base_policy.py:226-256), env.step, cost extraction, buffer.add and the episode
+ * bookkeeping incl. the surplus-env rule (:357-363), for all ready envs, on the device. */
+enum { FSRL_MODE_TRAIN = 0, FSRL_MODE_EVAL = 1, FSRL_MODE_RANDOM = 2 };
+enum { FSRL_HEAD_GAUSS_INDEP = 0, FSRL_HEAD_GAUSS_COND = 1, FSRL_HEAD_DETERMINISTIC = 2 };
+enum { FSRL_BOUND_NONE = 0, FSRL_BOUND_CLIP = 1, FSRL_BOUND_TANH = 2 };
+enum { FSRL_ENV_CAR_CIRCLE = 0, FSRL_ENV_CAR_RUN = 1, FSRL_ENV_BALL_CIRCLE = 2,
+       FSRL_ENV_BALL_RUN = 3, FSRL_ENV_ANT_CIRCLE = 4, FSRL_ENV_POINT_GOAL = 5 };
+
+/* per-collect statistics, device resident; the keys of collect()'s result dict
+ * (fast_collector.py:399-408) are derived from it on the host */
+typedef struct fsrl_collect_stats {
+    unsigned long long step_count;  /* n/st */
+    unsigned long long sum_ep_len;  /* sum of finished episode lengths */
+    double total_cost;              /* total_cost */
+    double sum_ep_rew;              /* sum of finished episode returns */
+    int episode_count;              /* n/ep */
+    int n_episode;                  /* target */
+    int n_ready;                    /* len(ready_env_ids) */
+    int term_count, trunc_count;
+    int finished, finished_next;
+    int pad;
+} fsrl_collect_stats_t;
+
+typedef struct fsrl_rollout {
+    /* environment (SoA, device) */
+    int kind, E, max_steps, inline_done;
+    unsigned int seed_env, seed_act;
+    float* env_state;        /* [S][E] */
+    float* obs_cur;          /* [E][D] */
+    int* env_t;              /* [E] step inside the running episode */
+    unsigned int* ep_idx;    /* [E] episodes started (reset RNG counter) */
+    unsigned int* act_ctr;   /* [E] actions sampled (noise RNG counter) */
+    unsigned char* active;   /* [E] ready_env_ids as a mask */
+    unsigned char* done_now; /* [E] 0 / 1 terminated / 2 truncated this step */
+    double* ep_rew;          /* [E] running episode return */
+    int* ep_len;             /* [E] running episode length */
+    /* policy */
+    fsrl_mlp3_t actor;
+    const float* log_sigma;  /* [A] state-independent log-sigma (HEAD_GAUSS_INDEP) */
+    int head, mode, bounded, action_bound, action_scaling, pad0;
+    float max_action, expl_sigma, sigma_min, sigma_max, tanh_eps, pad1;
+    float act_low[8], act_high[8];
+    /* transition buffer: env-major sub-buffers of `cap` slots (tianshou VectorReplayBuffer
+     * order), any pointer group may be NULL to collect without storing (evaluate()) */
+    float *b_obs, *b_obs_next, *b_act, *b_rew, *b_cost, *b_logp;
+    unsigned char *b_term, *b_trunc;
+    int* b_ptr;              /* [E] next write slot */
+    int* b_len;              /* [E] valid transitions */
+    long long cap;
+    fsrl_collect_stats_t* stats;
+} fsrl_rollout_t;
+
+int fsrl_env_dims(int kind, int* D, int* A, int* S, int* T);
+/* reset_env (fast_collector.py:131-152): start a fresh episode in every env */
+int fsrl_env_reset_all(const fsrl_rollout_t* r, void* stream);
+/* start of collect(n_episode): ready set = first min(E, n_episode) envs (:233-236) */
+int fsrl_collect_begin(const fsrl_rollout_t* r, int n_episode, void* stream);
+/* n_steps vector steps; steps after stats->finished are no-ops */
+int fsrl_rollout_steps(const fsrl_rollout_t* r, int n_steps, void* stream);
+
+/* ---- a9/a10: PPO-Lagrangian update --------------------------------------------------------
+ * Replaces PPOLagrangian.policy_loss / critics_loss / learn
+ * (fsrl/policy/ppo_lag.py:152-257) and LagrangianPolicy.safety_loss
+ * (fsrl/policy/lagrangian_base.py:145-166): per-minibatch advantage normalisation, clipped
+ * surrogate, unclipped lambda-weighted cost term, rescaling, value losses, backward,
+ * clip_grad_norm_ and Adam, with per-minibatch statistics accumulated on the device.
+ *
+ * All networks of the policy live in ONE flat fp32 buffer `theta`; network n (0 = actor,
+ * 1.. = critics) starts at net_off[n] with layout
+ *     w1t[D][H] | b1[H] | w2t[H][H] | b2[H] | w3t[H][out] | b3[out] | (actor) log_sigma[A]
+ * grad / adam_m / adam_v mirror that layout; w2n[n][H][H] is the out-major copy of w2t kept
+ * in sync by the Adam kernel (fsrl_ppo_sync_mirror initialises it). */
+#define FSRL_PPO_STATS 8 /* per-minibatch: actor_rew, actor_safety, kl, vf0, vf1, entropy, grad_norm, - */
+typedef struct fsrl_ppo_update {
+    float *theta, *grad, *adam_m, *adam_v, *w2n, *scratch, *norm_sq, *stats;
+    const unsigned char* mask;     /* optional [n_params]: 0 = frozen parameter */
+    long long net_off[3];
+    long long n_params;
+    int n_nets, D, H, A, C, actor_out, bmax, head_indep;
+    /* the processed batch (flat env-major arrays) and the minibatch permutation */
+    const float *obs, *act, *logp_old, *adv, *ret, *values; /* adv/ret/values: [C][ld] */
+    long long ld;
+    const int* perm;
+    /* hyper-parameters (ppo_lag.py:86-99) */
+    float eps_clip, dual_clip, vf_coef, max_grad_norm;
+    float max_action, lagrangian, rescaling, pad0;
+    int bounded, norm_adv, value_clip, use_lagrangian;
+    double lr, beta1, beta2, adam_eps;
+} fsrl_ppo_update_t;
+
+size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax);
+int fsrl_ppo_sync_mirror(const fsrl_ppo_update_t* u, void* stream);
+/* one repeat of learn()'s inner loop: all minibatches of Batch.split(batch_size,
+ * merge_last=True) over u->perm[0..n_total); Adam step counter continues from adam_t0;
+ * statistics go to stats[stats_slot0 + i]; *n_minibatches (host) receives the count */
+int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total, int batch_size,
+                       int stats_slot0, long long adam_t0, int* n_minibatches, void* stream);
+
+/* ---- a6: batched critic / actor forward ---------------------------------------------------
+ * y[r][:] = net(x[idx ? idx[r] : r][:]) for r < n_rows.  Replaces the chunked no_grad
+ * critic passes of compute_gae_returns (fsrl/policy/base_policy.py:416-422). */
+int fsrl_mlp_forward(const fsrl_mlp3_t* net, const float* x, const int* idx, long long n_rows,
+                     float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

