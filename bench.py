@@ -1,0 +1,335 @@
+"""bench.py -- BASELINE.json's metric on its headline config.
+
+metric : env-steps/sec over collect+update (the reference's ``train_speed``,
+         fsrl/trainer/base_trainer.py:345-347)
+config : c2 = PPO-Lagrangian, SafetyCarCircle-v0, 2048 envs, 2x256 MLP, batch_size 256,
+         repeat_per_collect 4, episode_per_collect = 2048 (one 300-step episode per env and
+         collect => 614 400 transitions per step), fp32
+step   : ONE collect + update cycle (OnpolicyTrainer.train_step + policy_update_fn)
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints one JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is derived.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TASK = "SafetyCarCircle-v0"
+ENVS = 2048
+HIDDEN = (256, 256)
+BATCH = 256
+REPEAT = 4
+SEED = 10
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def build(device, rank, envs=ENVS, hidden=HIDDEN):
+    from fsrl_b200 import envs as fenvs
+    from fsrl_b200.agent import PPOLagAgent
+    from fsrl_b200.data import FastCollector, VectorReplayBuffer
+    from fsrl_b200.trainer import OnpolicyTrainer
+    from fsrl_b200.utils.logger import BaseLogger
+    demo = fenvs.make(TASK)
+    logger = BaseLogger()
+    agent = PPOLagAgent(demo, logger=logger, cost_limit=10, device=device, seed=SEED, lr=5e-4,
+                        hidden_sizes=hidden, max_grad_norm=0.5)      # cfg values (ppol_cfg.py:14-33)
+    T = demo.spec.max_episode_steps
+    train_envs = fenvs.DeviceVectorEnv(TASK, envs, device=device, seed=SEED + 1000 * rank)
+    agent.policy.set_action_seed(SEED + 7 + 1000 * rank)
+    buf = VectorReplayBuffer(envs * T, envs, device=device)
+    col = FastCollector(agent.policy, train_envs, buf, exploration_noise=True)
+    trainer = OnpolicyTrainer(agent.policy, col, None, max_epoch=1, batch_size=BATCH, cost_limit=10,
+                              step_per_epoch=envs * T, repeat_per_collect=REPEAT,
+                              episode_per_collect=envs, episode_per_test=1, logger=logger,
+                              verbose=False, show_progress=False)
+    return agent, trainer, col, buf, T
+
+
+def one_cycle(trainer):
+    stats = trainer.train_step()
+    trainer.policy_update_fn(stats)
+    return stats
+
+
+def phase_times(agent, buf, iters=200):
+    """Average duration of the dominant update kernels, CUDA events on the launching stream
+    (fsrl_ppo_phase_times in csrc/ppo.cu launches each phase kernel `iters` times back to back
+    on a real 256-row minibatch of the batch that was just trained on)."""
+    import ctypes
+    from fsrl_b200 import _lib
+    pol = agent.policy
+    idx = buf.sample_indices(0)
+    batch = pol.process_fn(None, buf, idx)
+    n = batch.n
+    perm = torch.randperm(n, device=pol.device).to(torch.int32)
+    pol._ensure_update_state(BATCH, n, 1)
+    u = pol._descriptor(batch, perm)
+    ms = (ctypes.c_float * 3)()
+    _lib.check(_lib.lib.fsrl_ppo_phase_times(ctypes.byref(u), BATCH, iters, ms, torch.cuda.current_stream().cuda_stream))
+    return [float(x) for x in ms]
+
+
+def gae_time(buf, policy, iters=20):
+    from fsrl_b200 import ops
+    n = buf.maxsize
+    v = torch.randn(2, n, device=policy.device); vn = torch.randn(2, n, device=policy.device)
+    end = (buf.terminated | buf.truncated)
+    adv = torch.empty_like(v); ret = torch.empty_like(v)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=policy.device)
+    ts = []
+    for i in range(iters + 3):
+        flush.zero_()
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record(); ops.gae_dual(v, vn, buf.rew, buf.cost, end, buf.terminated, 0.99, 0.95, out=(adv, ret)); e.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(s.elapsed_time(e))
+    return float(np.mean(ts)), n
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    agent, trainer, col, buf, T = build(device, rank)
+    if world > 1:
+        from fsrl_b200 import parallel
+        parallel.attach(agent.policy, dist)
+    steps_per_cycle = ENVS * T
+
+    for _ in range(args.warmup):
+        one_cycle(trainer)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-timed region: K collect+update cycles ---------------------------------------------
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    ev0.record()
+    collect_s = 0.0
+    for _ in range(args.steps):
+        c0 = col.collect_time
+        one_cycle(trainer)
+        collect_s += col.collect_time - c0
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall = time.time() - t_wall0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_steps = steps_per_cycle * args.steps * world
+    value = total_steps / (ms * 1e-3)
+
+    if rank != 0:
+        return
+    # ---- e2e: the same cycles through the public trainer API, wall-clock incl. every host<->device
+    # copy the API performs (minibatch permutations up, statistics down) ----------------------------
+    n_mb = (steps_per_cycle + BATCH - 1) // BATCH
+    h2d = REPEAT * steps_per_cycle * 4                           # int32 permutation per repeat
+    d2h = REPEAT * n_mb * 8 * 4 + 64                             # per-minibatch stats + collect stats
+    e2e_value = total_steps / t_wall / world * world
+    # ---- roofline of the dominant kernel + GAE ----------------------------------------------------
+    pk, how = peaks()
+    ph = phase_times(agent, buf)
+    D, A, H = 8, 2, HIDDEN[0]
+    fl_net = lambda out: 2 * BATCH * (D * H + H * H + H * out) + 2 * BATCH * (H * out + H * H)
+    flops_a = fl_net(A) + 2 * fl_net(1)
+    ach = flops_a / (ph[0] * 1e-3) / 1e12
+    gms, gn = gae_time(buf, agent.policy)
+    gae_bytes = gn * 42
+    launches = args.steps * (T * 2 + 2 + 6 + REPEAT * n_mb * 3 + 4)
+    out = {
+        "metric": "env-steps/sec (collect+update) SafetyCarCircle-v0 PPO-Lag",
+        "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2: PPO-Lagrangian SafetyCarCircle-v0, 2048 envs/GPU x 300 steps, "
+                               "2x256 MLP, batch_size 256, repeat 4, max_grad_norm 0.5 "
+                               "(analytic on-device env model, random-init weights)",
+                   "envs_per_gpu": ENVS, "transitions_per_step": steps_per_cycle * world,
+                   "parallelism": f"dp{world}",
+                   "l2": "working set per cycle (buffers 53 MB + per-minibatch gathers over 614k rows) "
+                         "cycles through > L2-size of distinct data between reuses; no explicit flush"},
+        "collect_s_per_step": collect_s / args.steps,
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "how": "wall clock around the same K trainer cycles"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "ppo_fwdbwd_kernel<256>", "bound": "tensor", "achieved": ach,
+                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                     "traffic": None, "peak_source": how + " bf16 burst",
+                     "note": "fp32 SIMT FMA kernel (no tensor cores yet); flops = fwd+bwd of 3 MLPs on a 256-row minibatch",
+                     "phase_ms": {"fwdbwd": ph[0], "wgrad": ph[1], "adam": ph[2]}},
+        "roofline_gae": {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm",
+                         "achieved": gae_bytes / (gms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": gae_bytes / (gms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gms,
+                         "bytes_per_transition": 42, "peak_source": how},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_reference(sample_envs=args.cpu_envs, cycles=1)
+    print(json.dumps(out))
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle restatement of the reference path on the host cores
+# -------------------------------------------------------------------------------------------------
+def cpu_reference(sample_envs=32, cycles=1, threads=None):
+    """The reference's CPU path (FastCollector over per-env worker processes + numba GAE +
+    eager-torch PPO update) cannot be installed here (tianshou/gymnasium/pybullet absent,
+    no network): this times its restatement in oracle/ -- numpy env twin stepped in-process
+    (no IPC: a lower bound on the reference's collect cost), C port of gae_return, torch-CPU
+    autograd + Adam -- on a bounded sample of the c2 workload: `sample_envs` envs x 300 steps,
+    2x256 MLP, batch 256, 4 repeats."""
+    import oracle.collector as ocol
+    from oracle import nets as onets, ppo as oppo
+    from oracle.envs import OracleVecEnv
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(SEED); np.random.seed(SEED)
+    D, A, T = 8, 2, 300
+    actor = onets.GaussActor(D, A, list(HIDDEN))
+    critics = [onets.ValueNet(D, list(HIDDEN)) for _ in range(2)]
+    with torch.no_grad():
+        actor.sigma_param.fill_(-0.5)
+    for m in [actor] + critics:
+        for l in m.modules():
+            if isinstance(l, torch.nn.Linear):
+                torch.nn.init.orthogonal_(l.weight); torch.nn.init.zeros_(l.bias)
+    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
+    env = OracleVecEnv(0, sample_envs, SEED); env.reset()
+    buf = ocol.OracleBuffer(sample_envs * T, sample_envs, D, A)
+    ctr = np.zeros(sample_envs, np.uint32)
+    t0 = time.time()
+    n = 0
+    for _ in range(cycles):
+        buf.reset()
+        st = ocol.collect(env, actor, sample_envs, SEED, ctr, buf)
+        idx = buf.sample_all()
+        b = {k: getattr(buf, k)[idx] for k in ("obs", "obs_next", "act", "rew", "cost", "terminated", "truncated")}
+        b = oppo.process(actor, critics, b, 0.99, 0.95)
+        oppo.learn(actor, critics, opt, b, BATCH, REPEAT, 0.0, max_grad_norm=0.5)
+        n += st["n/st"]
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_envs} envs x {T} steps x {cycles} cycle(s) of c2 (2x256 MLP, batch 256, "
+                      f"repeat 4), in-process numpy env twin (no SubprocVectorEnv IPC), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        cpu_reference(sample_envs=4, cycles=1)
+    t0 = time.time()
+    vals = []
+    for _ in range(args.steps):
+        vals.append(cpu_reference(sample_envs=args.cpu_envs, cycles=1))
+    dt = time.time() - t0
+    n = args.steps * args.cpu_envs * 300
+    v = n / dt
+    cb = dict(vals[-1]); cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec (collect+update) SafetyCarCircle-v0 PPO-Lag",
+        "value": v, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2 shapes (2x256 MLP, batch 256, repeat 4) on a bounded sample of "
+                               f"{args.cpu_envs} envs x 300 steps per step; CPU restatement of the "
+                               "reference path (oracle/), the reference itself is not installable"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-envs", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -598,3 +598,50 @@ extern "C" int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total,
     if (n_minibatches) *n_minibatches = count;
     return FSRL_OK;
 }
+
+// Measurement aid for bench.py's roofline object: average duration of each phase kernel over
+// `iters` back-to-back launches on one minibatch of u->perm (CUDA events on `stream`).  The
+// Adam phase is launched with lr = 0 so that the weights are not disturbed.
+template <int H>
+static int ppo_time_phases(const fsrl_ppo_update_t& u0, int B, int iters, float* ms, cudaStream_t s) {
+    using TT = MlpTile<H>;
+    fsrl_ppo_update_t u = u0;
+    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * H + (size_t)TT::R * DOUT_LD);
+    FSRL_CUDA(cudaFuncSetAttribute(ppo_fwdbwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    cudaEvent_t e[4];
+    for (int i = 0; i < 4; ++i) FSRL_CUDA(cudaEventCreate(&e[i]));
+    const dim3 gA((B + TT::R - 1) / TT::R, u.n_nets);
+    const dim3 gB((H / WG_TK) * (H / WG_TO) + 3, u.n_nets);
+    const int n_plain = (int)((u.n_params + 255) / 256);
+    const int n_tiles = u.n_nets * (H / 32) * (H / 32);
+    FSRL_CUDA(cudaEventRecord(e[0], s));
+    for (int i = 0; i < iters; ++i) ppo_fwdbwd_kernel<H><<<gA, MLP_TPB, smemA, s>>>(u, 0, B, 0);
+    FSRL_CUDA(cudaEventRecord(e[1], s));
+    for (int i = 0; i < iters; ++i) ppo_wgrad_kernel<H><<<gB, WG_TPB, 0, s>>>(u, 0, B);
+    FSRL_CUDA(cudaEventRecord(e[2], s));
+    for (int i = 0; i < iters; ++i)
+        adam_kernel<<<n_plain + n_tiles, 256, 0, s>>>(u, 0.1f, 0.999f, 0.001f, 1.0f, 1e-8f, 0.0f, -1, n_plain);
+    FSRL_CUDA(cudaEventRecord(e[3], s));
+    FSRL_CUDA(cudaEventSynchronize(e[3]));
+    for (int i = 0; i < 3; ++i) {
+        float t = 0.f;
+        FSRL_CUDA(cudaEventElapsedTime(&t, e[i], e[i + 1]));
+        ms[i] = t / (float)iters;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]);
+    FSRL_LAUNCH_CHECK();
+    return FSRL_OK;
+}
+
+extern "C" int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters, float* ms_out, void* stream) {
+    int rc = check_update(u);
+    if (rc) return rc;
+    FSRL_REQUIRE(ms_out && iters > 0 && B > 1 && B <= u->bmax, "fsrl_ppo_phase_times: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (u->H) {
+        case 64: return ppo_time_phases<64>(*u, B, iters, ms_out, s);
+        case 128: return ppo_time_phases<128>(*u, B, iters, ms_out, s);
+        case 256: return ppo_time_phases<256>(*u, B, iters, ms_out, s);
+        default: return ppo_time_phases<512>(*u, B, iters, ms_out, s);
+    }
+}

@@ -76,12 +76,17 @@ class FastCollector(object):
         self.env.fill(r)
         if self.buffer is not None:
             self.buffer.fill(r)
-        if random:
-            r.mode = _lib.MODE_RANDOM
+        if hasattr(self.policy, "fill_rollout"):
+            self.policy.fill_rollout(r, exploration_noise=self.exploration_noise)
+        elif not random:
+            raise TypeError("the policy does not expose fill_rollout(); only random=True "
+                            "collection is possible with it")
+        else:
+            r.actor.H = 64
             r.action_bound = {"": 0, "clip": 1, "tanh": 2}[getattr(self.policy, "action_bound_method", "clip")]
             r.action_scaling = int(getattr(self.policy, "action_scaling", True))
-        else:
-            self.policy.fill_rollout(r, exploration_noise=self.exploration_noise)
+        if random:
+            r.mode = _lib.MODE_RANDOM
         return r
 
     def collect(self, n_episode: int = 1, random: bool = False, render: bool = False,

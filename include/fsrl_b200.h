@@ -167,6 +167,9 @@ int fsrl_ppo_sync_mirror(const fsrl_ppo_update_t* u, void* stream);
  * statistics go to stats[stats_slot0 + i]; *n_minibatches (host) receives the count */
 int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total, int batch_size,
                        int stats_slot0, long long adam_t0, int* n_minibatches, void* stream);
+/* measurement aid (bench.py roofline): mean duration [ms] of the three phase kernels over
+ * `iters` launches on the first B rows of u->perm; weights are left untouched (lr = 0) */
+int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters, float* ms_out, void* stream);
 
 /* ---- a6: batched critic / actor forward ---------------------------------------------------
  * y[r][:] = net(x[idx ? idx[r] : r][:]) for r < n_rows.  Replaces the chunked no_grad

@@ -89,6 +89,8 @@ def test_env_step_bitexact_given_same_actions():
             p = np.arange(E) * buf.cap + t
             assert np.array_equal(b["obs"][p], obs), (task, t)
             a = np.clip(b["act"][p], -1, 1).astype(np.float32)
+            # map_action scaling with low=-1, high=1 (not the identity in floating point)
+            a = (np.float32(-1) + (np.float32(2) * (a + np.float32(1))) / np.float32(2)).astype(np.float32)
             obs, rew, cost, term, trunc = oenv.step(a)
             assert np.array_equal(b["rew"][p], rew) and np.array_equal(b["cost"][p], cost), (task, t)
             assert np.array_equal(b["obs_next"][p], obs)
