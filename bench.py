@@ -98,6 +98,9 @@ def build(device, rank, envs=ENVS, hidden=HIDDEN):
     T = demo.spec.max_episode_steps
     train_envs = fenvs.DeviceVectorEnv(TASK, envs, device=device, seed=SEED + 1000 * rank)
     agent.policy.set_action_seed(SEED + 7 + 1000 * rank)
+    # fixed work per step: the KL early stop (ppo_lag.py:251-255) is disabled so that EVERY step
+    # runs all `REPEAT` passes = 4 x 2400 minibatch updates (the most work the config can do)
+    agent.policy._target_kl = float("inf")
     buf = VectorReplayBuffer(envs * T, envs, device=device)
     col = FastCollector(agent.policy, train_envs, buf, exploration_noise=True)
     trainer = OnpolicyTrainer(agent.policy, col, None, max_epoch=1, batch_size=BATCH, cost_limit=10,
@@ -113,13 +116,14 @@ def one_cycle(trainer):
     return stats
 
 
-def phase_times(agent, buf, iters=200):
+def phase_times(agent, col, buf, iters=200):
     """Average duration of the dominant update kernels, CUDA events on the launching stream
     (fsrl_ppo_phase_times in csrc/ppo.cu launches each phase kernel `iters` times back to back
     on a real 256-row minibatch of the batch that was just trained on)."""
     import ctypes
     from fsrl_b200 import _lib
     pol = agent.policy
+    col.collect(ENVS)                      # the trainer resets the buffer after every update
     idx = buf.sample_indices(0)
     batch = pol.process_fn(None, buf, idx)
     n = batch.n
@@ -208,7 +212,7 @@ def run_ours(args):
     e2e_value = total_steps / t_wall / world * world
     # ---- roofline of the dominant kernel + GAE ----------------------------------------------------
     pk, how = peaks()
-    ph = phase_times(agent, buf)
+    ph = phase_times(agent, col, buf)
     D, A, H = 8, 2, HIDDEN[0]
     fl_net = lambda out: 2 * BATCH * (D * H + H * H + H * out) + 2 * BATCH * (H * out + H * H)
     flops_a = fl_net(A) + 2 * fl_net(1)
@@ -226,6 +230,7 @@ def run_ours(args):
                                "(analytic on-device env model, random-init weights)",
                    "envs_per_gpu": ENVS, "transitions_per_step": steps_per_cycle * world,
                    "parallelism": f"dp{world}",
+                   "kl_early_stop": "disabled (fixed work: 4 repeats x 2400 minibatch updates per step)",
                    "l2": "working set per cycle (buffers 53 MB + per-minibatch gathers over 614k rows) "
                          "cycles through > L2-size of distinct data between reuses; no explicit flush"},
         "collect_s_per_step": collect_s / args.steps,
@@ -261,7 +266,7 @@ def cpu_reference(sample_envs=32, cycles=1, threads=None):
     import oracle.collector as ocol
     from oracle import nets as onets, ppo as oppo
     from oracle.envs import OracleVecEnv
-    threads = threads or os.cpu_count()
+    threads = threads or best_thread_count()
     torch.set_num_threads(threads)
     torch.manual_seed(SEED); np.random.seed(SEED)
     D, A, T = 8, 2, 300
@@ -285,12 +290,41 @@ def cpu_reference(sample_envs=32, cycles=1, threads=None):
         idx = buf.sample_all()
         b = {k: getattr(buf, k)[idx] for k in ("obs", "obs_next", "act", "rew", "cost", "terminated", "truncated")}
         b = oppo.process(actor, critics, b, 0.99, 0.95)
-        oppo.learn(actor, critics, opt, b, BATCH, REPEAT, 0.0, max_grad_norm=0.5)
+        oppo.learn(actor, critics, opt, b, BATCH, REPEAT, 0.0, max_grad_norm=0.5, target_kl=float("inf"))
         n += st["n/st"]
     dt = time.time() - t0
     return {"value": n / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
             "sample": f"{sample_envs} envs x {T} steps x {cycles} cycle(s) of c2 (2x256 MLP, batch 256, "
                       f"repeat 4), in-process numpy env twin (no SubprocVectorEnv IPC), {dt:.1f} s"}
+
+
+_BEST_THREADS = None
+
+
+def best_thread_count():
+    """The reference defaults to torch.set_num_threads(4) (ppol_cfg.py:11); tiny 2x256 MLPs do
+    not scale with cores, so pick the fastest of {4, 8, 16, all} on a short calibration."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    lin = torch.nn.Sequential(torch.nn.Linear(8, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256),
+                              torch.nn.ReLU(), torch.nn.Linear(256, 1))
+    x = torch.randn(256, 8)
+    best, best_t = 4, 1e9
+    for th in sorted({4, 8, 16, os.cpu_count() or 4}):
+        if th > (os.cpu_count() or 4):
+            continue
+        torch.set_num_threads(th)
+        for _ in range(3):
+            lin(x).sum().backward()
+        t0 = time.time()
+        for _ in range(30):
+            lin(x).sum().backward()
+        dt = time.time() - t0
+        if dt < best_t:
+            best, best_t = th, dt
+    _BEST_THREADS = best
+    return best
 
 
 def run_reference(args):

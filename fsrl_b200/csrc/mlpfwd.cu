@@ -48,8 +48,9 @@ using namespace fsrl;
 
 extern "C" int fsrl_mlp_forward(const fsrl_mlp3_t* net, const float* x, const int* idx,
                                 long long n_rows, float* y, void* stream) {
-    FSRL_REQUIRE(net && x && y, "fsrl_mlp_forward: null pointer");
     FSRL_REQUIRE(n_rows >= 0, "fsrl_mlp_forward: n_rows < 0");
+    if (n_rows == 0) return FSRL_OK;
+    FSRL_REQUIRE(net && x && y, "fsrl_mlp_forward: null pointer");
     FSRL_REQUIRE(net->out >= 1 && net->out <= MLP_MAX_OUT, "fsrl_mlp_forward: out dim %d unsupported", net->out);
     if (n_rows == 0) return FSRL_OK;
     const Mlp3 m = *reinterpret_cast<const Mlp3*>(net);

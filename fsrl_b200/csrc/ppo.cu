@@ -307,42 +307,62 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
     return red[0] + red[1] + red[2] + red[3];
 }
 
+// Roles by blockIdx.x (per net):  [0, NT) dW2t tiles (32 k x 64 o; k-tile 0 also emits db2)
+//                                 [NT, NT+NTO) layer 1: dW1t[:, o-tile], db1[o-tile]
+//                                 [NT+NTO, NT+2*NTO) layer 3: dW3t[k-tile, :] (+ db3, dlog_sigma)
+// Every role streams the minibatch in chunks of 32 rows: the next chunk is prefetched into
+// registers while the current one is consumed from shared memory.
 template <int H>
 __global__ void __launch_bounds__(WG_TPB)
 ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     constexpr int NTK = H / WG_TK, NTO = H / WG_TO, NT = NTK * NTO;
-    __shared__ __align__(16) float sL[WG_RC][WG_TK];
-    __shared__ __align__(16) float sG[WG_RC][WG_TO];
+    __shared__ __align__(16) float sL[WG_RC][WG_TO];     // left operand chunk (<= 64 cols)
+    __shared__ __align__(16) float sG[WG_RC][WG_TO];     // right operand chunk
     __shared__ float s_red[4];
     const int tid = threadIdx.x;
     const int net = blockIdx.y;
     const NetView nv = net_view(u, net);
     const int bx = blockIdx.x;
+    const int nchunk = (B + WG_RC - 1) / WG_RC;
     float sq = 0.f;
     if (bx < NT) {
         // ---- dW2t[k][o] = sum_r h1[r][k] * dz2[r][o] : 32 x 64 tile, 4 x 4 per thread ----------
         const int k0 = (bx / NTO) * WG_TK, o0 = (bx % NTO) * WG_TO;
         const int tk = tid / 16, to = tid % 16;
+        const bool do_bias = (k0 == 0);
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-        for (int rb = 0; rb < B; rb += WG_RC) {
-            // stage 32 rows: L 32x32 (2 float4 / thread), G 32x64 (4 float4 / thread)
+        float bsum = 0.f;                                  // db2 column sum (threads < 64)
+        float4 pl[2], pg[4];
+        auto prefetch = [&](int rb) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int f = tid + q * WG_TPB, rr = f / 8, cc = (f % 8) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rb + rr < B) v = *reinterpret_cast<const float4*>(nv.s_h1 + (size_t)(rb + rr) * H + k0 + cc);
-                *reinterpret_cast<float4*>(&sL[rr][cc]) = v;
+                pl[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_h1 + (size_t)(rb + rr) * H + k0 + cc))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rb + rr < B) v = *reinterpret_cast<const float4*>(nv.s_dz2 + (size_t)(rb + rr) * H + o0 + cc);
-                *reinterpret_cast<float4*>(&sG[rr][cc]) = v;
+                pg[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_dz2 + (size_t)(rb + rr) * H + o0 + cc))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        prefetch(0);
+        for (int ch = 0; ch < nchunk; ++ch) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int f = tid + q * WG_TPB, rr = f / 8, cc = (f % 8) * 4;
+                *reinterpret_cast<float4*>(&sL[rr][cc]) = pl[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
+                *reinterpret_cast<float4*>(&sG[rr][cc]) = pg[q];
             }
             __syncthreads();
+            if (ch + 1 < nchunk) prefetch((ch + 1) * WG_RC);
 #pragma unroll 8
             for (int rr = 0; rr < WG_RC; ++rr) {
                 const float4 l = *reinterpret_cast<const float4*>(&sL[rr][4 * tk]);
@@ -356,6 +376,10 @@ ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
                 acc[3][0] = fmaf(l.w, g.x, acc[3][0]); acc[3][1] = fmaf(l.w, g.y, acc[3][1]);
                 acc[3][2] = fmaf(l.w, g.z, acc[3][2]); acc[3][3] = fmaf(l.w, g.w, acc[3][3]);
             }
+            if (do_bias && tid < WG_TO) {
+#pragma unroll 8
+                for (int rr = 0; rr < WG_RC; ++rr) bsum += sG[rr][tid];
+            }
             __syncthreads();
         }
 #pragma unroll
@@ -364,63 +388,120 @@ ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
                 make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
             sq += acc[i][0] * acc[i][0] + acc[i][1] * acc[i][1] + acc[i][2] * acc[i][2] + acc[i][3] * acc[i][3];
         }
-    } else if (bx == NT) {
+        if (do_bias && tid < WG_TO) { nv.g_b2[o0 + tid] = bsum; sq += bsum * bsum; }
+    } else if (bx < NT + NTO) {
         // ---- layer 1: dW1t[d][o] = sum_r x[r][d] * dz1[r][o];  db1[o] = sum_r dz1[r][o] ---------
         const int D = u.D;
+        const int o0 = (bx - NT) * WG_TO;
         const int* perm = u.perm + mb_off;
-        for (int o = tid; o < H; o += WG_TPB) {
-            float b = 0.f;
-            for (int d0 = 0; d0 < D; d0 += 8) {
-                float acc[8];
+        const int o = tid % WG_TO, dg = tid / WG_TO;        // 2 d-groups of 8 per pass
+        for (int d0 = 0; d0 < D; d0 += 16) {
+            float acc[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-                float bb = 0.f;
-                for (int r = 0; r < B; ++r) {
-                    const float g = nv.s_dz1[(size_t)r * H + o];
-                    const float* x = u.obs + (size_t)perm[r] * D + d0;
-                    bb += g;
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            float bsum = 0.f;
+            float4 pg[4];
+            float px[4];
+            auto prefetch = [&](int rb) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (d0 + q < D) acc[q] = fmaf(__ldg(x + q), g, acc[q]);
+                for (int q = 0; q < 4; ++q) {
+                    const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
+                    pg[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_dz1 + (size_t)(rb + rr) * H + o0 + cc))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                b = bb;
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (d0 + q < D) { nv.g_w1t[(size_t)(d0 + q) * H + o] = acc[q]; sq += acc[q] * acc[q]; }
+                for (int q = 0; q < 4; ++q) {       // x chunk: 32 rows x 16 d  = 512 values
+                    const int f = tid + q * WG_TPB, rr = f / 16, dd = d0 + (f % 16);
+                    px[q] = (rb + rr < B && dd < D) ? __ldg(u.obs + (size_t)perm[rb + rr] * D + dd) : 0.f;
+                }
+            };
+            prefetch(0);
+            for (int ch = 0; ch < nchunk; ++ch) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int f = tid + q * WG_TPB;
+                    *reinterpret_cast<float4*>(&sG[f / 16][(f % 16) * 4]) = pg[q];
+                    sL[f / 16][f % 16] = px[q];
+                }
+                __syncthreads();
+                if (ch + 1 < nchunk) prefetch((ch + 1) * WG_RC);
+#pragma unroll 8
+                for (int rr = 0; rr < WG_RC; ++rr) {
+                    const float g = sG[rr][o];
+                    const float4 xa4 = *reinterpret_cast<const float4*>(&sL[rr][8 * dg]);
+                    const float4 xb4 = *reinterpret_cast<const float4*>(&sL[rr][8 * dg + 4]);
+                    acc[0] = fmaf(xa4.x, g, acc[0]); acc[1] = fmaf(xa4.y, g, acc[1]);
+                    acc[2] = fmaf(xa4.z, g, acc[2]); acc[3] = fmaf(xa4.w, g, acc[3]);
+                    acc[4] = fmaf(xb4.x, g, acc[4]); acc[5] = fmaf(xb4.y, g, acc[5]);
+                    acc[6] = fmaf(xb4.z, g, acc[6]); acc[7] = fmaf(xb4.w, g, acc[7]);
+                    bsum += g;
+                }
+                __syncthreads();
             }
-            nv.g_b1[o] = b; sq += b * b;
-        }
-    } else if (bx == NT + 1) {
-        // ---- db2[o] = sum_r dz2[r][o] ---------------------------------------------------------------
-        for (int o = tid; o < H; o += WG_TPB) {
-            float b = 0.f;
-            for (int r = 0; r < B; ++r) b += nv.s_dz2[(size_t)r * H + o];
-            nv.g_b2[o] = b; sq += b * b;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int d = d0 + 8 * dg + q;
+                if (d < D) { nv.g_w1t[(size_t)d * H + o0 + o] = acc[q]; sq += acc[q] * acc[q]; }
+            }
+            if (d0 == 0 && dg == 0) { nv.g_b1[o0 + o] = bsum; sq += bsum * bsum; }
         }
     } else {
         // ---- layer 3: dW3t[k][j] = sum_r h2[r][k] * dout[r][j];  db3;  dlog_sigma ------------------
         const int out = nv.m.out;
         const int A = u.A;
-        for (int k = tid; k < H; k += WG_TPB) {
-            float acc[MLP_MAX_OUT];
+        const int k0 = (bx - NT - NTO) * WG_TO;
+        const int k = tid % WG_TO, jg = tid / WG_TO;         // j = 8*jg + q
+        float acc[8];
 #pragma unroll
-            for (int j = 0; j < MLP_MAX_OUT; ++j) acc[j] = 0.f;
-            for (int r = 0; r < B; ++r) {
-                const float h = nv.s_h2[(size_t)r * H + k];
-                const float* g = nv.s_dout + (size_t)r * DOUT_LD;
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        float csum = 0.f;                                     // column sum of dout (threads < 16)
+        float4 pg[4];
+        float4 pd;
+        auto prefetch = [&](int rb) {
 #pragma unroll
-                for (int j = 0; j < MLP_MAX_OUT; ++j)
-                    if (j < out) acc[j] = fmaf(h, __ldg(g + j), acc[j]);
+            for (int q = 0; q < 4; ++q) {
+                const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
+                pg[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_h2 + (size_t)(rb + rr) * H + k0 + cc))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            const int rr = tid / 4, cc = (tid % 4) * 4;      // dout chunk: 32 rows x 16
+            pd = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_dout + (size_t)(rb + rr) * DOUT_LD + cc))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        prefetch(0);
+        for (int ch = 0; ch < nchunk; ++ch) {
 #pragma unroll
-            for (int j = 0; j < MLP_MAX_OUT; ++j)
-                if (j < out) { nv.g_w3t[(size_t)k * out + j] = acc[j]; sq += acc[j] * acc[j]; }
+            for (int q = 0; q < 4; ++q) {
+                const int f = tid + q * WG_TPB;
+                *reinterpret_cast<float4*>(&sG[f / 16][(f % 16) * 4]) = pg[q];
+            }
+            *reinterpret_cast<float4*>(&sL[tid / 4][(tid % 4) * 4]) = pd;
+            __syncthreads();
+            if (ch + 1 < nchunk) prefetch((ch + 1) * WG_RC);
+#pragma unroll 8
+            for (int rr = 0; rr < WG_RC; ++rr) {
+                const float h = sG[rr][k];
+                const float4 da = *reinterpret_cast<const float4*>(&sL[rr][8 * jg]);
+                const float4 db = *reinterpret_cast<const float4*>(&sL[rr][8 * jg + 4]);
+                acc[0] = fmaf(h, da.x, acc[0]); acc[1] = fmaf(h, da.y, acc[1]);
+                acc[2] = fmaf(h, da.z, acc[2]); acc[3] = fmaf(h, da.w, acc[3]);
+                acc[4] = fmaf(h, db.x, acc[4]); acc[5] = fmaf(h, db.y, acc[5]);
+                acc[6] = fmaf(h, db.z, acc[6]); acc[7] = fmaf(h, db.w, acc[7]);
+            }
+            if (k0 == 0 && tid < DOUT_LD) {
+#pragma unroll 8
+                for (int rr = 0; rr < WG_RC; ++rr) csum += sL[rr][tid];
+            }
+            __syncthreads();
         }
-        if (tid < DOUT_LD) {
-            float s = 0.f;
-            for (int r = 0; r < B; ++r) s += nv.s_dout[(size_t)r * DOUT_LD + tid];
-            if (tid < out) { nv.g_b3[tid] = s; sq += s * s; }
-            else if (net == 0 && u.head_indep && tid >= A && tid < 2 * A) { nv.g_log_sigma[tid - A] = s; sq += s * s; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = 8 * jg + q;
+            if (j < out) { nv.g_w3t[(size_t)(k0 + k) * out + j] = acc[q]; sq += acc[q] * acc[q]; }
+        }
+        if (k0 == 0 && tid < DOUT_LD) {
+            if (tid < out) { nv.g_b3[tid] = csum; sq += csum * csum; }
+            else if (net == 0 && u.head_indep && tid >= A && tid < 2 * A) { nv.g_log_sigma[tid - A] = csum; sq += csum * csum; }
         }
     }
     const float tot = block_sum_128(sq, s_red);
@@ -508,7 +589,7 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
     const dim3 gA((B + TT::R - 1) / TT::R, u.n_nets);
     ppo_fwdbwd_kernel<H><<<gA, MLP_TPB, smemA, s>>>(u, mb_off, B, slot);
     FSRL_LAUNCH_CHECK();
-    const dim3 gB((H / WG_TK) * (H / WG_TO) + 3, u.n_nets);
+    const dim3 gB((H / WG_TK) * (H / WG_TO) + 2 * (H / WG_TO), u.n_nets);
     ppo_wgrad_kernel<H><<<gB, WG_TPB, 0, s>>>(u, mb_off, B);
     FSRL_LAUNCH_CHECK();
     // torch.optim.Adam scalars (python doubles -> f32 at the op)
@@ -611,7 +692,7 @@ static int ppo_time_phases(const fsrl_ppo_update_t& u0, int B, int iters, float*
     cudaEvent_t e[4];
     for (int i = 0; i < 4; ++i) FSRL_CUDA(cudaEventCreate(&e[i]));
     const dim3 gA((B + TT::R - 1) / TT::R, u.n_nets);
-    const dim3 gB((H / WG_TK) * (H / WG_TO) + 3, u.n_nets);
+    const dim3 gB((H / WG_TK) * (H / WG_TO) + 2 * (H / WG_TO), u.n_nets);
     const int n_plain = (int)((u.n_params + 255) / 256);
     const int n_tiles = u.n_nets * (H / 32) * (H / 32);
     FSRL_CUDA(cudaEventRecord(e[0], s));

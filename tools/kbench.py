@@ -55,12 +55,20 @@ def bench_gae(envs, T):
                       "alg_bytes": alg_bytes, "GBps": gbs, "frac_of_%s_hbm" % how: gbs / pk["hbm_gbs"]}))
 
 
+def bench_ppo(iters):
+    import bench
+    agent, trainer, col, buf, T = bench.build("cuda:0", 0)
+    print(json.dumps({"phase_ms(fwdbwd,wgrad,adam)": bench.phase_times(agent, col, buf, iters=iters)}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what")
     ap.add_argument("--envs", type=int, default=2048)
     ap.add_argument("--T", type=int, default=300)
     a = ap.parse_args()
+    if a.what == "ppo":
+        bench_ppo(a.T if a.T != 300 else 50)
     if a.what == "gae":
         bench_gae(a.envs, a.T)
         bench_gae(a.envs * 16, a.T)
