@@ -109,6 +109,7 @@ SIGNATURES = {
     "fsrl_mlp_forward": (c_int, [ctypes.POINTER(Mlp3), c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),
     "fsrl_ppo_scratch_floats": (c_size, [c_int, c_int, c_int]),
     "fsrl_ppo_sync_mirror": (c_int, [ctypes.POINTER(PpoUpdate), c_vp]),
+    "fsrl_debug_clocks": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "fsrl_ppo_phase_times": (c_int, [ctypes.POINTER(PpoUpdate), c_int, c_int, ctypes.POINTER(c_f32), c_vp]),
     "fsrl_ppo_lag_epoch": (c_int, [ctypes.POINTER(PpoUpdate), ctypes.c_longlong, c_int, c_int,
                                    ctypes.c_longlong, ctypes.POINTER(c_int), c_vp]),

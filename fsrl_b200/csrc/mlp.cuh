@@ -1,18 +1,27 @@
-// Fused 2-hidden-layer MLP forward for a tile of rows, shared by the rollout step, the critic
-// evaluation before GAE, log-prob evaluation and the CPO line search.
+// Fused 2-hidden-layer MLP forward/backward building blocks for a tile of rows, shared by the
+// rollout step, the critic evaluation before GAE, the PPO/CPO/SAC update kernels.
 //
 // Replaces the tianshou Net/MLP/ActorProb/Critic forward the reference calls at
 // fsrl/policy/base_policy.py:178 (actor) and :421-422 (critics): h = ReLU(W2 ReLU(W1 x)).
 //
 // Canonical parameter layout (all kernels): every Linear is stored TRANSPOSED, Wt[in][out]
-// row-major, so that a warp reading one k-row of the weight touches contiguous memory
-// (coalesced global loads, conflict-free LDS.128).  torch sees `.weight` as the strided view
-// Wt.t().
+// row-major, so a k-row of the weight is contiguous (coalesced cp.async, conflict-free LDS).
+// torch sees `.weight` as the strided view Wt.t().
 //
-// Thread mapping (256 threads): a CTA owns R = 4096/H rows; thread (tr, to) accumulates a
-// 4x4 register tile (rows 4tr..4tr+3, cols 4to..4to+3).  Layer-2 weights stream through a
-// cp.async double-buffered shared-memory stage of KC k-rows; activations stay in shared
-// memory between layers.
+// GEMMs run on the tensor cores with fp32-faithful "3xTF32" arithmetic: every fp32 operand is
+// split into hi = tf32(x), lo = tf32(x - hi) and the product is accumulated as
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi in fp32 (mma.sync.m16n8k8.tf32), i.e. ~2^-21 relative
+// error per product -- indistinguishable from an fp32 FMA chain at the parity tolerances.
+// The row tiles here are 16..64 rows (a 256-row minibatch split over 16 CTAs), far below the
+// 128-row atoms of tcgen05, and the kernels are latency- not throughput-bound, so the
+// warp-level mma path is the right tensor-core granularity for this workload.
+//
+// Thread mapping (256 threads = 8 warps): a CTA owns R rows (R = 4096/H, at least 16); warp w
+// owns output columns [w*H/8, (w+1)*H/8) for all R rows: MT = R/16 m-tiles x NT = H/64
+// n-tiles of m16n8 accumulators.  Weights stream through a cp.async double-buffered
+// shared-memory stage of KC k-rows (row stride H+8 floats: conflict-free B fragments);
+// activations stay in shared memory between layers (row stride H+4: conflict-free A
+// fragments).
 #pragma once
 #include "common.cuh"
 #include <cuda_pipeline.h>
@@ -30,64 +39,114 @@ struct Mlp3 {            // device pointers, canonical layout
 };
 
 constexpr int MLP_TPB = 256;
-constexpr int MLP_KC = 16;          // k-rows of W2t per pipeline stage
+constexpr int MLP_KC = 16;          // k-rows of a weight matrix per pipeline stage
+constexpr int MLP_NST = 4;          // pipeline stages in flight (L2 latency x bandwidth ~ 64 KB per SM)
 constexpr int MLP_MAX_OUT = 16;
+constexpr int MLP_MAX_IN = 64;
 
 template <int H>
 struct MlpTile {
     static_assert(H == 64 || H == 128 || H == 256 || H == 512, "hidden width must be 64/128/256/512");
-    static constexpr int R = 4096 / H;          // rows per CTA
-    static constexpr int TO = H / 4;            // column groups
-    static constexpr int PARTS = MLP_TPB / R;   // lanes cooperating on one row in layer 3
-    // shared memory (floats): x[R][in_pad] | h1[R][H] | h2[R][H] | wstage[2][KC][H]
-    __host__ __device__ static constexpr int in_pad(int in) { return (in + 3) & ~3; }
-    __host__ __device__ static constexpr size_t smem_bytes(int in) {
-        return sizeof(float) * ((size_t)R * in_pad(in) + 2 * (size_t)R * H + 2 * (size_t)MLP_KC * H);
+    static constexpr int R = (4096 / H) < 16 ? 16 : (4096 / H);   // rows per CTA
+    static constexpr int MT = R / 16;           // m-tiles per warp
+    static constexpr int WN = H / 8;            // columns per warp
+    static constexpr int NT = WN / 8;           // n-tiles per warp
+    static constexpr int LDA = H + 4;           // activation row stride (floats)
+    static constexpr int LDW = H + 8;           // staged weight row stride (floats)
+    static constexpr int PARTS = MLP_TPB / R;   // lanes cooperating on one row in the head
+    static constexpr int NST = (H >= 512) ? 2 : MLP_NST;   // weight pipeline depth (smem budget)
+    __host__ __device__ static constexpr int in_pad(int in) { return ((in + 7) & ~7) + 4; }
+    __host__ __device__ static constexpr int stage_floats() { return NST * MLP_KC * LDW; }
+    // x[R][in_pad] | h1[R][LDA] | h2[R][LDA] | wstage[2][KC][LDW] | w3s[H][out]
+    __host__ __device__ static constexpr size_t smem_floats(int in, int out) {
+        return (size_t)R * in_pad(in) + 2 * (size_t)R * LDA + stage_floats() + (size_t)H * out;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(int in, int out = MLP_MAX_OUT) {
+        return sizeof(float) * smem_floats(in, out);
     }
 };
 
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
 
-// cp.async one KC x H stage of a row-major [H][H] matrix into buffer `buf` of wst
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// cp.async rows [chunk*KC, chunk*KC+KC) of a row-major [K][H] matrix into stage buffer `buf`;
+// rows >= K are zero-filled (layer 1 pads K up to a multiple of 8)
 template <int H>
-__device__ __forceinline__ void stage_load_hh(const float* mat, float* wst, int chunk, int buf) {
-    const float* src = mat + (size_t)chunk * MLP_KC * H;
-    float* dst = wst + (size_t)buf * MLP_KC * H;
-    for (int i = threadIdx.x * 4; i < MLP_KC * H; i += MLP_TPB * 4)
-        __pipeline_memcpy_async(dst + i, src + i, 16);
+__device__ __forceinline__ void stage_load(const float* mat, int K, float* wst, int chunk, int buf) {
+    using TT = MlpTile<H>;
+    float* dst = wst + (size_t)buf * MLP_KC * TT::LDW;
+    constexpr int SEG = H / 4;                      // 16-byte segments per row
+    for (int i = threadIdx.x; i < MLP_KC * SEG; i += MLP_TPB) {
+        const int rr = i / SEG, sg = i % SEG;
+        const int k = chunk * MLP_KC + rr;
+        float* d = dst + (size_t)rr * TT::LDW + 4 * sg;
+        if (k < K) __pipeline_memcpy_async(d, mat + (size_t)k * H + 4 * sg, 16);
+        else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __pipeline_commit();
 }
 
-// acc[4][4] += src[4tr+i][k] * mat[k][4to+j] over k in [0, H): `src` is a row-major [R][H]
-// shared-memory tile, `mat` a row-major [H][H] global matrix streamed through `wst`.
-// If stage0_in_flight the caller already issued stage_load_hh(mat, wst, 0, 0).
-// All threads must call; contains __syncthreads.
+// c[mt][nt] += A[16mt.., k] * W[k][warp cols] for k in [0, Kp): A is a shared-memory tile
+// (row stride lda, Kp a multiple of 8), W a row-major [K][H] global matrix streamed through
+// `wst`.  All threads must call; contains __syncthreads (the first one also orders the
+// caller's earlier shared-memory stores to A).
 template <int H>
-__device__ __forceinline__ void tile_gemm_hh(float (&acc)[4][4], const float* src, const float* mat,
-                                             float* wst, bool stage0_in_flight) {
+__device__ __forceinline__ void tc_gemm(float (&c)[MlpTile<H>::MT][MlpTile<H>::NT][4], const float* A,
+                                        int lda, int K, const float* W, float* wst,
+                                        bool stage0_in_flight) {
     using TT = MlpTile<H>;
-    const int tid = threadIdx.x;
-    const int to = tid % TT::TO, tr = tid / TT::TO;
-    if (!stage0_in_flight) stage_load_hh<H>(mat, wst, 0, 0);
-    constexpr int NCH = H / MLP_KC;
-    for (int ch = 0; ch < NCH; ++ch) {
-        if (ch + 1 < NCH) stage_load_hh<H>(mat, wst, ch + 1, (ch + 1) & 1);
-        if (ch + 1 < NCH) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-        __syncthreads();   // stage ch visible to all; also orders earlier smem stores of `src`
-        const float* w = wst + (size_t)(ch & 1) * MLP_KC * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int n0 = warp * TT::WN;
+    const int Kp = (K + 7) & ~7;
+    const int nch = (Kp + MLP_KC - 1) / MLP_KC;
+    // prologue: stages 0 .. NST-2 in flight (one commit group per stage, empty groups keep the
+    // wait_prior arithmetic uniform)
+    for (int p = stage0_in_flight ? 1 : 0; p < TT::NST - 1; ++p) {
+        if (p < nch) stage_load<H>(W, K, wst, p, p);
+        else __pipeline_commit();
+    }
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + TT::NST - 1 < nch) stage_load<H>(W, K, wst, ch + TT::NST - 1, (ch + TT::NST - 1) % TT::NST);
+        else __pipeline_commit();
+        __pipeline_wait_prior(TT::NST - 1);
+        __syncthreads();
+        const float* w = wst + (size_t)(ch % TT::NST) * MLP_KC * TT::LDW;
+        const int kleft = Kp - ch * MLP_KC;
 #pragma unroll
-        for (int kk = 0; kk < MLP_KC; kk += 4) {
-            float4 hv[4];
+        for (int ks = 0; ks < MLP_KC; ks += 8) {
+            if (ks < kleft) {
+                const int k0 = ch * MLP_KC + ks;
+                uint32_t bh[TT::NT][2], bl[TT::NT][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                hv[i] = *reinterpret_cast<const float4*>(src + (size_t)(4 * tr + i) * H + ch * MLP_KC + kk);
+                for (int nt = 0; nt < TT::NT; ++nt) {
+                    split_tf32(w[(size_t)(ks + t) * TT::LDW + n0 + 8 * nt + g], bh[nt][0], bl[nt][0]);
+                    split_tf32(w[(size_t)(ks + t + 4) * TT::LDW + n0 + 8 * nt + g], bh[nt][1], bl[nt][1]);
+                }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 wv = *reinterpret_cast<const float4*>(w + (size_t)(kk + q) * H + 4 * to);
+                for (int mt = 0; mt < TT::MT; ++mt) {
+                    uint32_t ah[4], al[4];
+                    const float* a = A + (size_t)(16 * mt + g) * lda + k0 + t;
+                    split_tf32(a[0], ah[0], al[0]);
+                    split_tf32(a[(size_t)8 * lda], ah[1], al[1]);
+                    split_tf32(a[4], ah[2], al[2]);
+                    split_tf32(a[(size_t)8 * lda + 4], ah[3], al[3]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float x = (q == 0) ? hv[i].x : (q == 1) ? hv[i].y : (q == 2) ? hv[i].z : hv[i].w;
-                    acc[i][0] = fmaf(x, wv.x, acc[i][0]); acc[i][1] = fmaf(x, wv.y, acc[i][1]);
-                    acc[i][2] = fmaf(x, wv.z, acc[i][2]); acc[i][3] = fmaf(x, wv.w, acc[i][3]);
+                    for (int nt = 0; nt < TT::NT; ++nt) {
+                        mma_tf32(c[mt][nt], al, bh[nt]);
+                        mma_tf32(c[mt][nt], ah, bl[nt]);
+                        mma_tf32(c[mt][nt], ah, bh[nt]);
+                    }
                 }
             }
         }
@@ -95,77 +154,114 @@ __device__ __forceinline__ void tile_gemm_hh(float (&acc)[4][4], const float* sr
     }
 }
 
-// Computes h2 = ReLU(W2 ReLU(W1 x + b1) + b2) for the R rows already staged in xs (row-major,
-// stride in_pad).  On return h2 (row-major [R][H]) is valid in shared memory for all threads.
-template <int H>
-__device__ __forceinline__ void mlp_hidden_forward(const Mlp3& m, const float* xs, float* h1,
-                                                   float* h2, float* wst) {
+// visit every accumulator pair of this thread: f(row, col, v0, v1) with (row, col), (row, col+1)
+template <int H, class F>
+__device__ __forceinline__ void tc_foreach(float (&c)[MlpTile<H>::MT][MlpTile<H>::NT][4], F f) {
     using TT = MlpTile<H>;
-    const int tid = threadIdx.x;
-    const int to = tid % TT::TO, tr = tid / TT::TO;
-    const int inp = TT::in_pad(m.in);
-
-    // prefetch stage 0 of W2t while layer 1 runs
-    stage_load_hh<H>(m.w2t, wst, 0, 0);
-
-    // ---- layer 1: in -> H (weights straight from L2 through the read-only path) ----------
-    float acc[4][4];
-    {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(m.b1 + 4 * to));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w; }
-        for (int k = 0; k < m.in; ++k) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(m.w1t + (size_t)k * H + 4 * to));
+    for (int mt = 0; mt < TT::MT; ++mt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float x = xs[(4 * tr + i) * inp + k];
-                acc[i][0] = fmaf(x, w.x, acc[i][0]); acc[i][1] = fmaf(x, w.y, acc[i][1]);
-                acc[i][2] = fmaf(x, w.z, acc[i][2]); acc[i][3] = fmaf(x, w.w, acc[i][3]);
-            }
+        for (int nt = 0; nt < TT::NT; ++nt) {
+            const int col = warp * TT::WN + 8 * nt + 2 * t;
+            f(16 * mt + g, col, c[mt][nt][0], c[mt][nt][1]);
+            f(16 * mt + g + 8, col, c[mt][nt][2], c[mt][nt][3]);
         }
+}
+
+template <int H>
+__device__ __forceinline__ void tc_init_bias(float (&c)[MlpTile<H>::MT][MlpTile<H>::NT][4], const float* bias) {
+    using TT = MlpTile<H>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(h1 + (size_t)(4 * tr + i) * H + 4 * to) =
-                make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+    for (int nt = 0; nt < TT::NT; ++nt) {
+        const int col = warp * TT::WN + 8 * nt + 2 * t;
+        const float b0 = bias ? __ldg(bias + col) : 0.f, b1 = bias ? __ldg(bias + col + 1) : 0.f;
+#pragma unroll
+        for (int mt = 0; mt < TT::MT; ++mt) { c[mt][nt][0] = b0; c[mt][nt][1] = b1; c[mt][nt][2] = b0; c[mt][nt][3] = b1; }
     }
-    // ---- layer 2: H -> H, W2t streamed through the double-buffered stage --------------------
-    {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(m.b2 + 4 * to));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w; }
+}
+
+// Shared-memory carve-up used by every kernel built on these blocks
+template <int H>
+struct MlpSmem {
+    float *x, *h1, *h2, *wst, *w3s;
+    __device__ MlpSmem(float* base, int in, int out) {
+        using TT = MlpTile<H>;
+        x = base;
+        h1 = x + (size_t)TT::R * TT::in_pad(in);
+        h2 = h1 + (size_t)TT::R * TT::LDA;
+        wst = h2 + (size_t)TT::R * TT::LDA;
+        w3s = wst + TT::stage_floats();
+        (void)out;
     }
-    tile_gemm_hh<H>(acc, h1, m.w2t, wst, /*stage0_in_flight=*/true);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(h2 + (size_t)(4 * tr + i) * H + 4 * to) =
-            make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+    __device__ float* end(int out) const { return w3s + (size_t)H * out; }
+};
+
+// Computes h1 = ReLU(W1 x + b1), h2 = ReLU(W2 h1 + b2) for the R rows staged in s.x (row
+// stride in_pad, columns >= in zero).  Also stages W3t into s.w3s.  On return h1/h2 (row
+// stride LDA) are valid in shared memory for all threads.
+template <int H>
+__device__ __forceinline__ void mlp_hidden_forward(const Mlp3& m, const MlpSmem<H>& s) {
+    using TT = MlpTile<H>;
+    const int inp = TT::in_pad(m.in);
+    // head weights -> smem (tiny), then stage 0 of W1t; both overlap with nothing yet, but keep
+    // the head copy out of the GEMM pipelines' group accounting by finishing it first
+    for (int i = threadIdx.x; i < H * m.out; i += MLP_TPB) s.w3s[i] = __ldg(m.w3t + i);
+    float c[TT::MT][TT::NT][4];
+    tc_init_bias<H>(c, m.b1);
+    tc_gemm<H>(c, s.x, inp, m.in, m.w1t, s.wst, false);
+    stage_load<H>(m.w2t, H, s.wst, 0, 0);            // prefetch W2t stage 0 under the epilogue
+    tc_foreach<H>(c, [&](int row, int col, float v0, float v1) {
+        *reinterpret_cast<float2*>(s.h1 + (size_t)row * TT::LDA + col) = make_float2(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+    });
+    tc_init_bias<H>(c, m.b2);
+    tc_gemm<H>(c, s.h1, TT::LDA, H, m.w2t, s.wst, true);
+    tc_foreach<H>(c, [&](int row, int col, float v0, float v1) {
+        *reinterpret_cast<float2*>(s.h2 + (size_t)row * TT::LDA + col) = make_float2(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+    });
     __syncthreads();
 }
 
 // Layer 3 (H -> out <= 16): PARTS lanes cooperate on each row, shuffle-reduce; on return the
 // lane with part == 0 of row r (thread r*PARTS) holds out[0..out) for that row.
 template <int H>
-__device__ __forceinline__ void mlp_head_forward(const Mlp3& m, const float* h2, float* out) {
+__device__ __forceinline__ void mlp_head_forward(const Mlp3& m, const MlpSmem<H>& s, float* out) {
     using TT = MlpTile<H>;
     const int tid = threadIdx.x;
     const int r = tid / TT::PARTS, part = tid % TT::PARTS;
+    const int no = m.out;
 #pragma unroll
     for (int j = 0; j < MLP_MAX_OUT; ++j) out[j] = 0.f;
     for (int k = part; k < H; k += TT::PARTS) {
-        const float x = h2[(size_t)r * H + k];
-        const float* w = m.w3t + (size_t)k * m.out;
+        const float x = s.h2[(size_t)r * TT::LDA + k];
+        const float* w = s.w3s + (size_t)k * no;
 #pragma unroll
         for (int j = 0; j < MLP_MAX_OUT; ++j)
-            if (j < m.out) out[j] = fmaf(x, __ldg(w + j), out[j]);
+            if (j < no) out[j] = fmaf(x, w[j], out[j]);
     }
 #pragma unroll
     for (int j = 0; j < MLP_MAX_OUT; ++j) {
-        if (j < m.out) {
+        if (j < no) {
             float v = out[j];
 #pragma unroll
             for (int o = TT::PARTS / 2; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, TT::PARTS);
             out[j] = v + __ldg(m.b3 + j);
         }
+    }
+}
+
+// stage R rows of x (optionally gathered) into s.x, zero-padding columns >= in
+template <int H, class RowPtr>
+__device__ __forceinline__ void mlp_stage_rows(const MlpSmem<H>& s, int in, RowPtr row_ptr) {
+    using TT = MlpTile<H>;
+    const int inp = TT::in_pad(in);
+    for (int i = threadIdx.x; i < TT::R * inp; i += MLP_TPB) {
+        const int r = i / inp, k = i % inp;
+        const float* p = row_ptr(r);
+        s.x[i] = (p != nullptr && k < in) ? p[k] : 0.f;
     }
 }
 

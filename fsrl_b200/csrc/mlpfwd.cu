@@ -13,26 +13,18 @@ mlp_forward_kernel(const Mlp3 m, const float* __restrict__ x, const int* __restr
     using TT = MlpTile<H>;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
-    const int INP = TT::in_pad(m.in);
-    float* xtile = smem;
-    float* h1 = xtile + TT::R * INP;
-    float* h2 = h1 + TT::R * H;
-    float* wst = h2 + TT::R * H;
+    const MlpSmem<H> sm(smem, m.in, m.out);
     const long long r0 = (long long)blockIdx.x * TT::R;
-    for (int i = tid; i < TT::R * INP; i += MLP_TPB) {
-        const int r = i / INP, k = i % INP;
+    mlp_stage_rows<H>(sm, m.in, [&](int r) -> const float* {
         const long long row = r0 + r;
-        float v = 0.f;
-        if (row < n_rows && k < m.in) {
-            const long long src = idx ? (long long)idx[row] : row;
-            v = x[src * m.in + k];
-        }
-        xtile[i] = v;
-    }
+        if (row >= n_rows) return nullptr;
+        const long long src = idx ? (long long)idx[row] : row;
+        return x + src * m.in;
+    });
     __syncthreads();
-    mlp_hidden_forward<H>(m, xtile, h1, h2, wst);
+    mlp_hidden_forward<H>(m, sm);
     float out[MLP_MAX_OUT];
-    mlp_head_forward<H>(m, h2, out);
+    mlp_head_forward<H>(m, sm, out);
     const int r = tid / TT::PARTS, part = tid % TT::PARTS;
     const long long row = r0 + r;
     if (part == 0 && row < n_rows) {

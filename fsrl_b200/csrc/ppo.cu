@@ -31,6 +31,9 @@ constexpr int ST_ACTOR_REW = 0, ST_ACTOR_SAFETY = 1, ST_KL = 2, ST_VF0 = 3, ST_V
 constexpr float LOG_SQRT_2PI_P = 0.9189385332046727f;
 constexpr int DOUT_LD = 16;   // scratch row stride of dOut (cols [A, 2A) carry dlog_sigma)
 
+__device__ long long g_dbg_clock[16];
+#define DBG_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
+
 struct NetView {   // resolved pointers of one network inside the flat buffers
     Mlp3 m;
     const float* w2n;      // mirror [out][in] of w2t
@@ -85,28 +88,24 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
     const int net = blockIdx.y;
     const int r0 = blockIdx.x * TT::R;
     const int D = u.D;
-    const int INP = TT::in_pad(D);
-    float* xtile = smem;
-    float* h1 = xtile + TT::R * INP;
-    float* h2 = h1 + TT::R * H;
-    float* wst = h2 + TT::R * H;
-    float* dz = wst + 2 * MLP_KC * H;                 // [R][H]
-    float* sdout = dz + TT::R * H;                    // [R][DOUT_LD]
+    const NetView nv = net_view(u, net);
+    const MlpSmem<H> sm(smem, D, nv.m.out);
+    float* dz = sm.end(nv.m.out);                     // [R][LDA]
+    float* sdout = dz + (size_t)TT::R * TT::LDA;      // [R][DOUT_LD]
     __shared__ int s_idx[64];
     __shared__ float s_red[MLP_TPB / 32];
     __shared__ float s_mean[2], s_rstd[2];
 
-    const NetView nv = net_view(u, net);
+    DBG_T(0);
     const int* perm = u.perm + mb_off;
     if (net == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by phase C of the previous step
 
     if (tid < TT::R) s_idx[tid] = (r0 + tid < B) ? perm[r0 + tid] : -1;
     __syncthreads();
-    for (int i = tid; i < TT::R * INP; i += MLP_TPB) {
-        const int r = i / INP, k = i % INP;
+    mlp_stage_rows<H>(sm, D, [&](int r) -> const float* {
         const int id = s_idx[r];
-        xtile[i] = (id >= 0 && k < D) ? u.obs[(size_t)id * D + k] : 0.f;
-    }
+        return id >= 0 ? u.obs + (size_t)id * D : nullptr;
+    });
     // per-minibatch advantage normalisation (ppo_lag.py:178-182): mean, unbiased std, no eps
     if (net == 0) {
         for (int c = 0; c < u.C; ++c) {
@@ -126,10 +125,13 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         }
     }
     __syncthreads();
+    DBG_T(1);
 
-    mlp_hidden_forward<H>(nv.m, xtile, h1, h2, wst);
+    mlp_hidden_forward<H>(nv.m, sm);
+    DBG_T(2);
     float out[MLP_MAX_OUT];
-    mlp_head_forward<H>(nv.m, h2, out);
+    mlp_head_forward<H>(nv.m, sm, out);
+    DBG_T(3);
 
     // ---- loss gradient at the head: one thread per row -----------------------------------------
     const int r = tid / TT::PARTS, part = tid % TT::PARTS;
@@ -221,6 +223,7 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
                     make_float4(dd[j], dd[j + 1], dd[j + 2], dd[j + 3]);
         }
     }
+    DBG_T(4);
     // minibatch statistics (loss/actor_rew, actor_safety, kl, vf_i): one atomic per CTA each
     {
         float* stat = u.stats + (size_t)slot * FSRL_PPO_STATS;
@@ -241,56 +244,44 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
     }
     __syncthreads();
 
+    DBG_T(5);
     // ---- backward through layer 3 and ReLU 2; spill h1 / h2 / dz2 for the weight gradients ------
-    const int to = tid % TT::TO, tr = tid / TT::TO;
     const int nout = (net == 0) ? u.A : 1;       // head columns that feed w3t (mu only)
-    {
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const int wout = nv.m.out;
+    for (int e = tid; e < TT::R * (H / 4); e += MLP_TPB) {
+        const int row = e / (H / 4), k4 = (e % (H / 4)) * 4;
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nout; ++j) {
-            float w[4];
+            const float g = sdout[row * DOUT_LD + j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) w[q] = __ldg(nv.m.w3t + (size_t)(4 * to + q) * nv.m.out + j);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float g = sdout[(4 * tr + i) * DOUT_LD + j];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(g, w[q], acc[i][q]);
-            }
+            for (int q = 0; q < 4; ++q) a4[q] = fmaf(g, sm.w3s[(size_t)(k4 + q) * wout + j], a4[q]);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = 4 * tr + i;
-            const float4 hv = *reinterpret_cast<const float4*>(h2 + (size_t)row * H + 4 * to);
-            const float4 g = make_float4(hv.x > 0.f ? acc[i][0] : 0.f, hv.y > 0.f ? acc[i][1] : 0.f,
-                                         hv.z > 0.f ? acc[i][2] : 0.f, hv.w > 0.f ? acc[i][3] : 0.f);
-            *reinterpret_cast<float4*>(dz + (size_t)row * H + 4 * to) = g;
-            if (r0 + row < u.bmax) {
-                *reinterpret_cast<float4*>(nv.s_dz2 + (size_t)(r0 + row) * H + 4 * to) = g;
-                *reinterpret_cast<float4*>(nv.s_h2 + (size_t)(r0 + row) * H + 4 * to) = hv;
-                *reinterpret_cast<float4*>(nv.s_h1 + (size_t)(r0 + row) * H + 4 * to) =
-                    *reinterpret_cast<const float4*>(h1 + (size_t)row * H + 4 * to);
-            }
+        const float4 hv = *reinterpret_cast<const float4*>(sm.h2 + (size_t)row * TT::LDA + k4);
+        const float4 g4 = make_float4(hv.x > 0.f ? a4[0] : 0.f, hv.y > 0.f ? a4[1] : 0.f,
+                                      hv.z > 0.f ? a4[2] : 0.f, hv.w > 0.f ? a4[3] : 0.f);
+        *reinterpret_cast<float4*>(dz + (size_t)row * TT::LDA + k4) = g4;
+        if (r0 + row < u.bmax) {
+            *reinterpret_cast<float4*>(nv.s_dz2 + (size_t)(r0 + row) * H + k4) = g4;
+            *reinterpret_cast<float4*>(nv.s_h2 + (size_t)(r0 + row) * H + k4) = hv;
+            *reinterpret_cast<float4*>(nv.s_h1 + (size_t)(r0 + row) * H + k4) =
+                *reinterpret_cast<const float4*>(sm.h1 + (size_t)row * TT::LDA + k4);
         }
     }
-    __syncthreads();
+    DBG_T(6);
     // ---- backward through layer 2: dH1 = dZ2 . W2 (W2n is [out][in]) then ReLU 1 ------------------
     {
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-        tile_gemm_hh<H>(acc, dz, nv.w2n, wst, false);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = 4 * tr + i;
-            const float4 hv = *reinterpret_cast<const float4*>(h1 + (size_t)row * H + 4 * to);
-            if (r0 + row < u.bmax)
-                *reinterpret_cast<float4*>(nv.s_dz1 + (size_t)(r0 + row) * H + 4 * to) =
-                    make_float4(hv.x > 0.f ? acc[i][0] : 0.f, hv.y > 0.f ? acc[i][1] : 0.f,
-                                hv.z > 0.f ? acc[i][2] : 0.f, hv.w > 0.f ? acc[i][3] : 0.f);
-        }
+        float c[TT::MT][TT::NT][4];
+        tc_init_bias<H>(c, nullptr);
+        tc_gemm<H>(c, dz, TT::LDA, H, nv.w2n, sm.wst, false);
+        tc_foreach<H>(c, [&](int row, int col, float v0, float v1) {
+            if (r0 + row < u.bmax) {
+                const float2 hv = *reinterpret_cast<const float2*>(sm.h1 + (size_t)row * TT::LDA + col);
+                *reinterpret_cast<float2*>(nv.s_dz1 + (size_t)(r0 + row) * H + col) =
+                    make_float2(hv.x > 0.f ? v0 : 0.f, hv.y > 0.f ? v1 : 0.f);
+            }
+        });
     }
+    DBG_T(7);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -580,7 +571,7 @@ template <int H>
 static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, int slot,
                                 long long adam_t, cudaStream_t s) {
     using TT = MlpTile<H>;
-    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * H + (size_t)TT::R * DOUT_LD);
+    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * TT::LDA + (size_t)TT::R * DOUT_LD);
     static bool attr_done = false;
     if (!attr_done) {
         FSRL_CUDA(cudaFuncSetAttribute(ppo_fwdbwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
@@ -687,7 +678,7 @@ template <int H>
 static int ppo_time_phases(const fsrl_ppo_update_t& u0, int B, int iters, float* ms, cudaStream_t s) {
     using TT = MlpTile<H>;
     fsrl_ppo_update_t u = u0;
-    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * H + (size_t)TT::R * DOUT_LD);
+    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * TT::LDA + (size_t)TT::R * DOUT_LD);
     FSRL_CUDA(cudaFuncSetAttribute(ppo_fwdbwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     cudaEvent_t e[4];
     for (int i = 0; i < 4; ++i) FSRL_CUDA(cudaEventCreate(&e[i]));
@@ -725,4 +716,9 @@ extern "C" int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters
         case 256: return ppo_time_phases<256>(*u, B, iters, ms_out, s);
         default: return ppo_time_phases<512>(*u, B, iters, ms_out, s);
     }
+}
+
+extern "C" int fsrl_debug_clocks(long long* out16) {
+    FSRL_CUDA(cudaMemcpyFromSymbol(out16, fsrl::g_dbg_clock, sizeof(long long) * 16));
+    return FSRL_OK;
 }

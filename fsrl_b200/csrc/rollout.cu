@@ -41,11 +41,10 @@ rollout_step_kernel(const fsrl_rollout_t a) {
 
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * TT::R;
+    const Mlp3& actor = *reinterpret_cast<const Mlp3*>(&a.actor);
+    const MlpSmem<H> sm(smem, D, actor.out);
     constexpr int INP = TT::in_pad(D);
-    float* xtile = smem;
-    float* h1 = xtile + TT::R * INP;
-    float* h2 = h1 + TT::R * H;
-    float* wst = h2 + TT::R * H;
+    float* xtile = sm.x;
 
     // tile-level early out: nothing active in this tile
     __shared__ int s_any;
@@ -59,18 +58,16 @@ rollout_step_kernel(const fsrl_rollout_t a) {
     if (!s_any) return;
 
     // ---- stage the observation tile ---------------------------------------------------------
-    for (int i = tid; i < TT::R * INP; i += MLP_TPB) {
-        const int r = i / INP, k = i % INP;
+    mlp_stage_rows<H>(sm, D, [&](int r) -> const float* {
         const int e = e0 + r;
-        xtile[i] = (e < a.E && k < D) ? a.obs_cur[(size_t)e * D + k] : 0.f;
-    }
+        return e < a.E ? a.obs_cur + (size_t)e * D : nullptr;
+    });
     __syncthreads();
 
     float out[MLP_MAX_OUT];
-    const Mlp3& actor = *reinterpret_cast<const Mlp3*>(&a.actor);
     if (a.mode != FSRL_MODE_RANDOM) {
-        mlp_hidden_forward<H>(actor, xtile, h1, h2, wst);
-        mlp_head_forward<H>(actor, h2, out);
+        mlp_hidden_forward<H>(actor, sm);
+        mlp_head_forward<H>(actor, sm, out);
     }
 
     // ---- one thread per env: sample, log-prob, map, step, store ------------------------------

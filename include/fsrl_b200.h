@@ -169,6 +169,9 @@ int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total, int batch_
                        int stats_slot0, long long adam_t0, int* n_minibatches, void* stream);
 /* measurement aid (bench.py roofline): mean duration [ms] of the three phase kernels over
  * `iters` launches on the first B rows of u->perm; weights are left untouched (lr = 0) */
+/* tuning aid: clock64() stamps taken by CTA (0,0) at the phase boundaries of the last
+ * ppo_fwdbwd launch (host array of 16) */
+int fsrl_debug_clocks(long long* out16);
 int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters, float* ms_out, void* stream);
 
 /* ---- a6: batched critic / actor forward ---------------------------------------------------

@@ -59,6 +59,13 @@ def bench_ppo(iters):
     import bench
     agent, trainer, col, buf, T = bench.build("cuda:0", 0)
     print(json.dumps({"phase_ms(fwdbwd,wgrad,adam)": bench.phase_times(agent, col, buf, iters=iters)}))
+    import ctypes
+    from fsrl_b200 import _lib
+    ck = (ctypes.c_longlong * 16)()
+    _lib.check(_lib.lib.fsrl_debug_clocks(ck))
+    c = list(ck)
+    print("fwdbwd CTA(0,0) cycles per section [prologue, hidden_fwd, head, lossgrad, stats, bwdL3, bwdL2]:",
+          [c[i + 1] - c[i] for i in range(7)], "total", c[7] - c[0])
 
 
 if __name__ == "__main__":
