@@ -89,6 +89,49 @@ class PpoUpdate(ctypes.Structure):
                 ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("adam_eps", c_f64)]
 
 
+
+class NetRef(ctypes.Structure):
+    _fields_ = [("off", ctypes.c_longlong), ("w2n_off", ctypes.c_longlong), ("D", c_int), ("H", c_int),
+                ("out", c_int), ("n_extra", c_int), ("slot", c_int), ("pad", c_int)]
+
+
+class NetList(ctypes.Structure):
+    _fields_ = [("n", c_int), ("pad", c_int), ("nets", NetRef * 8)]
+
+
+class Engine(ctypes.Structure):
+    _fields_ = [("theta", c_vp), ("grad", c_vp), ("adam_m", c_vp), ("adam_v", c_vp), ("w2n", c_vp),
+                ("scratch", c_vp), ("bmax", c_int), ("pad", c_int)]
+
+
+class EngInput(ctypes.Structure):
+    _fields_ = [("xa", c_vp), ("ia", c_vp), ("xb", c_vp), ("ib", c_vp), ("Da", c_int), ("Db", c_int)]
+
+
+class OffPolicy(ctypes.Structure):
+    _fields_ = [("eng", Engine), ("actor", NetList), ("actor_old", NetList), ("critics", NetList),
+                ("critics_old", NetList),
+                ("algo", c_int), ("D", c_int), ("A", c_int), ("C", c_int), ("twin", c_int),
+                ("n_step", c_int), ("bounded", c_int), ("use_alpha", c_int), ("auto_alpha", c_int),
+                ("use_lagrangian", c_int), ("seed", ctypes.c_uint), ("pad0", ctypes.c_uint),
+                ("gamma", c_f64), ("tau", c_f64), ("critic_lr", c_f64), ("actor_lr", c_f64),
+                ("alpha_lr", c_f32), ("target_entropy", c_f32), ("max_action", c_f32),
+                ("sigma_min", c_f32), ("sigma_max", c_f32), ("tanh_eps", c_f32), ("lagrangian", c_f32),
+                ("rescaling", c_f32),
+                ("b_obs", c_vp), ("b_obs_next", c_vp), ("b_act", c_vp), ("b_rew", c_vp), ("b_cost", c_vp),
+                ("b_term", c_vp), ("b_trunc", c_vp), ("b_ptr", c_vp), ("b_len", c_vp),
+                ("cap", ctypes.c_longlong),
+                ("w_term_idx", c_vp), ("w_partial", c_vp), ("w_gpow", c_vp), ("w_vmask", c_vp),
+                ("w_target", c_vp), ("w_act_next", c_vp), ("w_logp_next", c_vp), ("w_act", c_vp),
+                ("w_logp", c_vp), ("w_keep", c_vp),
+                ("actor_out", c_vp), ("actor_old_out", c_vp), ("actor_dout", c_vp),
+                ("q_out", c_vp * 4), ("q_dout", c_vp * 4), ("q_dx", c_vp * 4), ("q_old_out", c_vp * 4),
+                ("alpha", c_vp), ("alpha_state", c_vp)]
+
+
+ALGO_SAC, ALGO_DDPG = 0, 1
+OFF_STATS = 8
+
 MODE_TRAIN, MODE_EVAL, MODE_RANDOM = 0, 1, 2
 HEAD_GAUSS_INDEP, HEAD_GAUSS_COND, HEAD_DETERMINISTIC = 0, 1, 2
 BOUND_NONE, BOUND_CLIP, BOUND_TANH = 0, 1, 2
@@ -107,6 +150,17 @@ SIGNATURES = {
     "fsrl_collect_begin": (c_int, [ctypes.POINTER(Rollout), c_int, c_vp]),
     "fsrl_rollout_steps": (c_int, [ctypes.POINTER(Rollout), c_int, c_vp]),
     "fsrl_mlp_forward": (c_int, [ctypes.POINTER(Mlp3), c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),
+    "fsrl_engine_slot_floats": (c_size, [c_int, c_int]),
+    "fsrl_engine_forward": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(EngInput), c_int, c_int, c_vp]),
+    "fsrl_engine_backward": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), c_int, c_int, c_vp]),
+    "fsrl_engine_wgrad": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(EngInput), c_int, c_int, c_vp, c_vp]),
+    "fsrl_engine_adam": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), c_f64, c_f64, c_f64, c_f64,
+                                 ctypes.c_longlong, c_f64, c_f64, c_vp, c_f64, c_vp]),
+    "fsrl_engine_polyak": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(NetList), c_f64, c_vp]),
+    "fsrl_engine_sync_mirror": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), c_vp]),
+    "fsrl_nstep_prepare": (c_int, [ctypes.POINTER(OffPolicy), c_vp, c_int, c_vp]),
+    "fsrl_offpolicy_steps": (c_int, [ctypes.POINTER(OffPolicy), c_vp, c_int, c_int, ctypes.c_longlong,
+                                     ctypes.c_longlong, ctypes.c_ulonglong, c_vp, c_vp]),
     "fsrl_ppo_scratch_floats": (c_size, [c_int, c_int, c_int]),
     "fsrl_ppo_sync_mirror": (c_int, [ctypes.POINTER(PpoUpdate), c_vp]),
     "fsrl_debug_clocks": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),

@@ -1,4 +1,6 @@
 from .base_agent import BaseAgent, OffpolicyAgent, OnpolicyAgent
+from .ddpg_lag_agent import DDPGLagAgent
 from .ppo_lag_agent import PPOLagAgent
+from .sac_lag_agent import SACLagAgent
 
-__all__ = ["BaseAgent", "OffpolicyAgent", "OnpolicyAgent", "PPOLagAgent"]
+__all__ = ["BaseAgent", "OffpolicyAgent", "OnpolicyAgent", "PPOLagAgent", "SACLagAgent", "DDPGLagAgent"]

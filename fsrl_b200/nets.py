@@ -236,3 +236,55 @@ class Arena:
         if s.extra is None:
             return None
         return self.theta.data_ptr() + 4 * s.offsets()[6]
+
+
+# ---------------------------------------------------------------------------------------------
+# Q-critics of the off-policy learners (reference: fsrl/utils/net/continuous.py:12-155)
+# ---------------------------------------------------------------------------------------------
+class DoubleCritic(nn.Module):
+    """Two independent Q(s, a) heads; ``forward`` returns [q1, q2], ``predict`` (min, list)."""
+
+    def __init__(self, preprocess_net1: Net, preprocess_net2: Net, hidden_sizes=(), device=None, **_):
+        super().__init__()
+        self.device = device
+        self.preprocess1, self.preprocess2 = preprocess_net1, preprocess_net2
+        self.output_dim = 1
+        self.last1 = MLP(preprocess_net1.output_dim, 1, ())
+        self.last2 = MLP(preprocess_net2.output_dim, 1, ())
+        self.last2.load_state_dict(self.last1.state_dict())        # reference: deepcopy(last1)
+
+    def forward(self, obs, act=None, info={}):
+        dev = next(self.parameters()).device
+        obs = torch.as_tensor(obs, device=dev, dtype=torch.float32).flatten(1)
+        if act is not None:
+            act = torch.as_tensor(act, device=dev, dtype=torch.float32).flatten(1)
+            obs = torch.cat([obs, act], dim=1)
+        return [self.last1(self.preprocess1(obs)[0]), self.last2(self.preprocess2(obs)[0])]
+
+    def predict(self, obs, act=None, info={}):
+        q = self(obs, act, info)
+        return torch.min(q[0], q[1]), q
+
+
+class SingleCritic(Critic):
+    """tianshou Critic with the list-valued API of DoubleCritic."""
+
+    def forward(self, obs, act=None, info={}):
+        return [super().forward(obs, act, info)]
+
+    def predict(self, obs, act=None, info={}):
+        q = self(obs, act, info)
+        return q[0], q
+
+
+def slots_from_module(name: str, m: nn.Module) -> List[NetSlot]:
+    """1 slot for Actor/ActorProb/Critic, 2 for a DoubleCritic."""
+    if isinstance(m, DoubleCritic):
+        out = []
+        for k, (pre, last) in enumerate(((m.preprocess1, m.last1), (m.preprocess2, m.last2))):
+            body = _linears(pre.model)
+            if len(body) != 2:
+                raise ValueError("fsrl_b200 kernels support exactly two hidden layers")
+            out.append(NetSlot(f"{name}.{k}", m, body[0], body[1], _linears(last), None))
+        return out
+    return [slot_from_module(name, m)]

@@ -1,5 +1,8 @@
 from .base_policy import ActorCritic, BasePolicy, DeviceBatch
 from .lagrangian_base import LagrangianPolicy
 from .ppo_lag import PPOLagrangian
+from .sac_lag import SACLagrangian
+from .ddpg_lag import DDPGLagrangian, GaussianNoise
 
-__all__ = ["ActorCritic", "BasePolicy", "DeviceBatch", "LagrangianPolicy", "PPOLagrangian"]
+__all__ = ["ActorCritic", "BasePolicy", "DeviceBatch", "LagrangianPolicy", "PPOLagrangian",
+           "SACLagrangian", "DDPGLagrangian", "GaussianNoise"]

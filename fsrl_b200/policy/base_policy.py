@@ -22,7 +22,7 @@ from torch import nn
 
 from .. import _lib, ops
 from ..data.batch import Batch, to_numpy
-from ..nets import Actor, ActorProb, Arena, Critic, slot_from_module
+from ..nets import Actor, ActorProb, Arena, Critic, slot_from_module, slots_from_module
 from ..spaces import Box, Discrete, MultiBinary, MultiDiscrete
 from ..utils.logger import BaseLogger, DummyLogger
 
@@ -107,7 +107,11 @@ class BasePolicy(ABC, nn.Module):
         if torch.device(device).type != "cuda":
             raise RuntimeError("fsrl_b200 runs on CUDA devices only (got device=%r); there is no "
                                "CPU fallback" % (device,))
-        slots = [slot_from_module("net%d" % i, m) for i, m in enumerate(self._net_list())]
+        slots, self._slot_groups = [], []
+        for i, m in enumerate(self._net_list()):
+            ss = slots_from_module("net%d" % i, m)
+            self._slot_groups.append(ss)
+            slots += ss
         self._arena = Arena(slots, device)
         return self._arena
 

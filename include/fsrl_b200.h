@@ -180,6 +180,97 @@ int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters, float* ms
 int fsrl_mlp_forward(const fsrl_mlp3_t* net, const float* x, const int* idx, long long n_rows,
                      float* y, void* stream);
 
+/* ---- generic minibatch MLP engine (SAC / DDPG / CPO updates are assembled from it) --------
+ * Replaces the eager autograd forward/backward/optimizer.step of the reference's learners
+ * (fsrl/policy/sac_lag.py:185-258, ddpg_lag.py:165-213, cpo.py:147-162) and soft_update
+ * (fsrl/policy/base_policy.py:220-224).  Networks live in the flat arena (layout as for
+ * fsrl_ppo_update_t); each has a scratch slot of fsrl_engine_slot_floats(H, bmax) floats:
+ *   h1 | h2 | dz1 | dz2 : [bmax][H],  out | dout : [bmax][16],  dx : [bmax][64]
+ * forward writes `out` (+ h1, h2 when save != 0); the caller fills `dout` (d loss / d head
+ * output, columns [out, out+n_extra) = d loss / d extra parameters); backward produces dz1,
+ * dz2 (+ dx = d loss / d input); wgrad reduces them into `grad`; adam applies them. */
+#define FSRL_ENG_MAX_NETS 8
+#define FSRL_ENG_DX_LD 64
+typedef struct fsrl_netref {
+    long long off;      /* start of the net inside theta / grad / adam_m / adam_v */
+    long long w2n_off;  /* start of its W2 mirror inside w2n */
+    int D, H, out, n_extra;
+    int slot, pad;
+} fsrl_netref_t;
+typedef struct fsrl_netlist {
+    int n, pad;
+    fsrl_netref_t nets[FSRL_ENG_MAX_NETS];
+} fsrl_netlist_t;
+typedef struct fsrl_engine {
+    float *theta, *grad, *adam_m, *adam_v, *w2n, *scratch;
+    int bmax, pad;
+} fsrl_engine_t;
+/* input row r = concat(xa[ia ? ia[r] : r][0..Da), xb[ib ? ib[r] : r][0..Db)) */
+typedef struct fsrl_eng_input {
+    const float* xa;
+    const int* ia;
+    const float* xb;
+    const int* ib;
+    int Da, Db;
+} fsrl_eng_input_t;
+
+size_t fsrl_engine_slot_floats(int H, int bmax);
+int fsrl_engine_forward(const fsrl_engine_t* e, const fsrl_netlist_t* nets, const fsrl_eng_input_t* in,
+                        int B, int save, void* stream);
+int fsrl_engine_backward(const fsrl_engine_t* e, const fsrl_netlist_t* nets, int B, int want_dx, void* stream);
+int fsrl_engine_wgrad(const fsrl_engine_t* e, const fsrl_netlist_t* nets, const fsrl_eng_input_t* in, int B,
+                      int accumulate, float* norm_sq, void* stream);
+/* torch.optim.Adam step `step` (1-based) on the listed nets; grad <- grad*grad_scale + 2*l2_reg*p
+ * and, when norm_sq != NULL && max_grad_norm > 0, clip_grad_norm_ by sqrt(*norm_sq) */
+int fsrl_engine_adam(const fsrl_engine_t* e, const fsrl_netlist_t* nets, double lr, double beta1,
+                     double beta2, double eps, long long step, double grad_scale, double l2_reg,
+                     const float* norm_sq, double max_grad_norm, void* stream);
+int fsrl_engine_polyak(const fsrl_engine_t* e, const fsrl_netlist_t* dst, const fsrl_netlist_t* src,
+                       double tau, void* stream);
+int fsrl_engine_sync_mirror(const fsrl_engine_t* e, const fsrl_netlist_t* nets, void* stream);
+
+/* ---- a12-a14, a16: SAC- / DDPG-Lagrangian gradient steps -------------------------------------
+ * fsrl_offpolicy_steps runs n_steps iterations of `policy.update(batch_size, buffer)`
+ * (fsrl/trainer/offpolicy.py:102-104): process_fn = n-step targets for the reward and cost
+ * critics (fsrl/policy/base_policy.py:453-512,543-567; sac_lag.py:136-145; ddpg_lag.py:
+ * 125-131), critics_loss, policy_loss (lambda-weighted cost-Q term + rescaling,
+ * lagrangian_base.py:145-166; SAC: tanh-squashed rsample, log-prob correction, auto-alpha),
+ * sync_weight.  Networks are engine netlists: SAC critics = C x DoubleCritic = 2C nets
+ * (twin = 1, order r1 r2 c1 c2), DDPG critics = C nets. */
+#define FSRL_MAX_NSTEP 8
+#define FSRL_OFF_STATS 8
+enum { FSRL_OFF_ST_Q0 = 0, FSRL_OFF_ST_Q1 = 1, FSRL_OFF_ST_ACTOR_REW = 2, FSRL_OFF_ST_ACTOR_SAFETY = 3,
+       FSRL_OFF_ST_LOGP = 4, FSRL_OFF_ST_ALPHA_LOSS = 5, FSRL_OFF_ST_ALPHA = 6 };
+enum { FSRL_ALGO_SAC = 0, FSRL_ALGO_DDPG = 1 };
+typedef struct fsrl_offpolicy {
+    fsrl_engine_t eng;
+    fsrl_netlist_t actor, actor_old, critics, critics_old;
+    int algo, D, A, C, twin, n_step, bounded, use_alpha, auto_alpha, use_lagrangian;
+    unsigned int seed, pad0;
+    double gamma, tau, critic_lr, actor_lr;
+    float alpha_lr, target_entropy, max_action, sigma_min, sigma_max, tanh_eps, lagrangian, rescaling;
+    /* replay buffer (env-major sub-buffer rings, see fsrl_rollout_t) */
+    const float *b_obs, *b_obs_next, *b_act, *b_rew, *b_cost;
+    const unsigned char *b_term, *b_trunc;
+    const int *b_ptr, *b_len;
+    long long cap;
+    /* per-step work arrays, all sized for eng.bmax rows */
+    int* w_term_idx;
+    double *w_partial, *w_gpow;      /* [2][B], [B] */
+    float *w_vmask, *w_target;       /* [B], [2][B] */
+    float *w_act_next, *w_logp_next, *w_act, *w_logp, *w_keep; /* [B][A], [B], [B][A], [B], [B][24] */
+    /* engine scratch views (host-resolved): head outputs / gradients / input gradients */
+    float *actor_out, *actor_old_out, *actor_dout;
+    float *q_out[4], *q_dout[4], *q_dx[4], *q_old_out[4];
+    float* alpha;        /* device scalar */
+    float* alpha_state;  /* device [log_alpha, adam_m, adam_v, adam_t] */
+} fsrl_offpolicy_t;
+
+int fsrl_nstep_prepare(const fsrl_offpolicy_t* d, const int* idx, int B, void* stream);
+int fsrl_offpolicy_steps(const fsrl_offpolicy_t* d, const int* idx_all, int n_steps, int B,
+                         long long critic_t0, long long actor_t0, unsigned long long noise_t0,
+                         float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
