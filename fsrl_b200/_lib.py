@@ -129,6 +129,14 @@ class OffPolicy(ctypes.Structure):
                 ("alpha", c_vp), ("alpha_state", c_vp)]
 
 
+class Cpo(ctypes.Structure):
+    _fields_ = [("eng", Engine), ("actor", NetList), ("actor_r", NetList), ("N", ctypes.c_longlong),
+                ("ld", ctypes.c_longlong), ("A", c_int), ("bounded", c_int), ("max_action", c_f32),
+                ("pad0", c_f32), ("obs", c_vp), ("act", c_vp), ("logp_old", c_vp), ("mean_old", c_vp),
+                ("std_old", c_vp), ("adv", c_vp), ("perm", c_vp), ("out", c_vp), ("dout", c_vp),
+                ("log_sigma", c_vp)]
+
+
 ALGO_SAC, ALGO_DDPG = 0, 1
 OFF_STATS = 8
 
@@ -158,6 +166,13 @@ SIGNATURES = {
                                  ctypes.c_longlong, c_f64, c_f64, c_vp, c_f64, c_vp]),
     "fsrl_engine_polyak": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(NetList), c_f64, c_vp]),
     "fsrl_engine_sync_mirror": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), c_vp]),
+    "fsrl_cpo_head": (c_int, [ctypes.POINTER(Cpo), c_int, c_vp, c_vp]),
+    "fsrl_cpo_hvp": (c_int, [ctypes.POINTER(Cpo), c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "fsrl_vec_dot": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),
+    "fsrl_vec_axpby": (c_int, [c_f64, c_vp, c_f64, c_vp, ctypes.c_longlong, c_vp]),
+    "fsrl_vec_add_scaled": (c_int, [c_vp, c_f64, c_vp, c_vp, ctypes.c_longlong, c_vp]),
+    "fsrl_engine_wgrad_to": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(EngInput),
+                                     ctypes.c_longlong, c_vp, c_vp]),
     "fsrl_nstep_prepare": (c_int, [ctypes.POINTER(OffPolicy), c_vp, c_int, c_vp]),
     "fsrl_offpolicy_steps": (c_int, [ctypes.POINTER(OffPolicy), c_vp, c_int, c_int, ctypes.c_longlong,
                                      ctypes.c_longlong, ctypes.c_ulonglong, c_vp, c_vp]),

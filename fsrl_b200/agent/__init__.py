@@ -1,6 +1,7 @@
 from .base_agent import BaseAgent, OffpolicyAgent, OnpolicyAgent
+from .cpo_agent import CPOAgent
 from .ddpg_lag_agent import DDPGLagAgent
 from .ppo_lag_agent import PPOLagAgent
 from .sac_lag_agent import SACLagAgent
 
-__all__ = ["BaseAgent", "OffpolicyAgent", "OnpolicyAgent", "PPOLagAgent", "SACLagAgent", "DDPGLagAgent"]
+__all__ = ["BaseAgent", "OffpolicyAgent", "OnpolicyAgent", "PPOLagAgent", "SACLagAgent", "DDPGLagAgent", "CPOAgent"]

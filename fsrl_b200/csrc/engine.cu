@@ -11,56 +11,9 @@
 // Every kernel processes up to FSRL_ENG_MAX_NETS networks of equal hidden width in one launch
 // (blockIdx.y selects the net), reading parameters from the flat arena and exchanging
 // activations through an L2-resident scratch slot per network.
-#include "mlp.cuh"
-#include "fsrl_b200.h"
+#include "engine.cuh"
 
 namespace fsrl {
-
-constexpr int EDOUT_LD = 16;
-
-struct EngView {
-    Mlp3 m;
-    const float* w2n;
-    float *g_w1t, *g_b1, *g_w2t, *g_b2, *g_w3t, *g_b3, *g_extra;
-    float *s_h1, *s_h2, *s_dz1, *s_dz2, *s_out, *s_dout, *s_dx;
-};
-
-__host__ __device__ inline size_t eng_slot_floats(int H, int bmax) {
-    return (size_t)bmax * (4 * (size_t)H + 2 * EDOUT_LD + FSRL_ENG_DX_LD);
-}
-
-__device__ __forceinline__ EngView eng_view(const fsrl_engine_t& e, const fsrl_netref_t& n) {
-    EngView v;
-    const int H = n.H, D = n.D, out = n.out;
-    const float* th = e.theta + n.off;
-    float* g = e.grad + n.off;
-    size_t o = 0;
-    v.m.w1t = th + o; v.g_w1t = g + o; o += (size_t)D * H;
-    v.m.b1 = th + o;  v.g_b1 = g + o;  o += H;
-    v.m.w2t = th + o; v.g_w2t = g + o; o += (size_t)H * H;
-    v.m.b2 = th + o;  v.g_b2 = g + o;  o += H;
-    v.m.w3t = th + o; v.g_w3t = g + o; o += (size_t)H * out;
-    v.m.b3 = th + o;  v.g_b3 = g + o;  o += out;
-    v.g_extra = g + o;
-    v.m.in = D; v.m.H = H; v.m.out = out;
-    v.w2n = e.w2n + n.w2n_off;
-    float* sc = e.scratch + (size_t)n.slot * eng_slot_floats(H, e.bmax);
-    const size_t bh = (size_t)e.bmax * H;
-    v.s_h1 = sc; v.s_h2 = sc + bh; v.s_dz1 = sc + 2 * bh; v.s_dz2 = sc + 3 * bh;
-    v.s_out = sc + 4 * bh; v.s_dout = v.s_out + (size_t)e.bmax * EDOUT_LD;
-    v.s_dx = v.s_dout + (size_t)e.bmax * EDOUT_LD;
-    return v;
-}
-
-// input row = concat(xa[ia ? ia[row] : row][0..Da), xb[ib ? ib[row] : row][0..Db))
-__device__ __forceinline__ float eng_input(const fsrl_eng_input_t& in, long long row, int k) {
-    if (k < in.Da) {
-        const long long r = in.ia ? (long long)in.ia[row] : row;
-        return in.xa[r * in.Da + k];
-    }
-    const long long r = in.ib ? (long long)in.ib[row] : row;
-    return in.xb[r * in.Db + (k - in.Da)];
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -190,23 +143,47 @@ __device__ __forceinline__ float eng_block_sum_128(float v, float* red) {
 
 template <int H>
 __global__ void __launch_bounds__(EWG_TPB)
-eng_wgrad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, const fsrl_eng_input_t in, int B,
-                 int accumulate, float* norm_sq) {
+eng_wgrad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, const fsrl_eng_input_t in, int Btot,
+                 int accumulate, float* norm_sq, const WgradRoles roles) {
     constexpr int NTK = H / EWG_TK, NTO = H / EWG_TO, NT = NTK * NTO;
     __shared__ __align__(16) float sL[EWG_RC][EWG_TO];
     __shared__ __align__(16) float sG[EWG_RC][EWG_TO];
     __shared__ float s_red[4];
     const int tid = threadIdx.x;
     const fsrl_netref_t nr = nl.nets[blockIdx.y];
-    const EngView nv = eng_view(e, nr);
+    EngView nv = eng_view(e, nr);
+    const bool split = gridDim.z > 1;
+    // row range of this split
+    const long long rows_per = (((long long)Btot + gridDim.z - 1) / gridDim.z + EWG_RC - 1) / EWG_RC * EWG_RC;
+    const long long row_lo = (long long)blockIdx.z * rows_per;
+    const int B = (int)((row_lo >= Btot) ? 0 : ((Btot - row_lo < rows_per) ? (Btot - row_lo) : rows_per));
+    if (B == 0) return;
+    if (roles.dst) {
+        float* g = roles.dst;
+        size_t o = 0;
+        nv.g_w1t = g + o; o += (size_t)nr.D * H; nv.g_b1 = g + o; o += H; nv.g_w2t = g + o; o += (size_t)H * H;
+        nv.g_b2 = g + o; o += H; nv.g_w3t = g + o; o += (size_t)H * nr.out; nv.g_b3 = g + o; o += nr.out; nv.g_extra = g + o;
+    }
+    nv.s_h1 = const_cast<float*>(roles.L2 ? roles.L2 : nv.s_h1) + (size_t)row_lo * H;
+    nv.s_dz2 = const_cast<float*>(roles.G2 ? roles.G2 : nv.s_dz2) + (size_t)row_lo * H;
+    nv.s_dz1 = const_cast<float*>(roles.G1 ? roles.G1 : nv.s_dz1) + (size_t)row_lo * H;
+    nv.s_h2 = const_cast<float*>(roles.L3 ? roles.L3 : nv.s_h2) + (size_t)row_lo * H;
+    nv.s_dout = const_cast<float*>(roles.G3 ? roles.G3 : nv.s_dout) + (size_t)row_lo * EDOUT_LD;
     const int bx = blockIdx.x;
     const int nchunk = (B + EWG_RC - 1) / EWG_RC;
-    const float beta = accumulate ? 1.f : 0.f;
+    const float beta = (accumulate && !split) ? 1.f : 0.f;
     float sq = 0.f;
+    auto emit = [&](float* gp, float v) {       // write / accumulate / atomically combine one value
+        if (split) { atomicAdd(gp, v); return v; }
+        v += beta * (*gp);
+        *gp = v;
+        return v;
+    };
     if (bx < NT) {
+        if (!(roles.parts & 1)) return;
         const int k0 = (bx / NTO) * EWG_TK, o0 = (bx % NTO) * EWG_TO;
         const int tk = tid / 16, to = tid % 16;
-        const bool do_bias = (k0 == 0);
+        const bool do_bias = (k0 == 0) && roles.bias2;
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
@@ -261,17 +238,13 @@ eng_wgrad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, const fsrl_eng_
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float4* gp = reinterpret_cast<float4*>(nv.g_w2t + (size_t)(k0 + 4 * tk + i) * H + o0 + 4 * to);
-            float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            if (accumulate) { const float4 old = *gp; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
-            *gp = v;
-            sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            float* gp = nv.g_w2t + (size_t)(k0 + 4 * tk + i) * H + o0 + 4 * to;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float v = emit(gp + j, acc[i][j]); sq += v * v; }
         }
-        if (do_bias && tid < EWG_TO) {
-            const float v = bsum + beta * nv.g_b2[o0 + tid];
-            nv.g_b2[o0 + tid] = v; sq += v * v;
-        }
+        if (do_bias && tid < EWG_TO) { const float v = emit(nv.g_b2 + o0 + tid, bsum); sq += v * v; }
     } else if (bx < NT + NTO) {
+        if (!(roles.parts & 2)) return;
         const int D = nr.D;
         const int o0 = (bx - NT) * EWG_TO;
         const int o = tid % EWG_TO, dg = tid / EWG_TO;
@@ -292,7 +265,7 @@ eng_wgrad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, const fsrl_eng_
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int f = tid + q * EWG_TPB, rr = f / 16, dd = d0 + (f % 16);
-                    px[q] = (rb + rr < B && dd < D) ? eng_input(in, rb + rr, dd) : 0.f;
+                    px[q] = (rb + rr < B && dd < D) ? eng_input(in, row_lo + rb + rr, dd) : 0.f;
                 }
             };
             prefetch(0);
@@ -321,18 +294,12 @@ eng_wgrad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, const fsrl_eng_
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int d = d0 + 8 * dg + q;
-                if (d < D) {
-                    float* gp = nv.g_w1t + (size_t)d * H + o0 + o;
-                    const float v = acc[q] + beta * (*gp);
-                    *gp = v; sq += v * v;
-                }
+                if (d < D) { const float v = emit(nv.g_w1t + (size_t)d * H + o0 + o, acc[q]); sq += v * v; }
             }
-            if (d0 == 0 && dg == 0) {
-                const float v = bsum + beta * nv.g_b1[o0 + o];
-                nv.g_b1[o0 + o] = v; sq += v * v;
-            }
+            if (d0 == 0 && dg == 0) { const float v = emit(nv.g_b1 + o0 + o, bsum); sq += v * v; }
         }
     } else {
+        if (!(roles.parts & 4)) return;
         const int out = nr.out;
         const int k0 = (bx - NT - NTO) * EWG_TO;
         const int k = tid % EWG_TO, jg = tid / EWG_TO;
@@ -382,20 +349,13 @@ eng_wgrad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, const fsrl_eng_
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = 8 * jg + q;
-            if (j < out) {
-                float* gp = nv.g_w3t + (size_t)(k0 + k) * out + j;
-                const float v = acc[q] + beta * (*gp);
-                *gp = v; sq += v * v;
-            }
+            if (j < out) { const float v = emit(nv.g_w3t + (size_t)(k0 + k) * out + j, acc[q]); sq += v * v; }
         }
-        if (k0 == 0 && tid < EDOUT_LD) {
-            if (tid < out) {
-                const float v = csum + beta * nv.g_b3[tid];
-                nv.g_b3[tid] = v; sq += v * v;
-            } else if (nr.n_extra > 0 && tid >= out && tid < out + nr.n_extra) {
+        if (k0 == 0 && tid < EDOUT_LD && roles.bias3) {
+            if (tid < out) { const float v = emit(nv.g_b3 + tid, csum); sq += v * v; }
+            else if (nr.n_extra > 0 && tid >= out && tid < out + nr.n_extra) {
                 // head-gradient columns [out, out + n_extra) carry d loss / d extra (log-sigma)
-                const float v = csum + beta * nv.g_extra[tid - out];
-                nv.g_extra[tid - out] = v; sq += v * v;
+                const float v = emit(nv.g_extra + (tid - out), csum); sq += v * v;
             }
         }
     }
@@ -535,14 +495,6 @@ using namespace fsrl;
 
 extern "C" size_t fsrl_engine_slot_floats(int H, int bmax) { return eng_slot_floats(H, bmax); }
 
-#define ENG_DISPATCH_H(Hv, ...)                                   \
-    switch (Hv) {                                                 \
-        case 64: { constexpr int HH = 64; __VA_ARGS__; } break;   \
-        case 128: { constexpr int HH = 128; __VA_ARGS__; } break; \
-        case 256: { constexpr int HH = 256; __VA_ARGS__; } break; \
-        default: { constexpr int HH = 512; __VA_ARGS__; } break;  \
-    }
-
 extern "C" int fsrl_engine_forward(const fsrl_engine_t* e, const fsrl_netlist_t* nl,
                                    const fsrl_eng_input_t* in, int B, int save, void* stream) {
     int rc = eng_check(e, nl);
@@ -578,19 +530,46 @@ extern "C" int fsrl_engine_backward(const fsrl_engine_t* e, const fsrl_netlist_t
     return FSRL_OK;
 }
 
+namespace fsrl {
+// zero the gradient range of the listed nets (needed before a split-K wgrad that does not accumulate)
+__global__ void eng_zero_grad_kernel(const fsrl_engine_t e, const fsrl_netlist_t nl, float* dst_override) {
+    const fsrl_netref_t nr = nl.nets[blockIdx.y];
+    const long long n = (long long)nr.D * nr.H + nr.H + (long long)nr.H * nr.H + nr.H + (long long)nr.H * nr.out + nr.out + nr.n_extra;
+    float* g = dst_override ? dst_override : e.grad + nr.off;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) g[i] = 0.f;
+}
+
+int eng_wgrad_roles(const fsrl_engine_t* e, const fsrl_netlist_t* nl, const fsrl_eng_input_t* in, long long B,
+                    int accumulate, float* norm_sq, const WgradRoles& roles, cudaStream_t s) {
+    // split the rows so that every CTA streams <= 4096 rows (keeps all SMs busy on big batches)
+    int nsplit = (int)((B + 4095) / 4096);
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 65535) nsplit = 65535;
+    if (nsplit > 1) FSRL_REQUIRE(norm_sq == nullptr, "engine_wgrad: norm_sq is not available with split rows");
+    const bool partial = roles.parts != 7 || !roles.bias2 || !roles.bias3;
+    if (!accumulate && (nsplit > 1 || partial)) {
+        // start from zero and let every part accumulate (atomically when the rows are split)
+        FSRL_REQUIRE(roles.dst == nullptr || nl->n == 1, "engine_wgrad: dst override needs a single net");
+        eng_zero_grad_kernel<<<dim3(64, nl->n), 256, 0, s>>>(*e, *nl, roles.dst);
+        accumulate = 1;
+    }
+    ENG_DISPATCH_H(nl->nets[0].H, {
+        const dim3 g((HH / EWG_TK) * (HH / EWG_TO) + 2 * (HH / EWG_TO), nl->n, nsplit);
+        eng_wgrad_kernel<HH><<<g, EWG_TPB, 0, s>>>(*e, *nl, *in, (int)B, accumulate, norm_sq, roles);
+    });
+    FSRL_LAUNCH_CHECK();
+    return FSRL_OK;
+}
+}  // namespace fsrl
+
 extern "C" int fsrl_engine_wgrad(const fsrl_engine_t* e, const fsrl_netlist_t* nl, const fsrl_eng_input_t* in,
                                  int B, int accumulate, float* norm_sq, void* stream) {
     int rc = eng_check(e, nl);
     if (rc) return rc;
     FSRL_REQUIRE(in && in->xa && B >= 0 && B <= e->bmax, "engine_wgrad: bad input / B");
     if (B == 0) return FSRL_OK;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    ENG_DISPATCH_H(nl->nets[0].H, {
-        const dim3 g((HH / EWG_TK) * (HH / EWG_TO) + 2 * (HH / EWG_TO), nl->n);
-        eng_wgrad_kernel<HH><<<g, EWG_TPB, 0, s>>>(*e, *nl, *in, B, accumulate, norm_sq);
-    });
-    FSRL_LAUNCH_CHECK();
-    return FSRL_OK;
+    WgradRoles roles = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, 7};
+    return eng_wgrad_roles(e, nl, in, B, accumulate, norm_sq, roles, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fsrl_engine_adam(const fsrl_engine_t* e, const fsrl_netlist_t* nl, double lr, double beta1,

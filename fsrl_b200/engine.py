@@ -12,20 +12,24 @@ from .nets import Arena, NetSlot
 
 
 class EngineCtx:
-    def __init__(self, arena: Arena, bmax: int):
+    def __init__(self, arena: Arena, bmax: int, extra_slots: int = 0):
         self.arena = arena
         self.bmax = int(bmax)
         dev = arena.device
         H = arena.slots[0].H
         self.H = H
         self.slot_floats = _lib.lib.fsrl_engine_slot_floats(H, self.bmax)
-        n = len(arena.slots)
+        n = len(arena.slots) + int(extra_slots)
+        self._n_base = len(arena.slots)
         self.scratch = torch.zeros(n * self.slot_floats, dtype=torch.float32, device=dev)
-        self.w2n = torch.zeros(n * H * H, dtype=torch.float32, device=dev)
+        self.w2n = torch.zeros(len(arena.slots) * H * H, dtype=torch.float32, device=dev)
         self.adam_m = torch.zeros_like(arena.theta)
         self.adam_v = torch.zeros_like(arena.theta)
         self._index = {id(s): i for i, s in enumerate(arena.slots)}
         self.sync_mirror(arena.slots)
+
+    def extra_slot(self, k: int) -> int:
+        return self._n_base + k
 
     # ---- descriptors ----------------------------------------------------------------------------
     def engine(self) -> "_lib.Engine":

@@ -3,6 +3,7 @@ from .lagrangian_base import LagrangianPolicy
 from .ppo_lag import PPOLagrangian
 from .sac_lag import SACLagrangian
 from .ddpg_lag import DDPGLagrangian, GaussianNoise
+from .cpo import CPO
 
 __all__ = ["ActorCritic", "BasePolicy", "DeviceBatch", "LagrangianPolicy", "PPOLagrangian",
-           "SACLagrangian", "DDPGLagrangian", "GaussianNoise"]
+           "SACLagrangian", "DDPGLagrangian", "GaussianNoise", "CPO"]

@@ -271,6 +271,39 @@ int fsrl_offpolicy_steps(const fsrl_offpolicy_t* d, const int* idx_all, int n_st
                          long long critic_t0, long long actor_t0, unsigned long long noise_t0,
                          float* stats, void* stream);
 
+/* ---- a11: CPO (and the CG / Fisher machinery TRPO-Lag shares) ------------------------------------
+ * Replaces CPO._get_objective/_get_cost_surrogate/_MVP/_conjugate_gradients/policy_loss
+ * (fsrl/policy/cpo.py:163-204,234-351).  The batch is resident: a saved engine forward of the
+ * actor (P slot = actor.nets[0].slot) caches h1, h2 and the head output for all N rows;
+ * actor_r is the SAME network with a second scratch slot for the R-op quantities.
+ *   fsrl_cpo_head(mode)  per-row ratio / KL terms: sums[0..2] = sum ratio*adv_r, sum ratio*adv_c,
+ *                        sum kl; mode 1/2/3 also writes the head gradient of the objective,
+ *                        of -cost_surrogate, of the mean KL into the P slot's dout
+ *   fsrl_cpo_hvp         hv = Hessian(mean KL) v + damping v, exact (R-op), needs the P slot's
+ *                        dout / dz2 of the KL gradient pass
+ *   fsrl_vec_*           the O(P) vector arithmetic of conjugate gradients / line search */
+typedef struct fsrl_cpo {
+    fsrl_engine_t eng;
+    fsrl_netlist_t actor, actor_r;
+    long long N, ld;
+    int A, bounded;
+    float max_action, pad0;
+    const float *obs, *act, *logp_old, *mean_old, *std_old, *adv; /* adv: [2][ld] */
+    const int* perm;       /* optional minibatch row indices (NULL = rows 0..N-1) */
+    const float* out;      /* P slot head output  [bmax][16] */
+    float* dout;           /* P slot head gradient [bmax][16] */
+    const float* log_sigma;
+} fsrl_cpo_t;
+
+int fsrl_cpo_head(const fsrl_cpo_t* d, int mode, double* sums_dev4, void* stream);
+int fsrl_cpo_hvp(const fsrl_cpo_t* d, const float* v, float* v_w2n_scratch, float* hv, double damping,
+                 void* stream);
+int fsrl_vec_dot(const float* a, const float* b, long long n, double* out_dev, void* stream);
+int fsrl_vec_axpby(double a, const float* x, double b, float* y, long long n, void* stream);
+int fsrl_vec_add_scaled(const float* a, double s, const float* b, float* out, long long n, void* stream);
+int fsrl_engine_wgrad_to(const fsrl_engine_t* e, const fsrl_netlist_t* net1, const fsrl_eng_input_t* in,
+                         long long B, float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
