@@ -192,6 +192,8 @@ class CPO(BasePolicy):
             _lib.check(lib.fsrl_engine_wgrad_to(ctypes.byref(e), ctypes.byref(nl), ctypes.byref(inp), n, dst.data_ptr(), s))
             return sm
 
+        # entropy of the state-independent Gaussian BEFORE the step (:239)
+        ent = float((0.5 + 0.5 * np.log(2 * np.pi) + self.actor.sigma_param.detach().flatten()).sum().item())
         eng.forward([a], inp, n, save=True)
         sm = grad_into(1, v["g"])                                                   # :252
         adv_c = batch.adv[1] if perm is None else batch.adv[1][perm.long()]
@@ -272,7 +274,6 @@ class CPO(BasePolicy):
                     break
                 beta *= self._backtrack_coeff
             eng.sync_mirror([a])
-        ent = float((0.5 + 0.5 * np.log(2 * np.pi) + self.actor.sigma_param.detach().flatten()).sum().item())
         return {"loss/kl": float(kl), "loss/entropy": ent, "loss/rew_loss": float(objective),
                 "loss/cost_loss": float(cost_surrogate), "loss/optim_A": float(A_value),
                 "loss/optim_B": float(B_value), "loss/optim_C": float(c_value), "loss/optim_Q": float(scalar_q),
