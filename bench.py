@@ -96,8 +96,9 @@ def build(device, rank, envs=ENVS, hidden=HIDDEN):
     agent = PPOLagAgent(demo, logger=logger, cost_limit=10, device=device, seed=SEED, lr=5e-4,
                         hidden_sizes=hidden, max_grad_norm=0.5)      # cfg values (ppol_cfg.py:14-33)
     T = demo.spec.max_episode_steps
-    train_envs = fenvs.DeviceVectorEnv(TASK, envs, device=device, seed=SEED + 1000 * rank)
-    agent.policy.set_action_seed(SEED + 7 + 1000 * rank)
+    from fsrl_b200.parallel import shard_seed
+    train_envs = fenvs.DeviceVectorEnv(TASK, envs, device=device, seed=shard_seed(SEED + 1, rank))
+    agent.policy.set_action_seed(shard_seed(SEED + 7, rank))
     # fixed work per step: the KL early stop (ppo_lag.py:251-255) is disabled so that EVERY step
     # runs all `REPEAT` passes = 4 x 2400 minibatch updates (the most work the config can do)
     agent.policy._target_kl = float("inf")
@@ -168,7 +169,7 @@ def run_ours(args):
     agent, trainer, col, buf, T = build(device, rank)
     if world > 1:
         from fsrl_b200 import parallel
-        parallel.attach(agent.policy, dist)
+        parallel.attach(agent.policy, dist, device=device)
     steps_per_cycle = ENVS * T
 
     for _ in range(args.warmup):

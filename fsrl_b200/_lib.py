@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes
 import os
 
+import torch  # noqa: F401  (loads torch's bundled libnccl/cudart before ours resolve the same SONAMEs)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfsrl_b200.so")
 
@@ -166,6 +168,11 @@ SIGNATURES = {
                                  ctypes.c_longlong, c_f64, c_f64, c_vp, c_f64, c_vp]),
     "fsrl_engine_polyak": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(NetList), c_f64, c_vp]),
     "fsrl_engine_sync_mirror": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), c_vp]),
+    "fsrl_comm_unique_id": (c_int, [ctypes.c_char_p]),
+    "fsrl_comm_init": (c_int, [ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "fsrl_comm_destroy": (c_int, [c_vp]),
+    "fsrl_allreduce_fused": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp]),
+    "fsrl_allreduce_f64": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_cpo_head": (c_int, [ctypes.POINTER(Cpo), c_int, c_vp, c_vp]),
     "fsrl_cpo_hvp": (c_int, [ctypes.POINTER(Cpo), c_vp, c_vp, c_vp, c_f64, c_vp]),
     "fsrl_vec_dot": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),

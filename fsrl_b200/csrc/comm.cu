@@ -1,0 +1,59 @@
+// Multi-GPU plumbing for the data-parallel update: one process per GPU, each rank
+// owns its env shard and replay shard; per optimiser step ONE all-reduce of the flat gradient
+// buffer over NVLink/NVSwitch (NCCL), issued from the same C loop that launches the update
+// kernels so that no Python sits between the wgrad kernel, the collective and the Adam kernel.
+// The reference has no distributed code at all; this is the new engine's design.
+#include "common.cuh"
+#include "fsrl_b200.h"
+#include <nccl.h>
+#include <string.h>
+
+#define FSRL_NCCL(call)                                                                   \
+    do {                                                                                  \
+        ncclResult_t r__ = (call);                                                        \
+        if (r__ != ncclSuccess) {                                                         \
+            ::fsrl::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+            return FSRL_ECUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+extern "C" int fsrl_comm_unique_id(char* out128) {
+    FSRL_REQUIRE(out128 != nullptr, "comm: null id buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size changed");
+    ncclUniqueId id;
+    FSRL_NCCL(ncclGetUniqueId(&id));
+    memcpy(out128, &id, 128);
+    return FSRL_OK;
+}
+
+extern "C" int fsrl_comm_init(const char* id128, int rank, int world, void** comm_out) {
+    FSRL_REQUIRE(id128 && comm_out && world >= 1 && rank >= 0 && rank < world, "comm_init: bad arguments");
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t c;
+    FSRL_NCCL(ncclCommInitRank(&c, world, id, rank));
+    *comm_out = c;
+    return FSRL_OK;
+}
+
+extern "C" int fsrl_comm_destroy(void* comm) {
+    if (comm) FSRL_NCCL(ncclCommDestroy(static_cast<ncclComm_t>(comm)));
+    return FSRL_OK;
+}
+
+// in-place sum over ranks of n fp32 values (gradients ++ statistics in one flat buffer)
+extern "C" int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream) {
+    FSRL_REQUIRE(comm && buf && n >= 0, "allreduce: bad arguments");
+    if (n == 0) return FSRL_OK;
+    FSRL_NCCL(ncclAllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, static_cast<ncclComm_t>(comm),
+                            static_cast<cudaStream_t>(stream)));
+    return FSRL_OK;
+}
+
+extern "C" int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream) {
+    FSRL_REQUIRE(comm && buf && n >= 0, "allreduce: bad arguments");
+    if (n == 0) return FSRL_OK;
+    FSRL_NCCL(ncclAllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, static_cast<ncclComm_t>(comm),
+                            static_cast<cudaStream_t>(stream)));
+    return FSRL_OK;
+}

@@ -34,6 +34,8 @@ constexpr int DOUT_LD = 16;   // scratch row stride of dOut (cols [A, 2A) carry 
 __device__ long long g_dbg_clock[16];
 #define DBG_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
 
+__device__ __forceinline__ int slot_mb(const fsrl_ppo_update_t& u, int mb_off) { return mb_off / u.batch_size; }
+
 struct NetView {   // resolved pointers of one network inside the flat buffers
     Mlp3 m;
     const float* w2n;      // mirror [out][in] of w2t
@@ -107,7 +109,18 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         return id >= 0 ? u.obs + (size_t)id * D : nullptr;
     });
     // per-minibatch advantage normalisation (ppo_lag.py:178-182): mean, unbiased std, no eps
-    if (net == 0) {
+    if (net == 0 && u.moments != nullptr) {
+        // data-parallel run: sum / sum of squares of this minibatch were reduced over all ranks
+        // beforehand (ppo_adv_moments_kernel + one all-reduce per repeat)
+        if (tid < u.C) {
+            const double* mo = u.moments + ((size_t)slot_mb(u, mb_off) * 2 + tid) * 2;
+            const double nn = (double)B * (double)u.world;
+            const double mean = mo[0] / nn;
+            const double var = (mo[1] - nn * mean * mean) / (nn - 1.0);
+            s_mean[tid] = u.norm_adv ? (float)mean : 0.f;
+            s_rstd[tid] = u.norm_adv ? (float)(1.0 / sqrt(var)) : 1.0f;
+        }
+    } else if (net == 0) {
         for (int c = 0; c < u.C; ++c) {
             float s = 0.f;
             for (int i = tid; i < B; i += MLP_TPB) s += u.adv[(size_t)c * u.ld + perm[i]];
@@ -514,11 +527,12 @@ __global__ void __launch_bounds__(256)
 adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s, float eps,
             float neg_step, int slot, int n_plain_blocks) {
     __shared__ float tile[32][33];
-    float scale = 1.0f;
-    const float nsq = *u.norm_sq;
+    const float gs = (u.world > 1) ? 1.0f / (float)u.world : 1.0f;     // average the summed gradients
+    float scale = gs;
+    const float nsq = *u.norm_sq * gs * gs;
     if (u.max_grad_norm > 0.f) {
         const float coef = u.max_grad_norm / (sqrtf(nsq) + 1e-6f);
-        scale = fminf(coef, 1.0f);
+        scale = gs * fminf(coef, 1.0f);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && u.stats && slot >= 0)
         u.stats[(size_t)slot * FSRL_PPO_STATS + ST_GRADNORM] = sqrtf(nsq);
@@ -567,6 +581,46 @@ adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s,
     }
 }
 
+// sum of squares of the (all-reduced) gradient buffer -> *u.norm_sq
+__global__ void __launch_bounds__(1024) grad_norm_kernel(const fsrl_ppo_update_t u) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < u.n_params; i += 1024) { const float g = u.grad[i]; s += g * g; }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 32; ++w) t += red[w]; *u.norm_sq = t; }
+}
+
+// per-minibatch sum and sum of squares of the advantages (block b = minibatch b of the repeat)
+__global__ void __launch_bounds__(256) ppo_adv_moments_kernel(const fsrl_ppo_update_t u, long long n_total, int n_mb) {
+    __shared__ double red[2][8];
+    const int mb = blockIdx.x;
+    const long long off = (long long)mb * u.batch_size;
+    long long B = u.batch_size;
+    if (mb == n_mb - 1) B = n_total - off;
+    for (int c = 0; c < u.C; ++c) {
+        double s = 0.0, q = 0.0;
+        for (long long i = threadIdx.x; i < B; i += 256) {
+            const double a = (double)u.adv[(size_t)c * u.ld + u.perm[off + i]];
+            s += a; q += a * a;
+        }
+        s = warp_sum(s); q = warp_sum(q);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ts = 0.0, tq = 0.0;
+            for (int w = 0; w < 8; ++w) { ts += red[0][w]; tq += red[1][w]; }
+            u.moments_w[((size_t)mb * 2 + c) * 2] = ts;
+            u.moments_w[((size_t)mb * 2 + c) * 2 + 1] = tq;
+        }
+    }
+}
+
+extern "C" int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
+extern "C" int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
+
 template <int H>
 static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, int slot,
                                 long long adam_t, cudaStream_t s) {
@@ -583,6 +637,14 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
     const dim3 gB((H / WG_TK) * (H / WG_TO) + 2 * (H / WG_TO), u.n_nets);
     ppo_wgrad_kernel<H><<<gB, WG_TPB, 0, s>>>(u, mb_off, B);
     FSRL_LAUNCH_CHECK();
+    if (u.world > 1) {
+        // data parallel: ONE all-reduce of the flat gradient buffer per optimiser step, then the
+        // global norm of the reduced gradient (the local partial norms are meaningless now)
+        int rc = fsrl_allreduce_fused(u.comm, u.grad, u.n_params, s);
+        if (rc) return rc;
+        grad_norm_kernel<<<1, 1024, 0, s>>>(u);
+        FSRL_LAUNCH_CHECK();
+    }
     // torch.optim.Adam scalars (python doubles -> f32 at the op)
     const double b1 = u.beta1, b2 = u.beta2;
     const double bc1 = 1.0 - pow(b1, (double)adam_t), bc2 = 1.0 - pow(b2, (double)adam_t);
@@ -650,6 +712,17 @@ extern "C" int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int count = 0;
     const bool merge_last = (n_total % batch_size) > 0;       // tianshou Batch.split
+    FSRL_REQUIRE(u->world <= 1 || (u->comm && u->moments_w && u->batch_size == batch_size),
+                 "ppo: data-parallel run needs comm, moments buffer and batch_size in the descriptor");
+    if (u->world > 1) {
+        // every rank must run the same number of equally sized minibatches
+        FSRL_REQUIRE(!merge_last, "ppo: data-parallel run needs n_total %% batch_size == 0");
+        const int n_mb = (int)(n_total / batch_size);
+        ppo_adv_moments_kernel<<<n_mb, 256, 0, s>>>(*u, n_total, n_mb);
+        FSRL_LAUNCH_CHECK();
+        int rc2 = fsrl_allreduce_f64(u->comm, u->moments_w, (long long)n_mb * 4, s);
+        if (rc2) return rc2;
+    }
     for (long long off = 0; off < n_total; off += batch_size) {
         long long B = batch_size;
         bool last = false;

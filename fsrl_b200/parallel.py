@@ -1,0 +1,94 @@
+"""Data-parallel plumbing: one process per GPU, every rank owns E/G envs, its
+own rollout buffer and computes GAE locally (segments never cross envs).  Shared state is kept
+identical on all ranks by
+
+* per collect : one all-reduce of [sum cost, episodes, sum return, sum length] -> identical PID
+                multiplier everywhere (the reference's ``stats_train["cost"]`` becomes the global
+                mean episodic cost);
+* per repeat  : one all-reduce of the per-minibatch advantage moments, so the per-minibatch
+                normalisation (ppo_lag.py:178-182) is over the GLOBAL minibatch;
+* per step    : ONE NCCL all-reduce of the flat gradient buffer, issued from the C update loop
+                (csrc/ppo.cu) between the weight-gradient and Adam kernels;
+* per repeat  : the KL early-stop statistic is averaged so that all ranks stop together.
+
+The reference has no distributed code; this file is the new engine's design.
+Host-side scalar reductions go through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
+tests); gradients go through our own NCCL communicator created from a broadcast unique id.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+
+class DataParallel:
+    def __init__(self, dist, device: Optional[torch.device] = None, with_nccl: bool = True):
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.comm = None
+        if with_nccl and self.world > 1:
+            from . import _lib
+            buf = torch.zeros(128, dtype=torch.uint8, device=self.device)
+            if self.rank == 0:
+                raw = ctypes.create_string_buffer(128)
+                _lib.check(_lib.lib.fsrl_comm_unique_id(raw))
+                buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+            dist.broadcast(buf, src=0)
+            idb = bytes(buf.cpu().numpy().tobytes())
+            comm = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib.fsrl_comm_init(idb, self.rank, self.world, ctypes.byref(comm)))
+            self.comm = comm
+
+    # ---- host-side scalar reductions -----------------------------------------------------------
+    def all_sum(self, values) -> np.ndarray:
+        t = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def reduce_collect_stats(self, stats: Dict) -> Dict:
+        """Global view of one collect: episodic means over ALL ranks' episodes."""
+        n_ep, n_st = stats["n/ep"], stats["n/st"]
+        loc = [stats["total_cost"], n_ep, stats["rew"] * n_ep, stats["len"] * n_ep, n_st,
+               stats["truncated"] * n_ep, stats["terminated"] * n_ep]
+        g = self.all_sum(loc)
+        ep = max(g[1], 1.0)
+        out = dict(stats)
+        out.update({"total_cost": g[0], "n/ep": int(g[1]), "n/st": int(g[4]), "cost": g[0] / ep,
+                    "rew": g[2] / ep, "len": g[3] / ep, "truncated": g[5] / ep, "terminated": g[6] / ep,
+                    "local": stats})
+        return out
+
+    def mean_scalar(self, x: float) -> float:
+        return float(self.all_sum([x])[0] / self.world)
+
+    def broadcast_(self, t: torch.Tensor, src: int = 0) -> None:
+        self.dist.broadcast(t, src=src)
+
+
+def shard_seed(seed: int, rank: int) -> int:
+    """Independent env / noise streams per rank (same network init seed everywhere)."""
+    return (int(seed) + 1000003 * int(rank)) & 0xFFFFFFFF
+
+
+def attach(policy, dist, device=None) -> DataParallel:
+    """Make `policy` data parallel: broadcast rank 0's parameters, hook the collect-statistics
+    reduction into pre_update_fn, and hand the NCCL communicator to the update descriptor."""
+    device = device if device is not None else policy.device
+    dp = DataParallel(dist, device)
+    dp.broadcast_(policy.arena.theta)
+    if hasattr(policy, "_mirror_dirty"):
+        policy._mirror_dirty = True
+    policy._dp = dp
+    inner = policy.pre_update_fn
+
+    def pre_update_fn(stats_train, **kw):
+        return inner(stats_train=dp.reduce_collect_stats(stats_train), **kw)
+
+    policy.pre_update_fn = pre_update_fn
+    return dp

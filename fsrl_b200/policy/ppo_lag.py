@@ -122,6 +122,14 @@ class PPOLagrangian(LagrangianPolicy):
         u.use_lagrangian = int(self.use_lagrangian and self.critics_num > 1)
         g = self.optim.param_groups[0]
         u.lr, u.beta1, u.beta2, u.adam_eps = g["lr"], g["betas"][0], g["betas"][1], g["eps"]
+        dp = getattr(self, "_dp", None)
+        u.world = 1
+        if dp is not None and dp.world > 1:
+            n_mb = (batch.n + self._dp_batch - 1) // self._dp_batch
+            if getattr(self, "_moments", None) is None or self._moments.numel() < 4 * n_mb:
+                self._moments = torch.zeros(4 * n_mb, dtype=torch.float64, device=ar.device)
+            u.comm, u.world, u.batch_size = dp.comm, dp.world, self._dp_batch
+            u.moments_w = u.moments = self._moments.data_ptr()
         return u
 
     # -----------------------------------------------------------------------------------------------
@@ -135,6 +143,7 @@ class PPOLagrangian(LagrangianPolicy):
     def learn(self, batch: DeviceBatch, batch_size: int, repeat: int, **kwargs: Any) -> Dict[str, List[float]]:
         n = batch.n
         ar = self.arena
+        self._dp_batch = int(batch_size)
         self._ensure_update_state(batch_size, n, repeat)
         lib = _lib.lib
         stream = self._stream()
@@ -165,6 +174,8 @@ class PPOLagrangian(LagrangianPolicy):
                 rows.append(st)
                 slot += n_mb.value
                 approx_kl = float(st[:, 2].sum()) / (n_mb.value + 1e-7)                # :251
+                if getattr(self, "_dp", None) is not None:
+                    approx_kl = self._dp.mean_scalar(approx_kl)                          # all ranks stop together
                 if approx_kl > 1.5 * self._target_kl:
                     self.logger.print("Early stop at step %d due to reaching max kl." % step)
                     break

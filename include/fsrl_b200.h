@@ -158,6 +158,13 @@ typedef struct fsrl_ppo_update {
     float max_action, lagrangian, rescaling, pad0;
     int bounded, norm_adv, value_clip, use_lagrangian;
     double lr, beta1, beta2, adam_eps;
+    /* data-parallel run (world > 1): NCCL communicator, per-minibatch advantage moments
+     * [n_mb][2][2] (sum, sum of squares; reduced over ranks once per repeat); moments must
+     * alias moments_w */
+    void* comm;
+    double* moments_w;
+    const double* moments;
+    int world, batch_size;
 } fsrl_ppo_update_t;
 
 size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax);
@@ -303,6 +310,16 @@ int fsrl_vec_axpby(double a, const float* x, double b, float* y, long long n, vo
 int fsrl_vec_add_scaled(const float* a, double s, const float* b, float* out, long long n, void* stream);
 int fsrl_engine_wgrad_to(const fsrl_engine_t* e, const fsrl_netlist_t* net1, const fsrl_eng_input_t* in,
                          long long B, float* dst, void* stream);
+
+/* ---- 8(e): multi-GPU plumbing (one process per GPU, NCCL over NVLink) -------------------------
+ * The reference has no distributed code; ranks own env shards and replay shards, and per
+ * optimiser step ONE all-reduce of the flat gradient buffer is issued from the C update loop.
+ * The 128-byte unique id is created on rank 0 and broadcast by the host (torch.distributed). */
+int fsrl_comm_unique_id(char* out128);
+int fsrl_comm_init(const char* id128, int rank, int world, void** comm_out);
+int fsrl_comm_destroy(void* comm);
+int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
+int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
 
 #ifdef __cplusplus
 }
