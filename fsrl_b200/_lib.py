@@ -88,7 +88,9 @@ class PpoUpdate(ctypes.Structure):
                 ("rescaling", c_f32), ("pad0", c_f32),
                 ("bounded", c_int), ("norm_adv", c_int), ("value_clip", c_int),
                 ("use_lagrangian", c_int),
-                ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("adam_eps", c_f64)]
+                ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("adam_eps", c_f64),
+                ("comm", c_vp), ("moments_w", c_vp), ("moments", c_vp), ("world", c_int),
+                ("batch_size", c_int)]
 
 
 
@@ -151,6 +153,7 @@ PPO_STATS = 8
 SIGNATURES = {
     "fsrl_last_error": (ctypes.c_char_p, []),
     "fsrl_abi_version": (c_int, []),
+    "fsrl_abi_sizeof": (c_size, [c_int]),
     "fsrl_sm_count": (c_int, []),
     "fsrl_gae_dual_workspace_bytes": (c_size, [c_i64]),
     "fsrl_gae_dual": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_f64, c_f64,
@@ -203,6 +206,22 @@ def _bind():
 
 
 _bind()
+
+
+def _check_abi_sizes():
+    """The ctypes mirrors must have exactly the C sizes (a silent mismatch would let C read
+    past the end of a descriptor)."""
+    lib.fsrl_abi_sizeof.restype = c_size
+    lib.fsrl_abi_sizeof.argtypes = [c_int]
+    for which, cls in enumerate((Mlp3, CollectStats, Rollout, PpoUpdate, NetRef, NetList, Engine, EngInput,
+                                 OffPolicy, Cpo)):
+        want = lib.fsrl_abi_sizeof(which)
+        if want != ctypes.sizeof(cls):
+            raise ImportError(f"ABI mismatch: {cls.__name__} is {ctypes.sizeof(cls)} bytes in python, "
+                              f"{want} in libfsrl_b200.so -- rebuild / update fsrl_b200/_lib.py")
+
+
+_check_abi_sizes()
 
 
 def last_error() -> str:

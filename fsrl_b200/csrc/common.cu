@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: thread-local error text, version, device info.
 #include "common.cuh"
+#include "fsrl_b200.h"
 #include <stdarg.h>
 #include <string.h>
 
@@ -29,3 +30,20 @@ int sm_count() {
 extern "C" const char* fsrl_last_error(void) { return fsrl::g_err; }
 extern "C" int fsrl_abi_version(void) { return 1; }
 extern "C" int fsrl_sm_count(void) { return fsrl::sm_count(); }
+
+// sizes of the descriptor structs, checked against the ctypes mirrors at import time
+extern "C" size_t fsrl_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(fsrl_mlp3_t);
+        case 1: return sizeof(fsrl_collect_stats_t);
+        case 2: return sizeof(fsrl_rollout_t);
+        case 3: return sizeof(fsrl_ppo_update_t);
+        case 4: return sizeof(fsrl_netref_t);
+        case 5: return sizeof(fsrl_netlist_t);
+        case 6: return sizeof(fsrl_engine_t);
+        case 7: return sizeof(fsrl_eng_input_t);
+        case 8: return sizeof(fsrl_offpolicy_t);
+        case 9: return sizeof(fsrl_cpo_t);
+        default: return 0;
+    }
+}

@@ -32,6 +32,7 @@ extern "C" {
 /* ---- plumbing ------------------------------------------------------------------- */
 const char* fsrl_last_error(void);
 int fsrl_abi_version(void);
+size_t fsrl_abi_sizeof(int which); /* sizeof() of the descriptor structs, for binding self-checks */
 int fsrl_sm_count(void);
 
 /* ---- a6/a7: dual GAE(lambda) -------------------------------------------------------
