@@ -204,6 +204,8 @@ def run_ours(args):
     value = total_steps / (ms * 1e-3)
 
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     # ---- e2e: the same cycles through the public trainer API, wall-clock incl. every host<->device
     # copy the API performs (minibatch permutations up, statistics down) ----------------------------
@@ -251,7 +253,9 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_reference(sample_envs=args.cpu_envs, cycles=1)
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 # -------------------------------------------------------------------------------------------------
