@@ -131,7 +131,7 @@ def phase_times(agent, col, buf, iters=200):
     perm = torch.randperm(n, device=pol.device).to(torch.int32)
     pol._ensure_update_state(BATCH, n, 1)
     u = pol._descriptor(batch, perm)
-    ms = (ctypes.c_float * 3)()
+    ms = (ctypes.c_float * 4)()
     _lib.check(_lib.lib.fsrl_ppo_phase_times(ctypes.byref(u), BATCH, iters, ms, torch.cuda.current_stream().cuda_stream))
     return [float(x) for x in ms]
 
@@ -219,7 +219,7 @@ def run_ours(args):
     D, A, H = 8, 2, HIDDEN[0]
     fl_net = lambda out: 2 * BATCH * (D * H + H * H + H * out) + 2 * BATCH * (H * out + H * H)
     flops_a = fl_net(A) + 2 * fl_net(1)
-    ach = flops_a / (ph[0] * 1e-3) / 1e12
+    ach = flops_a / ((ph[0] + ph[1]) * 1e-3) / 1e12
     gms, gn = gae_time(buf, agent.policy)
     gae_bytes = gn * 42
     launches = args.steps * (T * 2 + 2 + 6 + REPEAT * n_mb * 3 + 4)
@@ -240,11 +240,11 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "how": "wall clock around the same K trainer cycles"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "ppo_fwdbwd_kernel<256>", "bound": "tensor", "achieved": ach,
+        "roofline": {"kernel": "ppo_fwd_kernel<256> + ppo_bwd_kernel<256>", "bound": "tensor", "achieved": ach,
                      "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
                      "traffic": None, "peak_source": how + " bf16 burst",
                      "note": "fp32 SIMT FMA kernel (no tensor cores yet); flops = fwd+bwd of 3 MLPs on a 256-row minibatch",
-                     "phase_ms": {"fwdbwd": ph[0], "wgrad": ph[1], "adam": ph[2]}},
+                     "phase_ms": {"fwd": ph[0], "bwd": ph[1], "wgrad": ph[2], "adam": ph[3]}},
         "roofline_gae": {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm",
                          "achieved": gae_bytes / (gms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": gae_bytes / (gms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gms,

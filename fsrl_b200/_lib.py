@@ -90,7 +90,7 @@ class PpoUpdate(ctypes.Structure):
                 ("use_lagrangian", c_int),
                 ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("adam_eps", c_f64),
                 ("comm", c_vp), ("moments_w", c_vp), ("moments", c_vp), ("world", c_int),
-                ("batch_size", c_int)]
+                ("batch_size", c_int), ("gather", c_vp), ("mb_stats", c_vp), ("barrier", c_vp)]
 
 
 
@@ -189,6 +189,7 @@ SIGNATURES = {
     "fsrl_ppo_scratch_floats": (c_size, [c_int, c_int, c_int]),
     "fsrl_ppo_sync_mirror": (c_int, [ctypes.POINTER(PpoUpdate), c_vp]),
     "fsrl_debug_clocks": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
+    "fsrl_debug_cta_cycles": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "fsrl_ppo_phase_times": (c_int, [ctypes.POINTER(PpoUpdate), c_int, c_int, ctypes.POINTER(c_f32), c_vp]),
     "fsrl_ppo_lag_epoch": (c_int, [ctypes.POINTER(PpoUpdate), ctypes.c_longlong, c_int, c_int,
                                    ctypes.c_longlong, ctypes.POINTER(c_int), c_vp]),

@@ -184,6 +184,135 @@ __device__ __forceinline__ void tc_init_bias(float (&c)[MlpTile<H>::MT][MlpTile<
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Column-slab GEMM: a CTA computes only NS of the H output columns (the minibatch kernels split
+// every layer's N dimension over H/NS CTAs to put 4x more SMs on the same tiny problem).  The
+// K range is split across the 8 warps (each warp owns all NS columns of its K/8 slice, so no
+// operand is loaded twice), partial tiles are summed through shared memory.
+// -------------------------------------------------------------------------------------------------
+constexpr int SLAB_NS = 64;
+constexpr int SLAB_LDB = SLAB_NS + 8;      // conflict-free B fragments
+constexpr int SLAB_LDR = SLAB_NS + 4;
+
+template <int H>
+__host__ __device__ constexpr size_t slab_b_floats() { return (size_t)H * SLAB_LDB; }
+template <int H>
+__host__ __device__ constexpr size_t slab_red_floats() { return (size_t)8 * MlpTile<H>::R * SLAB_LDR; }
+// one buffer serves as B slab and (afterwards) as the cross-warp reduce buffer
+template <int H>
+__host__ __device__ constexpr size_t slab_buf_floats() {
+    return slab_b_floats<H>() > slab_red_floats<H>() ? slab_b_floats<H>() : slab_red_floats<H>();
+}
+
+// whole [H][NS] slab of a row-major matrix (row stride gld, first column c0) -> bs via cp.async
+template <int H>
+__device__ __forceinline__ void slab_load(const float* W, int gld, int c0, float* bs) {
+    constexpr int SEG = SLAB_NS / 4;
+    for (int i = threadIdx.x; i < H * SEG; i += MLP_TPB) {
+        const int k = i / SEG, sg = i % SEG;
+        __pipeline_memcpy_async(bs + (size_t)k * SLAB_LDB + 4 * sg, W + (size_t)k * gld + c0 + 4 * sg, 16);
+    }
+    __pipeline_commit();
+}
+
+// out[row][col] = sum_k A[row][k] * bs[k][col]; epi(row, col4, float4) is called once per 4 outputs.
+// `red` may alias `bs` (a barrier separates the last read of bs from the first write of red).
+template <int H, class F>
+__device__ __forceinline__ void slab_gemm(const float* A, int lda, const float* bs, float* red, F epi) {
+    using TT = MlpTile<H>;
+    constexpr int NTS = SLAB_NS / 8;
+    constexpr int KW = H / 8;                      // k range per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float c[TT::MT][NTS][4];
+#pragma unroll
+    for (int mt = 0; mt < TT::MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) { c[mt][nt][0] = c[mt][nt][1] = c[mt][nt][2] = c[mt][nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < KW; ks += 8) {
+        const int k0 = warp * KW + ks;
+        uint32_t bh[NTS][2], bl[NTS][2];
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+            split_tf32(bs[(size_t)(k0 + t) * SLAB_LDB + 8 * nt + g], bh[nt][0], bl[nt][0]);
+            split_tf32(bs[(size_t)(k0 + t + 4) * SLAB_LDB + 8 * nt + g], bh[nt][1], bl[nt][1]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < TT::MT; ++mt) {
+            uint32_t ah[4], al[4];
+            const float* a = A + (size_t)(16 * mt + g) * lda + k0 + t;
+            split_tf32(a[0], ah[0], al[0]);
+            split_tf32(a[(size_t)8 * lda], ah[1], al[1]);
+            split_tf32(a[4], ah[2], al[2]);
+            split_tf32(a[(size_t)8 * lda + 4], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < NTS; ++nt) {
+                mma_tf32(c[mt][nt], al, bh[nt]);
+                mma_tf32(c[mt][nt], ah, bl[nt]);
+                mma_tf32(c[mt][nt], ah, bh[nt]);
+            }
+        }
+    }
+    __syncthreads();                               // all warps done reading bs (red may alias it)
+    float* mine = red + (size_t)warp * TT::R * SLAB_LDR;
+#pragma unroll
+    for (int mt = 0; mt < TT::MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+            *reinterpret_cast<float2*>(mine + (size_t)(16 * mt + g) * SLAB_LDR + 8 * nt + 2 * t) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+            *reinterpret_cast<float2*>(mine + (size_t)(16 * mt + g + 8) * SLAB_LDR + 8 * nt + 2 * t) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < TT::R * (SLAB_NS / 4); e += MLP_TPB) {
+        const int row = e / (SLAB_NS / 4), c4 = (e % (SLAB_NS / 4)) * 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float4 v = *reinterpret_cast<const float4*>(red + ((size_t)w * TT::R + row) * SLAB_LDR + c4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        epi(row, c4, s);
+    }
+}
+
+// c += A[.., k] * W[k][warp cols] with B fragments read straight from global (small K: layer 1)
+template <int H>
+__device__ __forceinline__ void tc_gemm_direct(float (&c)[MlpTile<H>::MT][MlpTile<H>::NT][4], const float* A,
+                                               int lda, int K, const float* W) {
+    using TT = MlpTile<H>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int n0 = warp * TT::WN;
+    const int Kp = (K + 7) & ~7;
+    for (int k0 = 0; k0 < Kp; k0 += 8) {
+        uint32_t bh[TT::NT][2], bl[TT::NT][2];
+#pragma unroll
+        for (int nt = 0; nt < TT::NT; ++nt) {
+            const float w0 = (k0 + t < K) ? __ldg(W + (size_t)(k0 + t) * H + n0 + 8 * nt + g) : 0.f;
+            const float w1 = (k0 + t + 4 < K) ? __ldg(W + (size_t)(k0 + t + 4) * H + n0 + 8 * nt + g) : 0.f;
+            split_tf32(w0, bh[nt][0], bl[nt][0]);
+            split_tf32(w1, bh[nt][1], bl[nt][1]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < TT::MT; ++mt) {
+            uint32_t ah[4], al[4];
+            const float* a = A + (size_t)(16 * mt + g) * lda + k0 + t;
+            split_tf32(a[0], ah[0], al[0]);
+            split_tf32(a[(size_t)8 * lda], ah[1], al[1]);
+            split_tf32(a[4], ah[2], al[2]);
+            split_tf32(a[(size_t)8 * lda + 4], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < TT::NT; ++nt) {
+                mma_tf32(c[mt][nt], al, bh[nt]);
+                mma_tf32(c[mt][nt], ah, bl[nt]);
+                mma_tf32(c[mt][nt], ah, bh[nt]);
+            }
+        }
+    }
+}
+
 // Shared-memory carve-up used by every kernel built on these blocks
 template <int H>
 struct MlpSmem {

@@ -10,10 +10,11 @@
 //   /root/reference/fsrl/policy/ppo_lag.py:223-247  forward/backward/clip_grad_norm_/Adam
 //   /root/reference/fsrl/policy/lagrangian_base.py:145-166  safety_loss
 //
-// Phase A (ppo_fwdbwd): grid (row tiles, nets).  Gathers the minibatch rows by permuted
-//   index, runs the fused MLP forward (mlp.cuh), evaluates the loss gradient at the head and
-//   back-propagates to dZ2 / dZ1; activations needed for the weight gradients go to an
-//   L2-resident scratch.
+// Phase A (ppo_fwd + ppo_bwd): grid (row tiles, column slabs, nets).  The permuted batch is
+//   gathered once per repeat into contiguous arrays; ppo_fwd runs layers 1-2 with the N
+//   dimension split over H/64 CTAs, ppo_bwd evaluates the head, the loss gradient and
+//   back-propagates to dZ2 / dZ1 (again one column slab per CTA); activations needed for the
+//   weight gradients go to an L2-resident scratch.
 // Phase B (ppo_wgrad): weight gradients as outer-product accumulations over the minibatch,
 //   each CTA owning a 32x64 tile of dW2t (no cross-CTA reduction), plus three small CTAs per
 //   net for layer 1 / layer 3 / biases; sum of squares for the global norm via one atomic per
@@ -32,7 +33,9 @@ constexpr float LOG_SQRT_2PI_P = 0.9189385332046727f;
 constexpr int DOUT_LD = 16;   // scratch row stride of dOut (cols [A, 2A) carry dlog_sigma)
 
 __device__ long long g_dbg_clock[16];
-#define DBG_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
+__device__ long long g_dbg_cta[512];
+#define DBG_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
+#define DBG_W(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
 
 __device__ __forceinline__ int slot_mb(const fsrl_ppo_update_t& u, int mb_off) { return mb_off / u.batch_size; }
 
@@ -79,82 +82,166 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase A
+// Phase A, split in two launches so that every layer's N dimension is spread over H/64 CTAs
+// (grid = row tiles x column slabs x nets = 192 CTAs for B = 256, H = 256):
+//   A1 ppo_fwd : x -> h1 (full, tiny K) -> h2[:, slab]           (scratch: h1, h2)
+//   A2 ppo_bwd : h2 (full) -> head -> loss gradient -> dz2 (full) -> dz1[:, slab]
+// Rows are addressed through row_of(): the epoch driver first gathers the permuted batch into
+// contiguous arrays (u.perm == nullptr afterwards), so minibatch rows are coalesced.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long row_of(const fsrl_ppo_update_t& u, int mb_off, int i) {
+    return u.perm ? (long long)u.perm[mb_off + i] : (long long)(mb_off + i);
+}
+
 template <int H>
 __global__ void __launch_bounds__(MLP_TPB)
-ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
+ppo_fwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     using TT = MlpTile<H>;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
-    const int net = blockIdx.y;
+    const int net = blockIdx.z, slab = blockIdx.y;
     const int r0 = blockIdx.x * TT::R;
+    const int c0 = slab * SLAB_NS;
     const int D = u.D;
+    const int inp = TT::in_pad(D);
     const NetView nv = net_view(u, net);
-    const MlpSmem<H> sm(smem, D, nv.m.out);
-    float* dz = sm.end(nv.m.out);                     // [R][LDA]
-    float* sdout = dz + (size_t)TT::R * TT::LDA;      // [R][DOUT_LD]
-    __shared__ int s_idx[64];
-    __shared__ float s_red[MLP_TPB / 32];
-    __shared__ float s_mean[2], s_rstd[2];
-
-    DBG_T(0);
-    const int* perm = u.perm + mb_off;
-    if (net == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by phase C of the previous step
-
-    if (tid < TT::R) s_idx[tid] = (r0 + tid < B) ? perm[r0 + tid] : -1;
-    __syncthreads();
-    mlp_stage_rows<H>(sm, D, [&](int r) -> const float* {
-        const int id = s_idx[r];
-        return id >= 0 ? u.obs + (size_t)id * D : nullptr;
-    });
-    // per-minibatch advantage normalisation (ppo_lag.py:178-182): mean, unbiased std, no eps
-    if (net == 0 && u.moments != nullptr) {
-        // data-parallel run: sum / sum of squares of this minibatch were reduced over all ranks
-        // beforehand (ppo_adv_moments_kernel + one all-reduce per repeat)
-        if (tid < u.C) {
-            const double* mo = u.moments + ((size_t)slot_mb(u, mb_off) * 2 + tid) * 2;
-            const double nn = (double)B * (double)u.world;
-            const double mean = mo[0] / nn;
-            const double var = (mo[1] - nn * mean * mean) / (nn - 1.0);
-            s_mean[tid] = u.norm_adv ? (float)mean : 0.f;
-            s_rstd[tid] = u.norm_adv ? (float)(1.0 / sqrt(var)) : 1.0f;
-        }
-    } else if (net == 0) {
-        for (int c = 0; c < u.C; ++c) {
-            float s = 0.f;
-            for (int i = tid; i < B; i += MLP_TPB) s += u.adv[(size_t)c * u.ld + perm[i]];
-            const float mean = block_sum_256(s, s_red) / (float)B;
-            float q = 0.f;
-            for (int i = tid; i < B; i += MLP_TPB) {
-                const float d = u.adv[(size_t)c * u.ld + perm[i]] - mean;
-                q += d * d;
-            }
-            const float var = block_sum_256(q, s_red) / (float)(B - 1);
-            if (tid == 0) {
-                s_mean[c] = u.norm_adv ? mean : 0.f;
-                s_rstd[c] = u.norm_adv ? 1.0f / sqrtf(var) : 1.0f;
-            }
-        }
+    float* xs = smem;                                   // [R][inp]
+    float* h1 = xs + (size_t)TT::R * inp;               // [R][LDA]
+    float* bs = h1 + (size_t)TT::R * TT::LDA;           // [H][SLAB_LDB]  (aliased by the reduce buffer)
+    if (net == 0 && slab == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by the previous step's Adam
+    slab_load<H>(nv.m.w2t, H, c0, bs);                  // in flight during layer 1
+    for (int i = tid; i < TT::R * inp; i += MLP_TPB) {
+        const int r = i / inp, k = i % inp;
+        xs[i] = (r0 + r < B && k < D) ? u.obs[(size_t)row_of(u, mb_off, r0 + r) * D + k] : 0.f;
     }
     __syncthreads();
-    DBG_T(1);
+    float c[TT::MT][TT::NT][4];
+    tc_init_bias<H>(c, nv.m.b1);
+    tc_gemm_direct<H>(c, xs, inp, D, nv.m.w1t);
+    tc_foreach<H>(c, [&](int row, int col, float v0, float v1) {
+        const float2 h = make_float2(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+        *reinterpret_cast<float2*>(h1 + (size_t)row * TT::LDA + col) = h;
+        if (slab == 0 && r0 + row < u.bmax) *reinterpret_cast<float2*>(nv.s_h1 + (size_t)(r0 + row) * H + col) = h;
+    });
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    slab_gemm<H>(h1, TT::LDA, bs, bs, [&](int row, int c4, float4 v) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(nv.m.b2 + c0 + c4));
+        if (r0 + row < u.bmax)
+            *reinterpret_cast<float4*>(nv.s_h2 + (size_t)(r0 + row) * H + c0 + c4) =
+                make_float4(fmaxf(v.x + b.x, 0.f), fmaxf(v.y + b.y, 0.f), fmaxf(v.z + b.z, 0.f), fmaxf(v.w + b.w, 0.f));
+    });
+}
 
-    mlp_hidden_forward<H>(nv.m, sm);
-    DBG_T(2);
-    float out[MLP_MAX_OUT];
-    mlp_head_forward<H>(nv.m, sm, out);
-    DBG_T(3);
+// per-row head dot product  out[j] = sum_k h2[k] * w3s[k][j]  over this lane's k subset, with the
+// column loop bounded at compile time (OUTP = next power of two >= wout)
+template <int OUTP>
+__device__ __forceinline__ void head_dot(const float* __restrict__ hrow, const float* __restrict__ w3s, int wout,
+                                         int part, int parts, int H, float* out) {
+    float acc[OUTP];
+#pragma unroll
+    for (int j = 0; j < OUTP; ++j) acc[j] = 0.f;
+    for (int k = part; k < H; k += parts) {
+        const float x = hrow[k];
+        const float* w = w3s + (size_t)k * wout;
+#pragma unroll
+        for (int j = 0; j < OUTP; ++j)
+            if (j < wout) acc[j] = fmaf(x, w[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < OUTP; ++j) out[j] = acc[j];
+}
 
-    // ---- loss gradient at the head: one thread per row -----------------------------------------
+template <int H>
+__global__ void __launch_bounds__(MLP_TPB)
+ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
+    using TT = MlpTile<H>;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int net = blockIdx.z, slab = blockIdx.y;
+    const int r0 = blockIdx.x * TT::R;
+    const int c0 = slab * SLAB_NS;
+    const NetView nv = net_view(u, net);
+    const int wout = nv.m.out;
+    float* h2 = smem;                                   // [R][LDA]
+    float* dz = h2 + (size_t)TT::R * TT::LDA;           // [R][LDA]
+    float* bs = dz + (size_t)TT::R * TT::LDA;           // [H][SLAB_LDB]
+    float* w3s = bs + slab_buf_floats<H>();             // [H][out]
+    float* sdout = w3s + (size_t)H * wout;              // [R][DOUT_LD]
+    __shared__ float s_red[MLP_TPB / 32];
+    __shared__ float s_mean[2], s_rstd[2];
+    DBG_T(0);
+    // h2 tile first (needed first), then the W2 slab: both in flight while the scalars below load
+    for (int el = tid; el < TT::R * (H / 4); el += MLP_TPB) {
+        const int row = el / (H / 4), k4 = (el % (H / 4)) * 4;
+        float* dst = h2 + (size_t)row * TT::LDA + k4;
+        if (r0 + row < B) __pipeline_memcpy_async(dst, nv.s_h2 + (size_t)(r0 + row) * H + k4, 16);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __pipeline_commit();
+    slab_load<H>(nv.w2n, H, c0, bs);                    // W2 in [out][in] layout: rows o, columns k-slab
+    for (int i = tid; i < H * wout; i += MLP_TPB) w3s[i] = __ldg(nv.m.w3t + i);
+    // per-row scalars of the loss: issued now, consumed after the head
     const int r = tid / TT::PARTS, part = tid % TT::PARTS;
+    const bool row_ok = (part == 0) && (r0 + r < B);
+    const long long id = row_ok ? row_of(u, mb_off, r0 + r) : 0;
+    float p_act[8], p_lpo = 0.f, p_adv0 = 0.f, p_adv1 = 0.f, p_ret = 0.f, p_val = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p_act[j] = 0.f;
+    if (row_ok) {
+        if (net == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < u.A) p_act[j] = u.act[(size_t)id * u.A + j];
+            p_lpo = u.logp_old[id];
+            p_adv0 = u.adv[id];
+            if (u.C > 1) p_adv1 = u.adv[(size_t)u.ld + id];
+        } else {
+            p_ret = u.ret[(size_t)(net - 1) * u.ld + id];
+            if (u.value_clip) p_val = u.values[(size_t)(net - 1) * u.ld + id];
+        }
+    }
+    DBG_T(1);
+    // per-minibatch advantage normalisation (ppo_lag.py:178-182): mean / 1/std of this minibatch
+    // were computed for every minibatch of the repeat by ppo_adv_stats_kernel
+    if (net == 0 && tid < u.C) {
+        const float* ms = u.mb_stats + ((size_t)slot_mb(u, mb_off) * 2 + tid) * 2;
+        s_mean[tid] = ms[0];
+        s_rstd[tid] = ms[1];
+    }
+    __pipeline_wait_prior(1);                            // h2 tile landed (the slab may still be in flight)
+    __syncthreads();
+
+    DBG_T(2);
+    // ---- head forward (every slab CTA recomputes it: H x out MACs per row, negligible) -----------
+    float out[MLP_MAX_OUT];
+#pragma unroll
+    for (int j = 0; j < MLP_MAX_OUT; ++j) out[j] = 0.f;
+    {
+        const float* hrow = h2 + (size_t)r * TT::LDA;
+        if (wout <= 1) head_dot<1>(hrow, w3s, wout, part, TT::PARTS, H, out);
+        else if (wout <= 2) head_dot<2>(hrow, w3s, wout, part, TT::PARTS, H, out);
+        else if (wout <= 4) head_dot<4>(hrow, w3s, wout, part, TT::PARTS, H, out);
+        else if (wout <= 8) head_dot<8>(hrow, w3s, wout, part, TT::PARTS, H, out);
+        else head_dot<16>(hrow, w3s, wout, part, TT::PARTS, H, out);
+    }
+#pragma unroll
+    for (int j = 0; j < MLP_MAX_OUT; ++j) {
+        if (j < wout) {
+            float v = out[j];
+#pragma unroll
+            for (int o = TT::PARTS / 2; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, TT::PARTS);
+            out[j] = v + __ldg(nv.m.b3 + j);
+        }
+    }
+
+    DBG_T(3);
+    // ---- loss gradient at the head: one thread per row -----------------------------------------
     float st_a = 0.f, st_b = 0.f, st_c = 0.f, st_d = 0.f;     // per-thread stat partials
     if (part == 0) {
         float dd[DOUT_LD];
 #pragma unroll
         for (int j = 0; j < DOUT_LD; ++j) dd[j] = 0.f;
-        const int id = s_idx[r];
-        if (id >= 0) {
+        if (row_ok) {
             const float invB = 1.0f / (float)B;
             if (net == 0) {
                 const int A = u.A;
@@ -166,13 +253,13 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
                         const float mu = u.bounded ? u.max_action * t : out[j];
                         dmu[j] = u.bounded ? u.max_action * (1.0f - t * t) : 1.0f;
                         sg[j] = expf(nv.log_sigma[j]);
-                        zz[j] = (u.act[(size_t)id * A + j] - mu) / sg[j];
+                        zz[j] = (p_act[j] - mu) / sg[j];
                         logp += -0.5f * zz[j] * zz[j] - nv.log_sigma[j] - LOG_SQRT_2PI_P;
                     }
                 }
-                const float lpo = u.logp_old[id];
+                const float lpo = p_lpo;
                 const float ratio = expf(logp - lpo);
-                const float ar = (u.adv[id] - s_mean[0]) * s_rstd[0];
+                const float ar = (p_adv0 - s_mean[0]) * s_rstd[0];
                 const float surr1 = ratio * ar;
                 const float rc = fminf(fmaxf(ratio, 1.0f - u.eps_clip), 1.0f + u.eps_clip);
                 const float surr2 = rc * ar;
@@ -191,7 +278,7 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
                 }
                 float g_saf = 0.f, lsaf = 0.f;
                 if (u.use_lagrangian && u.C > 1) {
-                    const float ac = (u.adv[(size_t)u.ld + id] - s_mean[1]) * s_rstd[1];
+                    const float ac = (p_adv1 - s_mean[1]) * s_rstd[1];
                     g_saf = ac * u.lagrangian;          // d mean(ratio*adv_c*lambda) / d ratio
                     lsaf = ratio * ac * u.lagrangian;
                 }
@@ -206,12 +293,11 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
                 }
                 st_a = lrew * invB; st_b = lsaf * invB; st_c = (lpo - logp) * invB;
             } else {
-                const int c = net - 1;
                 const float v = out[0];
-                const float ret = u.ret[(size_t)c * u.ld + id];
+                const float ret = p_ret;
                 float lv, gv;
                 if (u.value_clip) {
-                    const float vt = u.values[(size_t)c * u.ld + id];
+                    const float vt = p_val;
                     const float dv = fminf(fmaxf(v - vt, -u.eps_clip), u.eps_clip);
                     const float vc = vt + dv;
                     const float vf1 = (ret - v) * (ret - v), vf2 = (ret - vc) * (ret - vc);
@@ -229,7 +315,7 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         }
 #pragma unroll
         for (int j = 0; j < DOUT_LD; ++j) sdout[r * DOUT_LD + j] = dd[j];
-        if (r0 + r < u.bmax) {
+        if (slab == 0 && r0 + r < u.bmax) {
 #pragma unroll
             for (int j = 0; j < DOUT_LD; j += 4)
                 *reinterpret_cast<float4*>(nv.s_dout + (size_t)(r0 + r) * DOUT_LD + j) =
@@ -237,8 +323,8 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         }
     }
     DBG_T(4);
-    // minibatch statistics (loss/actor_rew, actor_safety, kl, vf_i): one atomic per CTA each
-    {
+    // minibatch statistics (loss/actor_rew, actor_safety, kl, vf_i): one atomic per row-tile CTA
+    if (slab == 0) {
         float* stat = u.stats + (size_t)slot * FSRL_PPO_STATS;
         if (net == 0) {
             const float a = block_sum_256(st_a, s_red), b = block_sum_256(st_b, s_red), c = block_sum_256(st_c, s_red);
@@ -258,265 +344,377 @@ ppo_fwdbwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
     __syncthreads();
 
     DBG_T(5);
-    // ---- backward through layer 3 and ReLU 2; spill h1 / h2 / dz2 for the weight gradients ------
+    // ---- backward through layer 3 and ReLU 2 (full width, redundant per slab: H x out per row) ----
     const int nout = (net == 0) ? u.A : 1;       // head columns that feed w3t (mu only)
-    const int wout = nv.m.out;
     for (int e = tid; e < TT::R * (H / 4); e += MLP_TPB) {
         const int row = e / (H / 4), k4 = (e % (H / 4)) * 4;
         float a4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nout; ++j) {
             const float g = sdout[row * DOUT_LD + j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a4[q] = fmaf(g, sm.w3s[(size_t)(k4 + q) * wout + j], a4[q]);
+            for (int q = 0; q < 4; ++q) a4[q] = fmaf(g, w3s[(size_t)(k4 + q) * wout + j], a4[q]);
         }
-        const float4 hv = *reinterpret_cast<const float4*>(sm.h2 + (size_t)row * TT::LDA + k4);
+        const float4 hv = *reinterpret_cast<const float4*>(h2 + (size_t)row * TT::LDA + k4);
         const float4 g4 = make_float4(hv.x > 0.f ? a4[0] : 0.f, hv.y > 0.f ? a4[1] : 0.f,
                                       hv.z > 0.f ? a4[2] : 0.f, hv.w > 0.f ? a4[3] : 0.f);
         *reinterpret_cast<float4*>(dz + (size_t)row * TT::LDA + k4) = g4;
-        if (r0 + row < u.bmax) {
-            *reinterpret_cast<float4*>(nv.s_dz2 + (size_t)(r0 + row) * H + k4) = g4;
-            *reinterpret_cast<float4*>(nv.s_h2 + (size_t)(r0 + row) * H + k4) = hv;
-            *reinterpret_cast<float4*>(nv.s_h1 + (size_t)(r0 + row) * H + k4) =
-                *reinterpret_cast<const float4*>(sm.h1 + (size_t)row * TT::LDA + k4);
-        }
+        if (slab == 0 && r0 + row < u.bmax) *reinterpret_cast<float4*>(nv.s_dz2 + (size_t)(r0 + row) * H + k4) = g4;
     }
     DBG_T(6);
-    // ---- backward through layer 2: dH1 = dZ2 . W2 (W2n is [out][in]) then ReLU 1 ------------------
-    {
-        float c[TT::MT][TT::NT][4];
-        tc_init_bias<H>(c, nullptr);
-        tc_gemm<H>(c, dz, TT::LDA, H, nv.w2n, sm.wst, false);
-        tc_foreach<H>(c, [&](int row, int col, float v0, float v1) {
-            if (r0 + row < u.bmax) {
-                const float2 hv = *reinterpret_cast<const float2*>(sm.h1 + (size_t)row * TT::LDA + col);
-                *reinterpret_cast<float2*>(nv.s_dz1 + (size_t)(r0 + row) * H + col) =
-                    make_float2(hv.x > 0.f ? v0 : 0.f, hv.y > 0.f ? v1 : 0.f);
-            }
-        });
-    }
+    __pipeline_wait_prior(0);
+    __syncthreads();
     DBG_T(7);
+    // ---- backward through layer 2: dH1[:, slab] = dZ2 . W2[:, slab], then ReLU 1 -------------------
+    slab_gemm<H>(dz, TT::LDA, bs, bs, [&](int row, int c4, float4 v) {
+        if (r0 + row < u.bmax) {
+            const float4 hv = __ldcg(reinterpret_cast<const float4*>(nv.s_h1 + (size_t)(r0 + row) * H + c0 + c4));
+            *reinterpret_cast<float4*>(nv.s_dz1 + (size_t)(r0 + row) * H + c0 + c4) =
+                make_float4(hv.x > 0.f ? v.x : 0.f, hv.y > 0.f ? v.y : 0.f, hv.z > 0.f ? v.z : 0.f, hv.w > 0.f ? v.w : 0.f);
+        }
+    });
+    DBG_T(8);
+}
+
+// contiguous copy of the permuted batch (one launch per repeat): minibatch k is then rows
+// [k*bs, (k+1)*bs) of g = obs[N][D] | act[N][A] | logp[N] | adv[C][N] | ret[C][N] | values[C][N]
+__global__ void ppo_gather_kernel(const fsrl_ppo_update_t u, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = u.perm[i];
+    const int D = u.D, A = u.A, C = u.C;
+    float* g = u.gather;
+    for (int k = 0; k < D; ++k) g[i * D + k] = u.obs[r * D + k];
+    g += n * D;
+    for (int k = 0; k < A; ++k) g[i * A + k] = u.act[r * A + k];
+    g += n * A;
+    g[i] = u.logp_old[r];
+    g += n;
+    for (int c = 0; c < C; ++c) g[(size_t)c * n + i] = u.adv[(size_t)c * u.ld + r];
+    g += (size_t)C * n;
+    for (int c = 0; c < C; ++c) g[(size_t)c * n + i] = u.ret[(size_t)c * u.ld + r];
+    g += (size_t)C * n;
+    if (u.values) for (int c = 0; c < C; ++c) g[(size_t)c * n + i] = u.values[(size_t)c * u.ld + r];
 }
 
 // ------------------------------------------------------------------------------------------
 // Phase B: weight gradients
 // ------------------------------------------------------------------------------------------
-constexpr int WG_TPB = 128, WG_TK = 32, WG_TO = 64, WG_RC = 32;
+constexpr int WG_TPB = 256, WG_T = 64, WG_TKT = 32, WG_RC = 64, WG_LD = WG_T + 4;
+// shared memory of a weight-gradient role: 2 stages x (L chunk + G chunk), each [WG_RC][WG_LD]
+constexpr size_t WG_SMEM_FLOATS = 2 * 2 * (size_t)WG_RC * WG_LD;
 
-__device__ __forceinline__ float block_sum_128(float v, float* red) {
-    v = warp_sum(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    return red[0] + red[1] + red[2] + red[3];
+// Adam hyper-parameters of one optimiser step (torch.optim.Adam scalars, python doubles -> f32)
+struct AdamStep {
+    float w1, b2, w2, bc2s, eps, neg_step;
+};
+
+__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamStep& a) {
+    m = m + a.w1 * (g - m);                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * a.b2 + (a.w2 * g) * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / a.bc2s + a.eps;
+    return p + (a.neg_step * m) / denom;    // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-// Roles by blockIdx.x (per net):  [0, NT) dW2t tiles (32 k x 64 o; k-tile 0 also emits db2)
-//                                 [NT, NT+NTO) layer 1: dW1t[:, o-tile], db1[o-tile]
-//                                 [NT+NTO, NT+2*NTO) layer 3: dW3t[k-tile, :] (+ db3, dlog_sigma)
-// Every role streams the minibatch in chunks of 32 rows: the next chunk is prefetched into
-// registers while the current one is consumed from shared memory.
-template <int H>
-__global__ void __launch_bounds__(WG_TPB)
-ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
-    constexpr int NTK = H / WG_TK, NTO = H / WG_TO, NT = NTK * NTO;
-    __shared__ __align__(16) float sL[WG_RC][WG_TO];     // left operand chunk (<= 64 cols)
-    __shared__ __align__(16) float sG[WG_RC][WG_TO];     // right operand chunk
-    __shared__ float s_red[4];
+// Device-wide barrier for co-resident grids (cooperative launch): monotonically increasing ticket
+// counter, one arrival per CTA, spin on an acquire load.
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ULL);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter));
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Roles by `bx` (per net): [0, NT)            dW2t tiles 32(k) x 64(o); k-tile 0 also owns db2
+//                          [NT, NT+NTO)       layer 1: dW1t[:, o-tile], db1[o-tile]
+//                          [NT+NTO, NT+2NTO)  layer 3: dW3t[k-tile, :] (+ db3, dlog_sigma)
+// Every role streams the minibatch through a cp.async double buffer of 64-row chunks.  With
+// FUSED the role keeps its gradient tile in registers, joins a grid barrier (the global norm is
+// then complete) and applies clip + Adam to the parameters it owns -- no gradient round trip.
+template <int H, bool FUSED>
+__device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int mb_off, int B, int bx, int net,
+                                               float* smem, const AdamStep ad, unsigned long long* bar,
+                                               unsigned long long bar_target, int slot) {
+    constexpr int NTT = H / WG_T, NTKT = H / WG_TKT, NT = NTKT * NTT;
+    __shared__ float s_red[WG_TPB / 32];
     const int tid = threadIdx.x;
-    const int net = blockIdx.y;
     const NetView nv = net_view(u, net);
-    const int bx = blockIdx.x;
+    float* sL[2] = {smem, smem + 2 * (size_t)WG_RC * WG_LD};
+    float* sG[2] = {smem + (size_t)WG_RC * WG_LD, smem + 3 * (size_t)WG_RC * WG_LD};
     const int nchunk = (B + WG_RC - 1) / WG_RC;
     float sq = 0.f;
+    // generic chunk loader: `wl` / `wg` floats per row from row-major sources with strides sl / sg
+    auto stage = [&](int ch, int buf, const float* srcL, int strideL, int offL, int wl,
+                     const float* srcG, int strideG, int offG, int wg) {
+        const int rb = ch * WG_RC;
+        for (int i = tid; i < WG_RC * (wl / 4); i += WG_TPB) {
+            const int rr = i / (wl / 4), c4 = (i % (wl / 4)) * 4;
+            float* dst = sL[buf] + (size_t)rr * WG_LD + c4;
+            if (rb + rr < B) __pipeline_memcpy_async(dst, srcL + (size_t)(rb + rr) * strideL + offL + c4, 16);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int i = tid; i < WG_RC * (wg / 4); i += WG_TPB) {
+            const int rr = i / (wg / 4), c4 = (i % (wg / 4)) * 4;
+            float* dst = sG[buf] + (size_t)rr * WG_LD + c4;
+            if (rb + rr < B) __pipeline_memcpy_async(dst, srcG + (size_t)(rb + rr) * strideG + offG + c4, 16);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __pipeline_commit();
+    };
+    float gscale = 1.0f;   // clip coefficient (FUSED)
+    auto finish = [&]() {  // norm contribution (+ barrier and clip scale when fused)
+        const float tot = block_sum_256(sq, s_red);
+        if (tid == 0 && tot != 0.f) atomicAdd(u.norm_sq, tot);
+        if (FUSED) {
+            grid_barrier(bar, bar_target);
+            const float nsq = __ldcg(u.norm_sq);
+            if (u.max_grad_norm > 0.f) gscale = fminf(u.max_grad_norm / (sqrtf(nsq) + 1e-6f), 1.0f);
+            if (bx == 0 && net == 0 && tid == 0 && u.stats && slot >= 0)
+                u.stats[(size_t)slot * FSRL_PPO_STATS + ST_GRADNORM] = sqrtf(nsq);
+        }
+    };
+    const long long pbase = u.net_off[net];
     if (bx < NT) {
-        // ---- dW2t[k][o] = sum_r h1[r][k] * dz2[r][o] : 32 x 64 tile, 4 x 4 per thread ----------
-        const int k0 = (bx / NTO) * WG_TK, o0 = (bx % NTO) * WG_TO;
+        // ---- dW2t[k][o] = sum_r h1[r][k] * dz2[r][o] : 32 x 64 tile, 2 x 4 per thread (FFMA issue is the
+        // bound on this chip, so the tiles are sized to spread over ~all SMs) ---------------------------
+        const int k0 = (bx / NTT) * WG_TKT, o0 = (bx % NTT) * WG_T;
         const int tk = tid / 16, to = tid % 16;
         const bool do_bias = (k0 == 0);
-        float acc[4][4];
+        float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-        float bsum = 0.f;                                  // db2 column sum (threads < 64)
-        float4 pl[2], pg[4];
-        auto prefetch = [&](int rb) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int f = tid + q * WG_TPB, rr = f / 8, cc = (f % 8) * 4;
-                pl[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_h1 + (size_t)(rb + rr) * H + k0 + cc))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
-                pg[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_dz2 + (size_t)(rb + rr) * H + o0 + cc))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        prefetch(0);
+        for (int i = 0; i < 2; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+        float bsum = 0.f;
+        DBG_W(10);
+        stage(0, 0, nv.s_h1, H, k0, WG_TKT, nv.s_dz2, H, o0, WG_T);
+        DBG_W(11);
         for (int ch = 0; ch < nchunk; ++ch) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int f = tid + q * WG_TPB, rr = f / 8, cc = (f % 8) * 4;
-                *reinterpret_cast<float4*>(&sL[rr][cc]) = pl[q];
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
-                *reinterpret_cast<float4*>(&sG[rr][cc]) = pg[q];
-            }
+            if (ch + 1 < nchunk) { stage(ch + 1, (ch + 1) & 1, nv.s_h1, H, k0, WG_TKT, nv.s_dz2, H, o0, WG_T); __pipeline_wait_prior(1); }
+            else __pipeline_wait_prior(0);
             __syncthreads();
-            if (ch + 1 < nchunk) prefetch((ch + 1) * WG_RC);
-#pragma unroll 8
+            const float* L = sL[ch & 1];
+            const float* G = sG[ch & 1];
+#pragma unroll 16
             for (int rr = 0; rr < WG_RC; ++rr) {
-                const float4 l = *reinterpret_cast<const float4*>(&sL[rr][4 * tk]);
-                const float4 g = *reinterpret_cast<const float4*>(&sG[rr][4 * to]);
+                const float2 l = *reinterpret_cast<const float2*>(L + (size_t)rr * WG_LD + 2 * tk);
+                const float4 g = *reinterpret_cast<const float4*>(G + (size_t)rr * WG_LD + 4 * to);
                 acc[0][0] = fmaf(l.x, g.x, acc[0][0]); acc[0][1] = fmaf(l.x, g.y, acc[0][1]);
                 acc[0][2] = fmaf(l.x, g.z, acc[0][2]); acc[0][3] = fmaf(l.x, g.w, acc[0][3]);
                 acc[1][0] = fmaf(l.y, g.x, acc[1][0]); acc[1][1] = fmaf(l.y, g.y, acc[1][1]);
                 acc[1][2] = fmaf(l.y, g.z, acc[1][2]); acc[1][3] = fmaf(l.y, g.w, acc[1][3]);
-                acc[2][0] = fmaf(l.z, g.x, acc[2][0]); acc[2][1] = fmaf(l.z, g.y, acc[2][1]);
-                acc[2][2] = fmaf(l.z, g.z, acc[2][2]); acc[2][3] = fmaf(l.z, g.w, acc[2][3]);
-                acc[3][0] = fmaf(l.w, g.x, acc[3][0]); acc[3][1] = fmaf(l.w, g.y, acc[3][1]);
-                acc[3][2] = fmaf(l.w, g.z, acc[3][2]); acc[3][3] = fmaf(l.w, g.w, acc[3][3]);
             }
-            if (do_bias && tid < WG_TO) {
+            if (do_bias && tid < WG_T) {
 #pragma unroll 8
-                for (int rr = 0; rr < WG_RC; ++rr) bsum += sG[rr][tid];
+                for (int rr = 0; rr < WG_RC; ++rr) bsum += G[(size_t)rr * WG_LD + tid];
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            *reinterpret_cast<float4*>(nv.g_w2t + (size_t)(k0 + 4 * tk + i) * H + o0 + 4 * to) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            sq += acc[i][0] * acc[i][0] + acc[i][1] * acc[i][1] + acc[i][2] * acc[i][2] + acc[i][3] * acc[i][3];
+        for (int i = 0; i < 2; ++i) sq += acc[i][0] * acc[i][0] + acc[i][1] * acc[i][1] + acc[i][2] * acc[i][2] + acc[i][3] * acc[i][3];
+        if (do_bias && tid < WG_T) sq += bsum * bsum;
+        DBG_W(12);
+        finish();
+        DBG_W(13);
+        if (!FUSED) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                *reinterpret_cast<float4*>(nv.g_w2t + (size_t)(k0 + 2 * tk + i) * H + o0 + 4 * to) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (do_bias && tid < WG_T) nv.g_b2[o0 + tid] = bsum;
+        } else {
+            const long long w2s = pbase + (long long)u.D * H + H;
+            float np[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long long idx = w2s + (long long)(k0 + 2 * tk + i) * H + o0 + 4 * to;
+                float4 p = *reinterpret_cast<float4*>(u.theta + idx);
+                float4 m = *reinterpret_cast<float4*>(u.adam_m + idx);
+                float4 v = *reinterpret_cast<float4*>(u.adam_v + idx);
+                p.x = adam_one(p.x, acc[i][0] * gscale, m.x, v.x, ad); p.y = adam_one(p.y, acc[i][1] * gscale, m.y, v.y, ad);
+                p.z = adam_one(p.z, acc[i][2] * gscale, m.z, v.z, ad); p.w = adam_one(p.w, acc[i][3] * gscale, m.w, v.w, ad);
+                *reinterpret_cast<float4*>(u.theta + idx) = p;
+                *reinterpret_cast<float4*>(u.adam_m + idx) = m;
+                *reinterpret_cast<float4*>(u.adam_v + idx) = v;
+                np[i][0] = p.x; np[i][1] = p.y; np[i][2] = p.z; np[i][3] = p.w;
+            }
+            float* mir = u.w2n + (size_t)net * H * H;      // out-major mirror: [o][k]
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float2*>(mir + (size_t)(o0 + 4 * to + j) * H + k0 + 2 * tk) = make_float2(np[0][j], np[1][j]);
+            if (do_bias && tid < WG_T) {
+                const long long idx = w2s + (long long)H * H + o0 + tid;
+                float m = u.adam_m[idx], v = u.adam_v[idx];
+                u.theta[idx] = adam_one(u.theta[idx], bsum * gscale, m, v, ad);
+                u.adam_m[idx] = m; u.adam_v[idx] = v;
+            }
         }
-        if (do_bias && tid < WG_TO) { nv.g_b2[o0 + tid] = bsum; sq += bsum * bsum; }
-    } else if (bx < NT + NTO) {
+    } else if (bx < NT + NTT) {
         // ---- layer 1: dW1t[d][o] = sum_r x[r][d] * dz1[r][o];  db1[o] = sum_r dz1[r][o] ---------
         const int D = u.D;
-        const int o0 = (bx - NT) * WG_TO;
-        const int* perm = u.perm + mb_off;
-        const int o = tid % WG_TO, dg = tid / WG_TO;        // 2 d-groups of 8 per pass
-        for (int d0 = 0; d0 < D; d0 += 16) {
-            float acc[8];
+        const int o0 = (bx - NT) * WG_T;
+        const int o = tid % WG_T, dg = tid / WG_T;          // 4 d-groups of 8 per pass
+        float acc_a[8], acc_b[8];                           // up to 2 passes of 32 inputs (D <= 64)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-            float bsum = 0.f;
-            float4 pg[4];
-            float px[4];
-            auto prefetch = [&](int rb) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
-                    pg[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_dz1 + (size_t)(rb + rr) * H + o0 + cc))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 8; ++q) { acc_a[q] = 0.f; acc_b[q] = 0.f; }
+        float bsum = 0.f;
+        const int npass = (D + 31) / 32;
+        auto run_pass = [&](const int d0, float (&acc)[8], const bool with_bias) {
+            // x chunk [64][32] (plain loads: rows may be gathered), dz1 chunk [64][64] (cp.async)
+            auto stage1 = [&](int ch, int buf) {
+                const int rb = ch * WG_RC;
+                for (int i = tid; i < WG_RC * 32; i += WG_TPB) {
+                    const int rr = i / 32, dd = d0 + (i % 32);
+                    sL[buf][(size_t)rr * WG_LD + (i % 32)] =
+                        (rb + rr < B && dd < D) ? __ldg(u.obs + (size_t)row_of(u, mb_off, rb + rr) * D + dd) : 0.f;
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {       // x chunk: 32 rows x 16 d  = 512 values
-                    const int f = tid + q * WG_TPB, rr = f / 16, dd = d0 + (f % 16);
-                    px[q] = (rb + rr < B && dd < D) ? __ldg(u.obs + (size_t)perm[rb + rr] * D + dd) : 0.f;
+                for (int i = tid; i < WG_RC * (WG_T / 4); i += WG_TPB) {
+                    const int rr = i / (WG_T / 4), c4 = (i % (WG_T / 4)) * 4;
+                    float* dst = sG[buf] + (size_t)rr * WG_LD + c4;
+                    if (rb + rr < B) __pipeline_memcpy_async(dst, nv.s_dz1 + (size_t)(rb + rr) * H + o0 + c4, 16);
+                    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                __pipeline_commit();
             };
-            prefetch(0);
+            stage1(0, 0);
             for (int ch = 0; ch < nchunk; ++ch) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int f = tid + q * WG_TPB;
-                    *reinterpret_cast<float4*>(&sG[f / 16][(f % 16) * 4]) = pg[q];
-                    sL[f / 16][f % 16] = px[q];
-                }
+                if (ch + 1 < nchunk) { stage1(ch + 1, (ch + 1) & 1); __pipeline_wait_prior(1); }
+                else __pipeline_wait_prior(0);
                 __syncthreads();
-                if (ch + 1 < nchunk) prefetch((ch + 1) * WG_RC);
+                const float* X = sL[ch & 1];
+                const float* G = sG[ch & 1];
 #pragma unroll 8
                 for (int rr = 0; rr < WG_RC; ++rr) {
-                    const float g = sG[rr][o];
-                    const float4 xa4 = *reinterpret_cast<const float4*>(&sL[rr][8 * dg]);
-                    const float4 xb4 = *reinterpret_cast<const float4*>(&sL[rr][8 * dg + 4]);
+                    const float g = G[(size_t)rr * WG_LD + o];
+                    const float4 xa4 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 8 * dg);
+                    const float4 xb4 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 8 * dg + 4);
                     acc[0] = fmaf(xa4.x, g, acc[0]); acc[1] = fmaf(xa4.y, g, acc[1]);
                     acc[2] = fmaf(xa4.z, g, acc[2]); acc[3] = fmaf(xa4.w, g, acc[3]);
                     acc[4] = fmaf(xb4.x, g, acc[4]); acc[5] = fmaf(xb4.y, g, acc[5]);
                     acc[6] = fmaf(xb4.z, g, acc[6]); acc[7] = fmaf(xb4.w, g, acc[7]);
-                    bsum += g;
+                    if (with_bias) bsum += g;
                 }
                 __syncthreads();
             }
+        };
+        run_pass(0, acc_a, true);
+        if (npass > 1) run_pass(32, acc_b, false);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int d = d0 + 8 * dg + q;
-                if (d < D) { nv.g_w1t[(size_t)d * H + o0 + o] = acc[q]; sq += acc[q] * acc[q]; }
+        for (int q = 0; q < 8; ++q) {
+            if (8 * dg + q < D) sq += acc_a[q] * acc_a[q];
+            if (32 + 8 * dg + q < D) sq += acc_b[q] * acc_b[q];
+        }
+        if (dg == 0) sq += bsum * bsum;
+        finish();
+        auto emit1 = [&](int d, float g) {
+            if (d >= D) return;
+            if (!FUSED) nv.g_w1t[(size_t)d * H + o0 + o] = g;
+            else {
+                const long long idx = pbase + (long long)d * H + o0 + o;
+                float m = u.adam_m[idx], v = u.adam_v[idx];
+                u.theta[idx] = adam_one(u.theta[idx], g * gscale, m, v, ad);
+                u.adam_m[idx] = m; u.adam_v[idx] = v;
             }
-            if (d0 == 0 && dg == 0) { nv.g_b1[o0 + o] = bsum; sq += bsum * bsum; }
+        };
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { emit1(8 * dg + q, acc_a[q]); emit1(32 + 8 * dg + q, acc_b[q]); }
+        if (dg == 0) {
+            if (!FUSED) nv.g_b1[o0 + o] = bsum;
+            else {
+                const long long idx = pbase + (long long)D * H + o0 + o;
+                float m = u.adam_m[idx], v = u.adam_v[idx];
+                u.theta[idx] = adam_one(u.theta[idx], bsum * gscale, m, v, ad);
+                u.adam_m[idx] = m; u.adam_v[idx] = v;
+            }
         }
     } else {
         // ---- layer 3: dW3t[k][j] = sum_r h2[r][k] * dout[r][j];  db3;  dlog_sigma ------------------
         const int out = nv.m.out;
         const int A = u.A;
-        const int k0 = (bx - NT - NTO) * WG_TO;
-        const int k = tid % WG_TO, jg = tid / WG_TO;         // j = 8*jg + q
-        float acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-        float csum = 0.f;                                     // column sum of dout (threads < 16)
-        float4 pg[4];
-        float4 pd;
-        auto prefetch = [&](int rb) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = tid + q * WG_TPB, rr = f / 16, cc = (f % 16) * 4;
-                pg[q] = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_h2 + (size_t)(rb + rr) * H + k0 + cc))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const int rr = tid / 4, cc = (tid % 4) * 4;      // dout chunk: 32 rows x 16
-            pd = (rb + rr < B) ? __ldcg(reinterpret_cast<const float4*>(nv.s_dout + (size_t)(rb + rr) * DOUT_LD + cc))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        prefetch(0);
+        const int k0 = (bx - NT - NTT) * WG_T;
+        const int k = tid % WG_T, jg = tid / WG_T;          // j = 4*jg + q
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float csum = 0.f;                                   // column sum of dout (threads < 16)
+        stage(0, 0, nv.s_h2, H, k0, WG_T, nv.s_dout, DOUT_LD, 0, DOUT_LD);
         for (int ch = 0; ch < nchunk; ++ch) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = tid + q * WG_TPB;
-                *reinterpret_cast<float4*>(&sG[f / 16][(f % 16) * 4]) = pg[q];
-            }
-            *reinterpret_cast<float4*>(&sL[tid / 4][(tid % 4) * 4]) = pd;
+            if (ch + 1 < nchunk) { stage(ch + 1, (ch + 1) & 1, nv.s_h2, H, k0, WG_T, nv.s_dout, DOUT_LD, 0, DOUT_LD); __pipeline_wait_prior(1); }
+            else __pipeline_wait_prior(0);
             __syncthreads();
-            if (ch + 1 < nchunk) prefetch((ch + 1) * WG_RC);
+            const float* Hh = sL[ch & 1];
+            const float* Dd = sG[ch & 1];
 #pragma unroll 8
             for (int rr = 0; rr < WG_RC; ++rr) {
-                const float h = sG[rr][k];
-                const float4 da = *reinterpret_cast<const float4*>(&sL[rr][8 * jg]);
-                const float4 db = *reinterpret_cast<const float4*>(&sL[rr][8 * jg + 4]);
+                const float h = Hh[(size_t)rr * WG_LD + k];
+                const float4 da = *reinterpret_cast<const float4*>(Dd + (size_t)rr * WG_LD + 4 * jg);
                 acc[0] = fmaf(h, da.x, acc[0]); acc[1] = fmaf(h, da.y, acc[1]);
                 acc[2] = fmaf(h, da.z, acc[2]); acc[3] = fmaf(h, da.w, acc[3]);
-                acc[4] = fmaf(h, db.x, acc[4]); acc[5] = fmaf(h, db.y, acc[5]);
-                acc[6] = fmaf(h, db.z, acc[6]); acc[7] = fmaf(h, db.w, acc[7]);
             }
             if (k0 == 0 && tid < DOUT_LD) {
 #pragma unroll 8
-                for (int rr = 0; rr < WG_RC; ++rr) csum += sL[rr][tid];
+                for (int rr = 0; rr < WG_RC; ++rr) csum += Dd[(size_t)rr * WG_LD + tid];
             }
             __syncthreads();
         }
+        const bool own_b3 = (k0 == 0) && tid < out;
+        const bool own_ls = (k0 == 0) && net == 0 && u.head_indep && tid >= A && tid < 2 * A && tid < DOUT_LD;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int j = 8 * jg + q;
-            if (j < out) { nv.g_w3t[(size_t)(k0 + k) * out + j] = acc[q]; sq += acc[q] * acc[q]; }
+        for (int q = 0; q < 4; ++q) if (4 * jg + q < out) sq += acc[q] * acc[q];
+        if (own_b3 || own_ls) sq += csum * csum;
+        finish();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = 4 * jg + q;
+            if (j < out) {
+                if (!FUSED) nv.g_w3t[(size_t)(k0 + k) * out + j] = acc[q];
+                else {
+                    const long long idx = pbase + (long long)u.D * H + H + (long long)H * H + H + (long long)(k0 + k) * out + j;
+                    float m = u.adam_m[idx], v = u.adam_v[idx];
+                    u.theta[idx] = adam_one(u.theta[idx], acc[q] * gscale, m, v, ad);
+                    u.adam_m[idx] = m; u.adam_v[idx] = v;
+                }
+            }
         }
-        if (k0 == 0 && tid < DOUT_LD) {
-            if (tid < out) { nv.g_b3[tid] = csum; sq += csum * csum; }
-            else if (net == 0 && u.head_indep && tid >= A && tid < 2 * A) { nv.g_log_sigma[tid - A] = csum; sq += csum * csum; }
+        if (own_b3 || own_ls) {
+            const long long b3s = pbase + (long long)u.D * H + H + (long long)H * H + H + (long long)H * out;
+            const long long idx = own_b3 ? b3s + tid : b3s + out + (tid - A);
+            if (!FUSED) { if (own_b3) nv.g_b3[tid] = csum; else nv.g_log_sigma[tid - A] = csum; }
+            else {
+                float m = u.adam_m[idx], v = u.adam_v[idx];
+                u.theta[idx] = adam_one(u.theta[idx], csum * gscale, m, v, ad);
+                u.adam_m[idx] = m; u.adam_v[idx] = v;
+            }
         }
     }
-    const float tot = block_sum_128(sq, s_red);
-    if (tid == 0 && tot != 0.f) atomicAdd(u.norm_sq, tot);
+}
+
+template <int H>
+__global__ void __launch_bounds__(WG_TPB)
+ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
+    extern __shared__ __align__(16) float smem[];
+    AdamStep ad = {};
+    const long long t0 = clock64();
+    ppo_wgrad_role<H, false>(u, mb_off, B, blockIdx.x, blockIdx.y, smem, ad, nullptr, 0ULL, -1);
+    if (threadIdx.x == 0 && blockIdx.x + gridDim.x * blockIdx.y < 512) g_dbg_cta[blockIdx.x + gridDim.x * blockIdx.y] = clock64() - t0;
+}
+
+// weight gradients + clip_grad_norm_ + Adam in one cooperative launch (single-GPU path)
+template <int H>
+__global__ void __launch_bounds__(WG_TPB)
+ppo_wgrad_adam_kernel(const fsrl_ppo_update_t u, int mb_off, int B, AdamStep ad, unsigned long long* bar,
+                      unsigned long long bar_target, int slot) {
+    extern __shared__ __align__(16) float smem[];
+    ppo_wgrad_role<H, true>(u, mb_off, B, blockIdx.x, blockIdx.y, smem, ad, bar, bar_target, slot);
 }
 
 // ------------------------------------------------------------------------------------------
 // Phase C: clip_grad_norm_ + Adam (torch.optim.Adam single-tensor arithmetic order)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, float w1, float b2,
-                                          float w2, float bc2s, float eps, float neg_step) {
+__device__ __forceinline__ float adam_one_s(float p, float g, float& m, float& v, float w1, float b2,
+                                            float w2, float bc2s, float eps, float neg_step) {
     m = m + w1 * (g - m);                 // exp_avg.lerp_(grad, 1 - beta1)
     v = v * b2 + (w2 * g) * g;            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) / bc2s + eps;
@@ -548,7 +746,7 @@ adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s,
         float m = u.adam_m[i], v = u.adam_v[i];
         const float g = (u.mask && u.mask[i] == 0) ? 0.f : u.grad[i] * scale;
         if (u.mask && u.mask[i] == 0) return;
-        u.theta[i] = adam_one(u.theta[i], g, m, v, w1, b2, w2, bc2s, eps, neg_step);
+        u.theta[i] = adam_one_s(u.theta[i], g, m, v, w1, b2, w2, bc2s, eps, neg_step);
         u.adam_m[i] = m; u.adam_v[i] = v;
     } else {
         // W2 tiles: 32 x 32, update canonical W2t[k][o] and its mirror W2n[o][k]
@@ -566,7 +764,7 @@ adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s,
             float p = u.theta[i];
             if (!frozen) {
                 float m = u.adam_m[i], v = u.adam_v[i];
-                p = adam_one(p, u.grad[i] * scale, m, v, w1, b2, w2, bc2s, eps, neg_step);
+                p = adam_one_s(p, u.grad[i] * scale, m, v, w1, b2, w2, bc2s, eps, neg_step);
                 u.theta[i] = p; u.adam_m[i] = m; u.adam_v[i] = v;
             }
             tile[kk][lx] = p;
@@ -602,7 +800,7 @@ __global__ void __launch_bounds__(256) ppo_adv_moments_kernel(const fsrl_ppo_upd
     for (int c = 0; c < u.C; ++c) {
         double s = 0.0, q = 0.0;
         for (long long i = threadIdx.x; i < B; i += 256) {
-            const double a = (double)u.adv[(size_t)c * u.ld + u.perm[off + i]];
+            const double a = (double)u.adv[(size_t)c * u.ld + (u.perm ? (long long)u.perm[off + i] : off + i)];
             s += a; q += a * a;
         }
         s = warp_sum(s); q = warp_sum(q);
@@ -618,24 +816,105 @@ __global__ void __launch_bounds__(256) ppo_adv_moments_kernel(const fsrl_ppo_upd
     }
 }
 
+// mean and 1/std (unbiased, no eps: ppo_lag.py:181-182) of the advantages of every minibatch of
+// the repeat: block b = minibatch b.  In a data-parallel run the sums were all-reduced first.
+__global__ void __launch_bounds__(256) ppo_adv_stats_kernel(const fsrl_ppo_update_t u, long long n_total, int n_mb) {
+    __shared__ double red[8];
+    __shared__ double s_m;
+    const int mb = blockIdx.x;
+    const long long off = (long long)mb * u.batch_size;
+    long long B = u.batch_size;
+    if (mb == n_mb - 1) B = n_total - off;
+    for (int c = 0; c < u.C; ++c) {
+        float* out = u.mb_stats + ((size_t)mb * 2 + c) * 2;
+        if (!u.norm_adv) { if (threadIdx.x == 0) { out[0] = 0.f; out[1] = 1.f; } continue; }
+        if (u.moments) {
+            if (threadIdx.x == 0) {
+                const double* mo = u.moments + ((size_t)mb * 2 + c) * 2;
+                const double nn = (double)B * (double)u.world;
+                const double mean = mo[0] / nn;
+                const double var = (mo[1] - nn * mean * mean) / (nn - 1.0);
+                out[0] = (float)mean; out[1] = (float)(1.0 / sqrt(var));
+            }
+            continue;
+        }
+        // two-pass like torch: mean in fp32 arithmetic would differ in the last bits only; use f64 sums
+        double sacc = 0.0;
+        for (long long i = threadIdx.x; i < B; i += 256)
+            sacc += (double)u.adv[(size_t)c * u.ld + (u.perm ? (long long)u.perm[off + i] : off + i)];
+        sacc = warp_sum(sacc);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sacc;
+        __syncthreads();
+        if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; s_m = t / (double)B; }
+        __syncthreads();
+        const float mean = (float)s_m;
+        double q = 0.0;
+        for (long long i = threadIdx.x; i < B; i += 256) {
+            const float d = u.adv[(size_t)c * u.ld + (u.perm ? (long long)u.perm[off + i] : off + i)] - mean;
+            q += (double)(d * d);
+        }
+        q = warp_sum(q);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w];
+            out[0] = mean; out[1] = 1.0f / sqrtf((float)(t / (double)(B - 1)));
+        }
+    }
+}
+
 extern "C" int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
 extern "C" int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
 
 template <int H>
 static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, int slot,
-                                long long adam_t, cudaStream_t s) {
+                                long long adam_t, long long bar_count, cudaStream_t s) {
     using TT = MlpTile<H>;
-    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * TT::LDA + (size_t)TT::R * DOUT_LD);
+    const size_t smemF = sizeof(float) * ((size_t)TT::R * TT::in_pad(u.D) + (size_t)TT::R * TT::LDA + slab_buf_floats<H>());
+    const size_t smemB = sizeof(float) * (2 * (size_t)TT::R * TT::LDA + slab_buf_floats<H>() + (size_t)H * MLP_MAX_OUT + (size_t)TT::R * DOUT_LD);
     static bool attr_done = false;
     if (!attr_done) {
-        FSRL_CUDA(cudaFuncSetAttribute(ppo_fwdbwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+        FSRL_CUDA(cudaFuncSetAttribute(ppo_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
+        FSRL_CUDA(cudaFuncSetAttribute(ppo_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
         attr_done = true;
     }
-    const dim3 gA((B + TT::R - 1) / TT::R, u.n_nets);
-    ppo_fwdbwd_kernel<H><<<gA, MLP_TPB, smemA, s>>>(u, mb_off, B, slot);
+    const dim3 gA((B + TT::R - 1) / TT::R, H / SLAB_NS, u.n_nets);
+    ppo_fwd_kernel<H><<<gA, MLP_TPB, smemF, s>>>(u, mb_off, B);
     FSRL_LAUNCH_CHECK();
-    const dim3 gB((H / WG_TK) * (H / WG_TO) + 2 * (H / WG_TO), u.n_nets);
-    ppo_wgrad_kernel<H><<<gB, WG_TPB, 0, s>>>(u, mb_off, B);
+    ppo_bwd_kernel<H><<<gA, MLP_TPB, smemB, s>>>(u, mb_off, B, slot);
+    FSRL_LAUNCH_CHECK();
+    constexpr int NTT = H / WG_T;
+    const dim3 gB((H / WG_TKT) * NTT + 2 * NTT, u.n_nets);
+    const size_t smemW = sizeof(float) * WG_SMEM_FLOATS;
+    static bool attr_w = false;
+    static int fuse_ok = -1;
+    if (!attr_w) {
+        FSRL_CUDA(cudaFuncSetAttribute(ppo_wgrad_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW));
+        FSRL_CUDA(cudaFuncSetAttribute(ppo_wgrad_adam_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW));
+        int per_sm = 0;
+        FSRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_wgrad_adam_kernel<H>, WG_TPB, smemW));
+        fuse_ok = (per_sm * sm_count() >= (int)(gB.x * 3)) ? 1 : 0;     // whole grid co-resident?
+        attr_w = true;
+    }
+    // torch.optim.Adam scalars (python doubles -> f32 at the op)
+    const double b1 = u.beta1, b2 = u.beta2;
+    const double bc1 = 1.0 - pow(b1, (double)adam_t), bc2 = 1.0 - pow(b2, (double)adam_t);
+    const float neg_step = (float)(-(u.lr / bc1));
+    const float bc2s = (float)sqrt(bc2);
+    if (u.world <= 1 && fuse_ok == 1 && u.barrier != nullptr && u.mask == nullptr) {
+        // single GPU: gradients never leave the registers -- tiles -> norm -> barrier -> clip + Adam
+        AdamStep ad = {(float)(1.0 - b1), (float)b2, (float)(1.0 - b2), bc2s, (float)u.adam_eps, neg_step};
+        unsigned long long target = (unsigned long long)(bar_count + 1) * gB.x * gB.y;
+        fsrl_ppo_update_t uu = u;
+        int mo = mb_off, bb = B, sl = slot;
+        unsigned long long* barp = u.barrier;
+        void* args[] = {&uu, &mo, &bb, &ad, &barp, &target, &sl};
+        FSRL_CUDA(cudaLaunchCooperativeKernel((void*)ppo_wgrad_adam_kernel<H>, gB, dim3(WG_TPB), args, smemW, s));
+        return FSRL_OK;
+    }
+    ppo_wgrad_kernel<H><<<gB, WG_TPB, smemW, s>>>(u, mb_off, B);
     FSRL_LAUNCH_CHECK();
     if (u.world > 1) {
         // data parallel: ONE all-reduce of the flat gradient buffer per optimiser step, then the
@@ -645,11 +924,6 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
         grad_norm_kernel<<<1, 1024, 0, s>>>(u);
         FSRL_LAUNCH_CHECK();
     }
-    // torch.optim.Adam scalars (python doubles -> f32 at the op)
-    const double b1 = u.beta1, b2 = u.beta2;
-    const double bc1 = 1.0 - pow(b1, (double)adam_t), bc2 = 1.0 - pow(b2, (double)adam_t);
-    const float neg_step = (float)(-(u.lr / bc1));
-    const float bc2s = (float)sqrt(bc2);
     const int n_plain = (int)((u.n_params + 255) / 256);
     const int n_tiles = u.n_nets * (H / 32) * (H / 32);
     adam_kernel<<<n_plain + n_tiles, 256, 0, s>>>(u, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), bc2s,
@@ -707,11 +981,31 @@ extern "C" int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total,
     int rc = check_update(u);
     if (rc) return rc;
     FSRL_REQUIRE(u->obs && u->act && u->logp_old && u->adv && u->ret && u->perm && u->stats, "ppo: null batch pointer");
+    FSRL_REQUIRE(n_total <= 2147483647LL, "ppo: batch too large for 32-bit row offsets");
     FSRL_REQUIRE(batch_size >= 2 && n_total >= 2, "ppo: batch too small");
     FSRL_REQUIRE(2 * batch_size - 1 <= u->bmax || n_total <= u->bmax, "ppo: scratch bmax %d too small for batch_size %d", u->bmax, batch_size);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int count = 0;
     const bool merge_last = (n_total % batch_size) > 0;       // tianshou Batch.split
+    fsrl_ppo_update_t ug = *u;
+    if (u->barrier) FSRL_CUDA(cudaMemsetAsync(u->barrier, 0, sizeof(unsigned long long), s));
+    if (u->gather) {
+        // one coalescing pass per repeat: the permuted batch becomes contiguous, minibatch k is
+        // rows [k*bs, (k+1)*bs) and no kernel chases indices afterwards
+        ppo_gather_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, s>>>(*u, n_total);
+        FSRL_LAUNCH_CHECK();
+        float* g = u->gather;
+        ug.obs = g; g += n_total * u->D;
+        ug.act = g; g += n_total * u->A;
+        ug.logp_old = g; g += n_total;
+        ug.adv = g; g += (long long)u->C * n_total;
+        ug.ret = g; g += (long long)u->C * n_total;
+        ug.values = u->values ? g : nullptr;
+        ug.ld = n_total;
+        ug.perm = nullptr;
+    }
+    ug.batch_size = batch_size;
+    u = &ug;
     FSRL_REQUIRE(u->world <= 1 || (u->comm && u->moments_w && u->batch_size == batch_size),
                  "ppo: data-parallel run needs comm, moments buffer and batch_size in the descriptor");
     if (u->world > 1) {
@@ -723,6 +1017,13 @@ extern "C" int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total,
         int rc2 = fsrl_allreduce_f64(u->comm, u->moments_w, (long long)n_mb * 4, s);
         if (rc2) return rc2;
     }
+    {
+        const long long n_mb_all = merge_last ? (n_total / batch_size) : (n_total + batch_size - 1) / batch_size;
+        const int n_mb = (int)(n_mb_all < 1 ? 1 : n_mb_all);
+        FSRL_REQUIRE(u->mb_stats != nullptr, "ppo: mb_stats buffer missing");
+        ppo_adv_stats_kernel<<<n_mb, 256, 0, s>>>(*u, n_total, n_mb);
+        FSRL_LAUNCH_CHECK();
+    }
     for (long long off = 0; off < n_total; off += batch_size) {
         long long B = batch_size;
         bool last = false;
@@ -731,10 +1032,10 @@ extern "C" int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total,
         FSRL_REQUIRE(B <= u->bmax, "ppo: minibatch of %lld rows exceeds scratch (%d)", B, u->bmax);
         int r2;
         switch (u->H) {
-            case 64: r2 = ppo_launch_minibatch<64>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, s); break;
-            case 128: r2 = ppo_launch_minibatch<128>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, s); break;
-            case 256: r2 = ppo_launch_minibatch<256>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, s); break;
-            default: r2 = ppo_launch_minibatch<512>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, s); break;
+            case 64: r2 = ppo_launch_minibatch<64>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, count, s); break;
+            case 128: r2 = ppo_launch_minibatch<128>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, count, s); break;
+            case 256: r2 = ppo_launch_minibatch<256>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, count, s); break;
+            default: r2 = ppo_launch_minibatch<512>(*u, (int)off, (int)B, stats_slot0 + count, adam_t0 + count + 1, count, s); break;
         }
         if (r2) return r2;
         ++count;
@@ -751,29 +1052,36 @@ template <int H>
 static int ppo_time_phases(const fsrl_ppo_update_t& u0, int B, int iters, float* ms, cudaStream_t s) {
     using TT = MlpTile<H>;
     fsrl_ppo_update_t u = u0;
-    const size_t smemA = TT::smem_bytes(u.D) + sizeof(float) * ((size_t)TT::R * TT::LDA + (size_t)TT::R * DOUT_LD);
-    FSRL_CUDA(cudaFuncSetAttribute(ppo_fwdbwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    cudaEvent_t e[4];
-    for (int i = 0; i < 4; ++i) FSRL_CUDA(cudaEventCreate(&e[i]));
-    const dim3 gA((B + TT::R - 1) / TT::R, u.n_nets);
-    const dim3 gB((H / WG_TK) * (H / WG_TO) + 2 * (H / WG_TO), u.n_nets);
+    const size_t smemF = sizeof(float) * ((size_t)TT::R * TT::in_pad(u.D) + (size_t)TT::R * TT::LDA + slab_buf_floats<H>());
+    const size_t smemB = sizeof(float) * (2 * (size_t)TT::R * TT::LDA + slab_buf_floats<H>() + (size_t)H * MLP_MAX_OUT + (size_t)TT::R * DOUT_LD);
+    FSRL_CUDA(cudaFuncSetAttribute(ppo_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
+    FSRL_CUDA(cudaFuncSetAttribute(ppo_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    cudaEvent_t e[5];
+    for (int i = 0; i < 5; ++i) FSRL_CUDA(cudaEventCreate(&e[i]));
+    const dim3 gA((B + TT::R - 1) / TT::R, H / SLAB_NS, u.n_nets);
+    constexpr int NTT = H / WG_T;
+    const dim3 gB((H / WG_TKT) * NTT + 2 * NTT, u.n_nets);
+    const size_t smemW = sizeof(float) * WG_SMEM_FLOATS;
+    FSRL_CUDA(cudaFuncSetAttribute(ppo_wgrad_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW));
     const int n_plain = (int)((u.n_params + 255) / 256);
     const int n_tiles = u.n_nets * (H / 32) * (H / 32);
     FSRL_CUDA(cudaEventRecord(e[0], s));
-    for (int i = 0; i < iters; ++i) ppo_fwdbwd_kernel<H><<<gA, MLP_TPB, smemA, s>>>(u, 0, B, 0);
+    for (int i = 0; i < iters; ++i) ppo_fwd_kernel<H><<<gA, MLP_TPB, smemF, s>>>(u, 0, B);
     FSRL_CUDA(cudaEventRecord(e[1], s));
-    for (int i = 0; i < iters; ++i) ppo_wgrad_kernel<H><<<gB, WG_TPB, 0, s>>>(u, 0, B);
+    for (int i = 0; i < iters; ++i) ppo_bwd_kernel<H><<<gA, MLP_TPB, smemB, s>>>(u, 0, B, 0);
     FSRL_CUDA(cudaEventRecord(e[2], s));
+    for (int i = 0; i < iters; ++i) ppo_wgrad_kernel<H><<<gB, WG_TPB, smemW, s>>>(u, 0, B);
+    FSRL_CUDA(cudaEventRecord(e[3], s));
     for (int i = 0; i < iters; ++i)
         adam_kernel<<<n_plain + n_tiles, 256, 0, s>>>(u, 0.1f, 0.999f, 0.001f, 1.0f, 1e-8f, 0.0f, -1, n_plain);
-    FSRL_CUDA(cudaEventRecord(e[3], s));
-    FSRL_CUDA(cudaEventSynchronize(e[3]));
-    for (int i = 0; i < 3; ++i) {
+    FSRL_CUDA(cudaEventRecord(e[4], s));
+    FSRL_CUDA(cudaEventSynchronize(e[4]));
+    for (int i = 0; i < 4; ++i) {
         float t = 0.f;
         FSRL_CUDA(cudaEventElapsedTime(&t, e[i], e[i + 1]));
         ms[i] = t / (float)iters;
     }
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]);
     FSRL_LAUNCH_CHECK();
     return FSRL_OK;
 }
@@ -793,5 +1101,9 @@ extern "C" int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters
 
 extern "C" int fsrl_debug_clocks(long long* out16) {
     FSRL_CUDA(cudaMemcpyFromSymbol(out16, fsrl::g_dbg_clock, sizeof(long long) * 16));
+    return FSRL_OK;
+}
+extern "C" int fsrl_debug_cta_cycles(long long* out512) {
+    FSRL_CUDA(cudaMemcpyFromSymbol(out512, fsrl::g_dbg_cta, sizeof(long long) * 512));
     return FSRL_OK;
 }

@@ -83,7 +83,7 @@ class PPOLagrangian(LagrangianPolicy):
             self._scratch = torch.zeros(nfl, dtype=torch.float32, device=ar.device)
         if getattr(self, "_w2n", None) is None:
             self._w2n = torch.zeros(n_nets * H * H, dtype=torch.float32, device=ar.device)
-            self._norm_sq = torch.zeros(4, dtype=torch.float32, device=ar.device)
+            self._norm_sq = torch.zeros(8, dtype=torch.float32, device=ar.device)
             self._mirror_dirty = True
         n_mb = (n_total + batch_size - 1) // batch_size
         need = repeat * n_mb * _lib.PPO_STATS
@@ -122,6 +122,16 @@ class PPOLagrangian(LagrangianPolicy):
         u.use_lagrangian = int(self.use_lagrangian and self.critics_num > 1)
         g = self.optim.param_groups[0]
         u.lr, u.beta1, u.beta2, u.adam_eps = g["lr"], g["betas"][0], g["betas"][1], g["eps"]
+        need = batch.n * (s0.D + s0.out + 1 + 3 * self.critics_num)
+        if getattr(self, "_gather", None) is None or self._gather.numel() < need:
+            self._gather = torch.empty(need, dtype=torch.float32, device=ar.device)
+        u.gather = self._gather.data_ptr()
+        n_mb_max = batch.n // max(int(getattr(self, '_dp_batch', 1)), 1) + 2
+        if getattr(self, "_mb_stats", None) is None or self._mb_stats.numel() < 4 * n_mb_max:
+            self._mb_stats = torch.zeros(4 * n_mb_max, dtype=torch.float32, device=ar.device)
+        u.mb_stats = self._mb_stats.data_ptr()
+        u.batch_size = int(getattr(self, '_dp_batch', 0))
+        u.barrier = self._norm_sq.data_ptr() + 8
         dp = getattr(self, "_dp", None)
         u.world = 1
         if dp is not None and dp.world > 1:
@@ -152,6 +162,7 @@ class PPOLagrangian(LagrangianPolicy):
         rows = []
         perm_dev = torch.empty(n, dtype=torch.int32, device=ar.device)
         perm_host = torch.empty(n, dtype=torch.int32).pin_memory()
+        next_perm = None
         with torch.cuda.device(ar.device):
             if self._mirror_dirty:
                 u0 = self._descriptor(batch, perm_dev)
@@ -161,7 +172,11 @@ class PPOLagrangian(LagrangianPolicy):
                 if self._recompute_adv and step > 0:
                     batch = self.compute_gae_returns(batch, self._buffer, self._indices, self._lambda)
                 # Batch.split(batch_size, shuffle=True): np.random.permutation (global RNG)
-                perm_host.numpy()[:] = np.random.permutation(n)
+                if next_perm is not None:
+                    perm_host.numpy()[:] = next_perm
+                    next_perm = None
+                else:
+                    perm_host.numpy()[:] = np.random.permutation(n)
                 perm_dev.copy_(perm_host, non_blocking=True)
                 u = self._descriptor(batch, perm_dev)
                 n_mb = ctypes.c_int(0)
@@ -169,6 +184,13 @@ class PPOLagrangian(LagrangianPolicy):
                                                   self.optim.step_count, ctypes.byref(n_mb), stream))
                 self.optim.step_count += n_mb.value
                 self.gradient_steps += n_mb.value
+                # while the GPU chews through this repeat, draw the next permutation on the host; if
+                # the KL test below stops the loop the draw is rolled back so that the NumPy stream
+                # is consumed exactly as in the reference
+                rng_state = None
+                if step + 1 < repeat:
+                    rng_state = np.random.get_state()
+                    next_perm = np.random.permutation(n)
                 st = self._stats_dev[slot * _lib.PPO_STATS:(slot + n_mb.value) * _lib.PPO_STATS] \
                     .view(n_mb.value, _lib.PPO_STATS).cpu().numpy()                    # sync point
                 rows.append(st)
@@ -176,6 +198,8 @@ class PPOLagrangian(LagrangianPolicy):
                 approx_kl = float(st[:, 2].sum()) / (n_mb.value + 1e-7)                # :251
                 if getattr(self, "_dp", None) is not None:
                     approx_kl = self._dp.mean_scalar(approx_kl)                          # all ranks stop together
+                if approx_kl > 1.5 * self._target_kl and rng_state is not None:
+                    np.random.set_state(rng_state)
                 if approx_kl > 1.5 * self._target_kl:
                     self.logger.print("Early stop at step %d due to reaching max kl." % step)
                     break

@@ -166,6 +166,14 @@ typedef struct fsrl_ppo_update {
     double* moments_w;
     const double* moments;
     int world, batch_size;
+    /* optional [N*(D+A+1+3C)] floats: the epoch driver gathers the permuted batch into it once
+     * per repeat so that every minibatch is a contiguous row range */
+    float* gather;
+    /* [n_minibatches][2][2] floats: (mean, 1/std) of the advantages of every minibatch of the
+     * repeat, filled by the epoch driver */
+    float* mb_stats;
+    /* device u64 ticket counter of the in-kernel grid barrier (fused wgrad + Adam launch) */
+    unsigned long long* barrier;
 } fsrl_ppo_update_t;
 
 size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax);
@@ -175,11 +183,13 @@ int fsrl_ppo_sync_mirror(const fsrl_ppo_update_t* u, void* stream);
  * statistics go to stats[stats_slot0 + i]; *n_minibatches (host) receives the count */
 int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total, int batch_size,
                        int stats_slot0, long long adam_t0, int* n_minibatches, void* stream);
-/* measurement aid (bench.py roofline): mean duration [ms] of the three phase kernels over
+/* measurement aid (bench.py roofline): mean duration [ms] of the four phase kernels (fwd, bwd,
+ * wgrad, adam) over
  * `iters` launches on the first B rows of u->perm; weights are left untouched (lr = 0) */
 /* tuning aid: clock64() stamps taken by CTA (0,0) at the phase boundaries of the last
  * ppo_fwdbwd launch (host array of 16) */
 int fsrl_debug_clocks(long long* out16);
+int fsrl_debug_cta_cycles(long long* out512); /* per-CTA cycle counts of the last ppo_wgrad launch */
 int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters, float* ms_out, void* stream);
 
 /* ---- a6: batched critic / actor forward ---------------------------------------------------

@@ -58,14 +58,19 @@ def bench_gae(envs, T):
 def bench_ppo(iters):
     import bench
     agent, trainer, col, buf, T = bench.build("cuda:0", 0)
-    print(json.dumps({"phase_ms(fwdbwd,wgrad,adam)": bench.phase_times(agent, col, buf, iters=iters)}))
+    print(json.dumps({"phase_ms(fwd,bwd,wgrad,adam)": bench.phase_times(agent, col, buf, iters=iters)}))
     import ctypes
     from fsrl_b200 import _lib
     ck = (ctypes.c_longlong * 16)()
     _lib.check(_lib.lib.fsrl_debug_clocks(ck))
     c = list(ck)
-    print("fwdbwd CTA(0,0) cycles per section [prologue, hidden_fwd, head, lossgrad, stats, bwdL3, bwdL2]:",
-          [c[i + 1] - c[i] for i in range(7)], "total", c[7] - c[0])
+    print("ppo_bwd CTA(0,0,0) cycles [loads, advstats, sync, head, lossgrad, stats, dz2, wait_slab, slab_gemm]:",
+          [c[i + 1] - c[i] for i in range(8)], "total", c[8] - c[0])
+    cc = (ctypes.c_longlong * 512)()
+    _lib.check(_lib.lib.fsrl_debug_cta_cycles(cc))
+    cc = list(cc)[:120]
+    print("wgrad per-CTA cycles net0 roles:", cc[:40])
+    print("wgrad tile CTA cycles [stage0 issue, chunk loop, finish]:", [c[11] - c[10], c[12] - c[11], c[13] - c[12]])
 
 
 if __name__ == "__main__":
