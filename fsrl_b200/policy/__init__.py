@@ -4,6 +4,7 @@ from .ppo_lag import PPOLagrangian
 from .sac_lag import SACLagrangian
 from .ddpg_lag import DDPGLagrangian, GaussianNoise
 from .cpo import CPO
+from .trpo_lag import TRPOLagrangian
 
 __all__ = ["ActorCritic", "BasePolicy", "DeviceBatch", "LagrangianPolicy", "PPOLagrangian",
-           "SACLagrangian", "DDPGLagrangian", "GaussianNoise", "CPO"]
+           "SACLagrangian", "DDPGLagrangian", "GaussianNoise", "CPO", "TRPOLagrangian"]

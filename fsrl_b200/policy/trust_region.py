@@ -1,0 +1,114 @@
+"""Device machinery shared by the trust-region learners (CPO, TRPO-Lagrangian): resident-batch
+engine context, head-gradient / Hessian-vector-product calls (csrc/cpo.cu), conjugate gradients
+(reference: fsrl/policy/cpo.py:184-204, trpo_lag.py:261-283) and the critic regression step."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..engine import EngineCtx
+from .base_policy import DeviceBatch
+
+
+class TrustRegionMixin:
+    _eng: Optional[EngineCtx] = None
+    _critic_t = 0
+    _l2_reg = 0.0
+    _damping_coeff = 0.1
+
+    # ---- engine ----------------------------------------------------------------------------------------
+    def _ensure_engine(self, n: int) -> EngineCtx:
+        if self._eng is None or self._eng.bmax < n:
+            self._eng = EngineCtx(self.arena, n, extra_slots=1)
+            P = self.arena.slots[0].size
+            dev = self.device
+            self._vec = {k: torch.zeros(P, dtype=torch.float32, device=dev)
+                         for k in ("g", "b", "x", "r", "p", "z", "Hinv_g", "Hinv_b", "hv", "theta0", "step")}
+            self._v_w2n = torch.zeros(self.arena.slots[0].H ** 2, dtype=torch.float32, device=dev)
+            self._sums = torch.zeros(4, dtype=torch.float64, device=dev)
+            self._dot = torch.zeros(1, dtype=torch.float64, device=dev)
+        return self._eng
+
+    # ---- device helpers -----------------------------------------------------------------------------------
+    def _s(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _dotp(self, a, b) -> float:
+        _lib.check(_lib.lib.fsrl_vec_dot(a.data_ptr(), b.data_ptr(), a.numel(), self._dot.data_ptr(), self._s()))
+        return float(self._dot.item())
+
+    def _descriptor(self, batch: DeviceBatch, perm: Optional[torch.Tensor], n: int) -> "_lib.Cpo":
+        eng = self._eng
+        a = self.arena.slots[0]
+        d = _lib.Cpo()
+        d.eng = eng.engine()
+        d.actor = eng.netlist([a])
+        r = eng.netlist([a])
+        r.nets[0].slot = eng.extra_slot(0)
+        d.actor_r = r
+        d.N, d.ld, d.A = n, batch.adv.shape[1], a.out
+        d.bounded, d.max_action = int(not self.actor._unbounded), float(self.actor._max)
+        d.obs, d.act, d.logp_old = batch.obs.data_ptr(), batch.act.data_ptr(), batch.logp_old.data_ptr()
+        d.mean_old, d.std_old, d.adv = batch.mean_old.data_ptr(), batch.std_old.data_ptr(), batch.adv.data_ptr()
+        d.perm = None if perm is None else perm.data_ptr()
+        d.out = eng.slot_view(a, "out").data_ptr()
+        d.dout = eng.slot_view(a, "dout").data_ptr()
+        d.log_sigma = self.arena.extra_ptr(a)
+        return d
+
+    def _head(self, d, mode: int):
+        _lib.check(_lib.lib.fsrl_cpo_head(ctypes.byref(d), mode, self._sums.data_ptr(), self._s()))
+
+    def _hvp(self, d, v, out):
+        _lib.check(_lib.lib.fsrl_cpo_hvp(ctypes.byref(d), v.data_ptr(), self._v_w2n.data_ptr(), out.data_ptr(),
+                                         float(self._damping_coeff), self._s()))
+
+    def _cg(self, d, rhs: torch.Tensor, out: torch.Tensor, nsteps: int = 10, residual_tol: float = 1e-8):
+        """cpo.py:184-204, vectors on the device, two scalars per iteration on the host."""
+        v = self._vec
+        x, r, p, z = v["x"], v["r"], v["p"], v["z"]
+        x.zero_(); r.copy_(rhs); p.copy_(rhs)
+        rs_old = self._dotp(r, r)
+        lib, s, n = _lib.lib, self._s(), rhs.numel()
+        for _ in range(nsteps):
+            self._hvp(d, p, z)
+            alpha = rs_old / self._dotp(p, z)
+            _lib.check(lib.fsrl_vec_axpby(alpha, p.data_ptr(), 1.0, x.data_ptr(), n, s))
+            _lib.check(lib.fsrl_vec_axpby(-alpha, z.data_ptr(), 1.0, r.data_ptr(), n, s))
+            rs_new = self._dotp(r, r)
+            if rs_new < residual_tol:
+                break
+            _lib.check(lib.fsrl_vec_axpby(1.0, r.data_ptr(), rs_new / rs_old, p.data_ptr(), n, s))
+            rs_old = rs_new
+        out.copy_(x)
+
+    # ---- critic regression (:147-162) ------------------------------------------------------------------------
+    def critics_loss(self, batch: DeviceBatch, perm: Optional[torch.Tensor], n: int) -> dict:
+        eng = self._eng
+        crit = self.arena.slots[1:1 + self.critics_num]
+        inp = eng.make_input(batch.obs, perm)
+        eng.forward(crit, inp, n, save=True)
+        stats = {}
+        l2 = 0.0
+        for i, s in enumerate(crit):
+            v = eng.slot_view(s, "out")[:n, 0]
+            ret = batch.ret[i] if perm is None else batch.ret[i][perm.long()]
+            td = v - ret
+            dout = eng.slot_view(s, "dout")
+            dout[:n].zero_()
+            dout[:n, 0] = 2.0 * td / n
+            th = self.arena.theta[s.offset:s.offset + s.size]
+            reg = float((th * th).sum().item()) * self._l2_reg
+            stats["loss/vf" + str(i)] = float((td * td).mean().item()) + reg
+        eng.backward(crit, n)
+        eng.wgrad(crit, inp, n)
+        self._critic_t += 1
+        g = self.optim.param_groups[0]
+        eng.adam(crit, g["lr"], self._critic_t, betas=g["betas"], eps=g["eps"], l2_reg=self._l2_reg)
+        stats["loss/vf_total"] = sum(stats["loss/vf" + str(i)] for i in range(self.critics_num))
+        return stats
+
