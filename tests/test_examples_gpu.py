@@ -25,7 +25,7 @@ def test_agents_train_through_reference_imports(algo, extra, tmp_path):
     import train_agent
     argv = ["--algo", algo, "--task", "SafetyBallRun-v0", "--epoch", "2", "--step_per_epoch", "1600",
             "--training_num", "16", "--episode_per_collect", "16", "--testing_num", "2", "--hidden_sizes", "(64,64)",
-            "--buffer_size", "6400", "--logdir", str(tmp_path), "--verbose", "False"] + extra
+            "--buffer_size", "6400", "--logdir", str(tmp_path), "--verbose", "False", "--save_interval", "1"] + extra
     epoch, stats, info = train_agent.main(argv)
     assert epoch == 2 and info["train_speed"] > 0
     assert np.isfinite(stats["train/reward"]) and "update/env_step" in stats or True
