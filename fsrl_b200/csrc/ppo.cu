@@ -399,7 +399,7 @@ __global__ void ppo_gather_kernel(const fsrl_ppo_update_t u, long long n) {
 // ------------------------------------------------------------------------------------------
 // Phase B: weight gradients
 // ------------------------------------------------------------------------------------------
-constexpr int WG_TPB = 256, WG_T = 64, WG_TKT = 32, WG_RC = 64, WG_LD = WG_T + 4;
+constexpr int WG_TPB = 256, WG_T = 64, WG_TKT = 32, WG_RC = 128, WG_LD = WG_T + 4;
 // shared memory of a weight-gradient role: 2 stages x (L chunk + G chunk), each [WG_RC][WG_LD]
 constexpr size_t WG_SMEM_FLOATS = 2 * 2 * (size_t)WG_RC * WG_LD;
 
@@ -445,8 +445,9 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
     __shared__ float s_red[WG_TPB / 32];
     const int tid = threadIdx.x;
     const NetView nv = net_view(u, net);
-    float* sL[2] = {smem, smem + 2 * (size_t)WG_RC * WG_LD};
-    float* sG[2] = {smem + (size_t)WG_RC * WG_LD, smem + 3 * (size_t)WG_RC * WG_LD};
+    constexpr size_t WG_CHUNK = (size_t)WG_RC * WG_LD;
+    auto sLp = [&](int buf) { return smem + (size_t)(2 * buf) * WG_CHUNK; };
+    auto sGp = [&](int buf) { return smem + (size_t)(2 * buf + 1) * WG_CHUNK; };
     const int nchunk = (B + WG_RC - 1) / WG_RC;
     float sq = 0.f;
     // generic chunk loader: `wl` / `wg` floats per row from row-major sources with strides sl / sg
@@ -455,24 +456,27 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         const int rb = ch * WG_RC;
         for (int i = tid; i < WG_RC * (wl / 4); i += WG_TPB) {
             const int rr = i / (wl / 4), c4 = (i % (wl / 4)) * 4;
-            float* dst = sL[buf] + (size_t)rr * WG_LD + c4;
+            float* dst = sLp(buf) + (size_t)rr * WG_LD + c4;
             if (rb + rr < B) __pipeline_memcpy_async(dst, srcL + (size_t)(rb + rr) * strideL + offL + c4, 16);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int i = tid; i < WG_RC * (wg / 4); i += WG_TPB) {
             const int rr = i / (wg / 4), c4 = (i % (wg / 4)) * 4;
-            float* dst = sG[buf] + (size_t)rr * WG_LD + c4;
+            float* dst = sGp(buf) + (size_t)rr * WG_LD + c4;
             if (rb + rr < B) __pipeline_memcpy_async(dst, srcG + (size_t)(rb + rr) * strideG + offG + c4, 16);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __pipeline_commit();
     };
     float gscale = 1.0f;   // clip coefficient (FUSED)
+    const long long t_start = clock64();
     auto finish = [&]() {  // norm contribution (+ barrier and clip scale when fused)
+        if (FUSED && tid == 0) { const int c = bx + 40 * net; if (c < 256) g_dbg_cta[c] = clock64() - t_start; }
         const float tot = block_sum_256(sq, s_red);
         if (tid == 0 && tot != 0.f) atomicAdd(u.norm_sq, tot);
         if (FUSED) {
             grid_barrier(bar, bar_target);
+            if (tid == 0) { const int c = bx + 40 * net; if (c < 256) g_dbg_cta[256 + c] = clock64() - t_start; }
             const float nsq = __ldcg(u.norm_sq);
             if (u.max_grad_norm > 0.f) gscale = fminf(u.max_grad_norm / (sqrtf(nsq) + 1e-6f), 1.0f);
             if (bx == 0 && net == 0 && tid == 0 && u.stats && slot >= 0)
@@ -497,8 +501,8 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
             if (ch + 1 < nchunk) { stage(ch + 1, (ch + 1) & 1, nv.s_h1, H, k0, WG_TKT, nv.s_dz2, H, o0, WG_T); __pipeline_wait_prior(1); }
             else __pipeline_wait_prior(0);
             __syncthreads();
-            const float* L = sL[ch & 1];
-            const float* G = sG[ch & 1];
+            const float* L = sLp(ch & 1);
+            const float* G = sGp(ch & 1);
 #pragma unroll 16
             for (int rr = 0; rr < WG_RC; ++rr) {
                 const float2 l = *reinterpret_cast<const float2*>(L + (size_t)rr * WG_LD + 2 * tk);
@@ -558,70 +562,77 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         const int D = u.D;
         const int o0 = (bx - NT) * WG_T;
         const int o = tid % WG_T, dg = tid / WG_T;          // 4 d-groups of 8 per pass
-        float acc_a[8], acc_b[8];                           // up to 2 passes of 32 inputs (D <= 64)
+        // one sweep over up to 64 inputs: thread (o, dg) owns d = 16*dg + q, q < 16 (statically indexed
+        // accumulators: they must live in registers across the grid barrier of the fused variant)
+        float acc[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { acc_a[q] = 0.f; acc_b[q] = 0.f; }
+        for (int q = 0; q < 16; ++q) acc[q] = 0.f;
         float bsum = 0.f;
-        const int npass = (D + 31) / 32;
-        auto run_pass = [&](const int d0, float (&acc)[8], const bool with_bias) {
-            // x chunk [64][32] (plain loads: rows may be gathered), dz1 chunk [64][64] (cp.async)
-            auto stage1 = [&](int ch, int buf) {
-                const int rb = ch * WG_RC;
-                for (int i = tid; i < WG_RC * 32; i += WG_TPB) {
-                    const int rr = i / 32, dd = d0 + (i % 32);
-                    sL[buf][(size_t)rr * WG_LD + (i % 32)] =
-                        (rb + rr < B && dd < D) ? __ldg(u.obs + (size_t)row_of(u, mb_off, rb + rr) * D + dd) : 0.f;
-                }
-                for (int i = tid; i < WG_RC * (WG_T / 4); i += WG_TPB) {
-                    const int rr = i / (WG_T / 4), c4 = (i % (WG_T / 4)) * 4;
-                    float* dst = sG[buf] + (size_t)rr * WG_LD + c4;
-                    if (rb + rr < B) __pipeline_memcpy_async(dst, nv.s_dz1 + (size_t)(rb + rr) * H + o0 + c4, 16);
-                    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                __pipeline_commit();
-            };
-            stage1(0, 0);
-            for (int ch = 0; ch < nchunk; ++ch) {
-                if (ch + 1 < nchunk) { stage1(ch + 1, (ch + 1) & 1); __pipeline_wait_prior(1); }
-                else __pipeline_wait_prior(0);
-                __syncthreads();
-                const float* X = sL[ch & 1];
-                const float* G = sG[ch & 1];
-#pragma unroll 8
+        const int dw = (D + 3) & ~3;                        // staged input width (multiple of 4, <= 64)
+        auto stage1 = [&](int ch, int buf) {
+            const int rb = ch * WG_RC;
+            float* xs_ = sLp(buf);
+            float* gs_ = sGp(buf);
+            for (int i = tid; i < WG_RC * dw; i += WG_TPB) {
+                const int rr = i / dw, dd = i % dw;
+                xs_[(size_t)rr * WG_LD + dd] =
+                    (rb + rr < B && dd < D) ? __ldg(u.obs + (size_t)row_of(u, mb_off, rb + rr) * D + dd) : 0.f;
+            }
+            for (int i = tid; i < WG_RC * (WG_T / 4); i += WG_TPB) {
+                const int rr = i / (WG_T / 4), c4 = (i % (WG_T / 4)) * 4;
+                float* dst = gs_ + (size_t)rr * WG_LD + c4;
+                if (rb + rr < B) __pipeline_memcpy_async(dst, nv.s_dz1 + (size_t)(rb + rr) * H + o0 + c4, 16);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __pipeline_commit();
+        };
+        // columns >= dw of the x stage are never written: zero them once (both buffers)
+        for (int i = tid; i < 2 * WG_RC * WG_T; i += WG_TPB) {
+            const int bsel = i / (WG_RC * WG_T), r2 = (i / WG_T) % WG_RC, c2 = i % WG_T;
+            if (c2 >= dw) sLp(bsel)[(size_t)r2 * WG_LD + c2] = 0.f;
+        }
+        const bool active = 16 * dg < D;                    // this d-group has real inputs
+        stage1(0, 0);
+        for (int ch = 0; ch < nchunk; ++ch) {
+            if (ch + 1 < nchunk) { stage1(ch + 1, (ch + 1) & 1); __pipeline_wait_prior(1); }
+            else __pipeline_wait_prior(0);
+            __syncthreads();
+            const float* X = sLp(ch & 1);
+            const float* G = sGp(ch & 1);
+            if (active) {
+#pragma unroll 4
                 for (int rr = 0; rr < WG_RC; ++rr) {
                     const float g = G[(size_t)rr * WG_LD + o];
-                    const float4 xa4 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 8 * dg);
-                    const float4 xb4 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 8 * dg + 4);
-                    acc[0] = fmaf(xa4.x, g, acc[0]); acc[1] = fmaf(xa4.y, g, acc[1]);
-                    acc[2] = fmaf(xa4.z, g, acc[2]); acc[3] = fmaf(xa4.w, g, acc[3]);
-                    acc[4] = fmaf(xb4.x, g, acc[4]); acc[5] = fmaf(xb4.y, g, acc[5]);
-                    acc[6] = fmaf(xb4.z, g, acc[6]); acc[7] = fmaf(xb4.w, g, acc[7]);
-                    if (with_bias) bsum += g;
+                    const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg);
+                    const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg + 4);
+                    const float4 x2 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg + 8);
+                    const float4 x3 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg + 12);
+                    acc[0] = fmaf(x0.x, g, acc[0]); acc[1] = fmaf(x0.y, g, acc[1]); acc[2] = fmaf(x0.z, g, acc[2]); acc[3] = fmaf(x0.w, g, acc[3]);
+                    acc[4] = fmaf(x1.x, g, acc[4]); acc[5] = fmaf(x1.y, g, acc[5]); acc[6] = fmaf(x1.z, g, acc[6]); acc[7] = fmaf(x1.w, g, acc[7]);
+                    acc[8] = fmaf(x2.x, g, acc[8]); acc[9] = fmaf(x2.y, g, acc[9]); acc[10] = fmaf(x2.z, g, acc[10]); acc[11] = fmaf(x2.w, g, acc[11]);
+                    acc[12] = fmaf(x3.x, g, acc[12]); acc[13] = fmaf(x3.y, g, acc[13]); acc[14] = fmaf(x3.z, g, acc[14]); acc[15] = fmaf(x3.w, g, acc[15]);
+                    bsum += g;
                 }
-                __syncthreads();
             }
-        };
-        run_pass(0, acc_a, true);
-        if (npass > 1) run_pass(32, acc_b, false);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (8 * dg + q < D) sq += acc_a[q] * acc_a[q];
-            if (32 + 8 * dg + q < D) sq += acc_b[q] * acc_b[q];
+            __syncthreads();
         }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) if (16 * dg + q < D) sq += acc[q] * acc[q];
         if (dg == 0) sq += bsum * bsum;
         finish();
-        auto emit1 = [&](int d, float g) {
-            if (d >= D) return;
-            if (!FUSED) nv.g_w1t[(size_t)d * H + o0 + o] = g;
-            else {
-                const long long idx = pbase + (long long)d * H + o0 + o;
-                float m = u.adam_m[idx], v = u.adam_v[idx];
-                u.theta[idx] = adam_one(u.theta[idx], g * gscale, m, v, ad);
-                u.adam_m[idx] = m; u.adam_v[idx] = v;
-            }
-        };
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { emit1(8 * dg + q, acc_a[q]); emit1(32 + 8 * dg + q, acc_b[q]); }
+        for (int q = 0; q < 16; ++q) {
+            const int d = 16 * dg + q;
+            if (d < D) {
+                if (!FUSED) nv.g_w1t[(size_t)d * H + o0 + o] = acc[q];
+                else {
+                    const long long idx = pbase + (long long)d * H + o0 + o;
+                    float m = u.adam_m[idx], v = u.adam_v[idx];
+                    u.theta[idx] = adam_one(u.theta[idx], acc[q] * gscale, m, v, ad);
+                    u.adam_m[idx] = m; u.adam_v[idx] = v;
+                }
+            }
+        }
         if (dg == 0) {
             if (!FUSED) nv.g_b1[o0 + o] = bsum;
             else {
@@ -644,8 +655,8 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
             if (ch + 1 < nchunk) { stage(ch + 1, (ch + 1) & 1, nv.s_h2, H, k0, WG_T, nv.s_dout, DOUT_LD, 0, DOUT_LD); __pipeline_wait_prior(1); }
             else __pipeline_wait_prior(0);
             __syncthreads();
-            const float* Hh = sL[ch & 1];
-            const float* Dd = sG[ch & 1];
+            const float* Hh = sLp(ch & 1);
+            const float* Dd = sGp(ch & 1);
 #pragma unroll 8
             for (int rr = 0; rr < WG_RC; ++rr) {
                 const float h = Hh[(size_t)rr * WG_LD + k];

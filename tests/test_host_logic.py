@@ -1,0 +1,120 @@
+"""CPU tests of the host-side logic (no GPU, no compute kernels): replay-buffer index contract vs
+the oracle restatement of tianshou's VectorReplayBuffer semantics, the Batch
+container, config tables, compat shims, logger on-disk formats."""
+import dataclasses
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+
+def _filled_buffers(E=4, cap=7, seed=0):
+    from fsrl_b200.data.buffer import DeviceVectorReplayBuffer
+    from oracle.collector import OracleBuffer
+    rng = np.random.default_rng(seed)
+    buf = DeviceVectorReplayBuffer(E * cap, E, device="cpu")
+    buf.allocate(3, 2, "cpu")
+    ob = OracleBuffer(E * cap, E, 3, 2)
+    steps = rng.integers(2, 2 * cap, E)          # some envs wrap their ring
+    for e in range(E):
+        for t in range(steps[e]):
+            term, trunc = bool(rng.random() < 0.15), bool(rng.random() < 0.1)
+            ids = np.array([e])
+            ob.add(ids, rng.standard_normal((1, 3)).astype(np.float32), np.zeros((1, 2), np.float32),
+                   np.float32([t]), np.float32([0]), np.float32([0]), np.array([term]), np.array([trunc and not term]),
+                   np.zeros((1, 3), np.float32))
+    buf.terminated.copy_(torch.from_numpy(ob.terminated.astype(np.uint8)))
+    buf.truncated.copy_(torch.from_numpy(ob.truncated.astype(np.uint8)))
+    buf.rew.copy_(torch.from_numpy(ob.rew))
+    buf.ptr.copy_(torch.from_numpy(ob.ptr.astype(np.int32)))
+    buf.len.copy_(torch.from_numpy(ob.len.astype(np.int32)))
+    return buf, ob
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_buffer_index_contract_matches_oracle(seed):
+    from oracle.offpolicy import buffer_next
+    buf, ob = _filled_buffers(seed=seed)
+    idx = buf.sample_indices(0).numpy()
+    assert np.array_equal(idx, ob.sample_all())                       # sub-buffer order, chronological
+    assert len(buf) == int(ob.len.sum())
+    assert np.array_equal(np.sort(buf.unfinished_index().numpy()), np.sort(ob.unfinished_index()))
+    valid = torch.from_numpy(ob.sample_all())
+    assert np.array_equal(buf.next(valid).numpy(), buffer_next(ob, valid.numpy()))
+    np.random.seed(5)
+    samp = buf.sample_indices(64).numpy()
+    assert np.isin(samp, ob.sample_all()).all()
+    buf.reset()
+    assert len(buf) == 0 and buf.sample_indices(0).numel() == 0
+
+
+def test_batch_container():
+    from fsrl_b200.data import Batch
+    b = Batch(obs=np.arange(6).reshape(3, 2), info={"cost": np.array([0., 1., 0.])}, policy=Batch())
+    assert len(b) == 3 and b.info.cost[1] == 1.0
+    s = b[1:]
+    assert len(s) == 2 and s.info.cost.tolist() == [1.0, 0.0]
+    b.update(act=np.zeros(3))
+    assert "act" in b and b.get("missing", 7) == 7 and b.pop("act").shape == (3,)
+
+
+def test_config_tables_match_reference_defaults():
+    from fsrl_b200.config import cpo_cfg, ddpgl_cfg, ppol_cfg, sacl_cfg
+    p = ppol_cfg.TrainCfg()
+    assert (p.lr, p.target_kl, p.vf_coef, p.max_grad_norm, p.eps_clip, p.batch_size, p.repeat_per_collect,
+            p.episode_per_collect, p.hidden_sizes, p.lagrangian_pid) == \
+        (5e-4, 0.02, 0.25, 0.5, 0.2, 256, 4, 20, (128, 128), (0.05, 0.0005, 0.1))       # ppol_cfg.py:14-49
+    c = cpo_cfg.TrainCfg()
+    assert (c.lr, c.target_kl, c.max_backtracks, c.optim_critic_iters, c.l2_reg, c.batch_size) == \
+        (1e-3, 0.01, 100, 10, 0.001, 99999)                                                 # cpo_cfg.py:14-45
+    s = sacl_cfg.TrainCfg()
+    assert (s.actor_lr, s.critic_lr, s.alpha_lr, s.tau, s.n_step, s.gamma, s.update_per_step) == \
+        (5e-4, 1e-3, 3e-4, 0.05, 2, 0.97, 0.2)
+    d = ddpgl_cfg.MujocoBaseCfg()
+    assert (d.gamma, d.n_step, d.buffer_size, d.cost_limit, d.exploration_noise) == (0.99, 3, 800000, 25, 0.1)
+    assert ppol_cfg.Bullet10MCfg().epoch == 1000 and dataclasses.is_dataclass(p)
+
+
+def test_compat_shims_resolve_reference_imports():
+    import fsrl_b200.compat as compat
+    compat.install()
+    import gymnasium as gym
+    from tianshou.env import ShmemVectorEnv
+    from tianshou.utils.net.continuous import ActorProb
+    from fsrl.agent import PPOLagAgent
+    from fsrl.policy import PPOLagrangian
+    from fsrl.utils.exp_util import auto_name
+    env = gym.make("SafetyCarCircle-v0")
+    assert env.observation_space.shape == (8,) and env.action_space.shape == (2,)
+    assert env.spec.max_episode_steps == 300
+    assert auto_name({"a": 1, "b": 2}, {"a": 1, "b": 3}, "ppol") == "ppol-b_3"
+    with pytest.raises(KeyError):
+        gym.make("NoSuchTask-v0")
+
+
+def test_logger_formats(tmp_path):
+    from fsrl_b200.utils.exp_util import load_config_and_model
+    from fsrl_b200.utils.logger import BaseLogger
+    lg = BaseLogger(str(tmp_path), log_txt=True, name="run")
+    lg.save_config({"task": "SafetyCarCircle-v0", "hidden_sizes": (64, 64)}, verbose=False)
+    lg.setup_checkpoint_fn(lambda: {"model": {"w": torch.ones(2)}})
+    lg.store(tab="train", reward=1.0); lg.store(tab="train", reward=3.0)
+    lg.store_many("loss", "kl", [0.1, 0.3])
+    assert lg.get_mean("train/reward") == 2.0 and abs(lg.get_mean("loss/kl") - 0.2) < 1e-12
+    lg.save_checkpoint()
+    lg.write(100)
+    lines = open(os.path.join(tmp_path, "run", "progress.txt")).read().strip().split("\n")
+    assert lines[0].split("\t")[0] == "Steps" and lines[1].split("\t")[0] == "100"
+    cfg, model = load_config_and_model(os.path.join(tmp_path, "run"))
+    assert cfg["task"] == "SafetyCarCircle-v0" and torch.equal(model["model"]["w"], torch.ones(2))
+
+
+def test_env_registry_and_dims_without_gpu():
+    from fsrl_b200 import envs
+    for task, (D, A, T) in {"SafetyCarCircle-v0": (8, 2, 300), "SafetyCarRun-v0": (7, 2, 200),
+                            "SafetyBallCircle-v0": (8, 2, 200), "SafetyBallRun-v0": (7, 2, 100),
+                            "SafetyAntCircle-v0": (34, 8, 500), "SafetyPointGoal1Gymnasium-v0": (60, 2, 1000)}.items():
+        e = envs.make(task)
+        assert e.observation_space.shape == (D,) and e.action_space.shape == (A,) and e.spec.max_episode_steps == T

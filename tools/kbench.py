@@ -73,12 +73,27 @@ def bench_ppo(iters):
     print("wgrad tile CTA cycles [stage0 issue, chunk loop, finish]:", [c[11] - c[10], c[12] - c[11], c[13] - c[12]])
 
 
+def bench_fused():
+    import bench, ctypes
+    from fsrl_b200 import _lib
+    agent, trainer, col, buf, T = bench.build("cuda:0", 0)
+    bench.one_cycle(trainer)
+    torch.cuda.synchronize()
+    cc = (ctypes.c_longlong * 512)()
+    _lib.check(_lib.lib.fsrl_debug_cta_cycles(cc))
+    cc = list(cc)
+    print("fused wgrad: cycles to end of role compute, net0 roles [32 tiles | 4 L1 | 4 L3]:", cc[:40])
+    print("fused wgrad: cycles to barrier exit, net0:", cc[256:296])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what")
     ap.add_argument("--envs", type=int, default=2048)
     ap.add_argument("--T", type=int, default=300)
     a = ap.parse_args()
+    if a.what == "fused":
+        bench_fused()
     if a.what == "ppo":
         bench_ppo(a.T if a.T != 300 else 50)
     if a.what == "gae":
