@@ -181,6 +181,8 @@ SIGNATURES = {
     "fsrl_vec_dot": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),
     "fsrl_vec_axpby": (c_int, [c_f64, c_vp, c_f64, c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_vec_add_scaled": (c_int, [c_vp, c_f64, c_vp, c_vp, ctypes.c_longlong, c_vp]),
+    "fsrl_mse_head": (c_int, [c_vp, c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp, c_vp]),
+    "fsrl_standardize": (c_int, [c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_engine_wgrad_to": (c_int, [ctypes.POINTER(Engine), ctypes.POINTER(NetList), ctypes.POINTER(EngInput),
                                      ctypes.c_longlong, c_vp, c_vp]),
     "fsrl_nstep_prepare": (c_int, [ctypes.POINTER(OffPolicy), c_vp, c_int, c_vp]),

@@ -433,3 +433,69 @@ extern "C" int fsrl_engine_wgrad_to(const fsrl_engine_t* e, const fsrl_netlist_t
     WgradRoles roles = {nullptr, nullptr, nullptr, nullptr, nullptr, dst, 1, 1, 7};
     return eng_wgrad_roles(e, nl, in, B, 0, nullptr, roles, static_cast<cudaStream_t>(stream));
 }
+
+// ---- critic regression head + whole-batch advantage standardisation ---------------------------------
+namespace fsrl {
+// dout[i][0] = 2 (V_i - ret_i) / N for one critic slot; sums[0] += sum td^2
+__global__ void mse_head_kernel(const float* __restrict__ out, const float* __restrict__ ret, const int* __restrict__ perm,
+                                long long N, float* __restrict__ dout, double* __restrict__ sums) {
+    __shared__ double red[8];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    if (i < N) {
+        const long long r = perm ? (long long)perm[i] : i;
+        const float td = out[(size_t)i * 16] - ret[r];
+        float4 z = make_float4(2.0f * td / (float)N, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dout + (size_t)i * 16) = z;
+        z.x = 0.f;
+        *reinterpret_cast<float4*>(dout + (size_t)i * 16 + 4) = z;
+        *reinterpret_cast<float4*>(dout + (size_t)i * 16 + 8) = z;
+        *reinterpret_cast<float4*>(dout + (size_t)i * 16 + 12) = z;
+        s = (double)td * (double)td;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; atomicAdd(sums, t); }
+}
+
+// x <- (x - mean) / std (unbiased, no eps) over n elements: cpo.py:127-131 / trpo_lag.py:129-133
+__global__ void __launch_bounds__(1024) standardize_kernel(float* x, long long n) {
+    __shared__ double red[32];
+    __shared__ double s_mean, s_rstd;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) s += (double)x[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 32; ++w) t += red[w]; s_mean = t / (double)n; }
+    __syncthreads();
+    const float mean = (float)s_mean;
+    double q = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) { const float d = x[i] - mean; q += (double)(d * d); }
+    q = warp_sum(q);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 32; ++w) t += red[w]; s_rstd = 1.0 / sqrt(t / (double)(n - 1)); }
+    __syncthreads();
+    const float rstd = (float)s_rstd;
+    for (long long i = threadIdx.x; i < n; i += 1024) x[i] = (x[i] - mean) * rstd;
+}
+}  // namespace fsrl
+
+// head gradient of mean((ret - V)^2) for one critic (P-slot out/dout [bmax][16]); sums_dev[0] += sum td^2
+extern "C" int fsrl_mse_head(const float* out, const float* ret, const int* perm, long long N, float* dout,
+                             double* sums_dev, void* stream) {
+    FSRL_REQUIRE(out && ret && dout && sums_dev && N >= 1, "mse_head: bad arguments");
+    fsrl::mse_head_kernel<<<(unsigned)((N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, ret, perm, N, dout, sums_dev);
+    FSRL_LAUNCH_CHECK();
+    return FSRL_OK;
+}
+
+extern "C" int fsrl_standardize(float* x, long long n, void* stream) {
+    FSRL_REQUIRE(x && n >= 2, "standardize: need at least two elements");
+    fsrl::standardize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, n);
+    FSRL_LAUNCH_CHECK();
+    return FSRL_OK;
+}

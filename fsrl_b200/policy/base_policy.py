@@ -146,6 +146,18 @@ class BasePolicy(ABC, nn.Module):
             _lib.check(_lib.lib.fsrl_mlp_forward(ctypes.byref(m), x.data_ptr(), ip, n, out.data_ptr(), self._stream()))
         return out
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Parameters alias the device arena, so loading writes straight into it; derived copies (the
+        out-major W2 mirrors used by the backward kernels) are refreshed afterwards."""
+        self.arena
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        if hasattr(self, "_mirror_dirty"):
+            self._mirror_dirty = True
+        eng = getattr(self, "_eng", None)
+        if eng is not None:
+            eng.sync_mirror(self.arena.slots)
+        return out
+
     # ---- rollout descriptor (consumed by FastCollector) ----------------------------------------------
     def _rollout_mode(self) -> int:
         if self._deterministic_eval and not self.training:

@@ -69,10 +69,8 @@ class CPO(TrustRegionMixin, BasePolicy):
     def process_fn(self, batch, buffer, indices) -> DeviceBatch:
         batch = self.compute_gae_returns(batch, buffer, indices, self._lambda)          # :126
         if self._norm_adv:                                                             # :127-131
-            adv = batch.adv
-            mean = adv.mean(dim=1, keepdim=True)
-            std = adv.std(dim=1, keepdim=True)
-            adv.sub_(mean).div_(std)
+            for c in range(self.critics_num):
+                _lib.check(_lib.lib.fsrl_standardize(batch.adv[c].data_ptr(), batch.n, self._stream()))
         # old distribution (:133-144): mean from one actor pass; std is state independent
         z = self.net_forward(0, batch.obs)
         mu = self.actor._max * torch.tanh(z) if not self.actor._unbounded else z

@@ -54,8 +54,8 @@ class TRPOLagrangian(TrustRegionMixin, LagrangianPolicy):
     def process_fn(self, batch, buffer, indices) -> DeviceBatch:
         batch = self.compute_gae_returns(batch, buffer, indices, self._lambda)
         if self._norm_adv:                                                   # :129-133
-            adv = batch.adv
-            adv.sub_(adv.mean(dim=1, keepdim=True)).div_(adv.std(dim=1, keepdim=True))
+            for c in range(self.critics_num):
+                _lib.check(_lib.lib.fsrl_standardize(batch.adv[c].data_ptr(), batch.n, self._stream()))
         batch.mean_old = torch.empty((batch.n, self.arena.slots[0].out), dtype=torch.float32, device=self.device)
         batch.std_old = torch.empty_like(batch.mean_old)
         return batch

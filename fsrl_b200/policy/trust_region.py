@@ -93,17 +93,14 @@ class TrustRegionMixin:
         inp = eng.make_input(batch.obs, perm)
         eng.forward(crit, inp, n, save=True)
         stats = {}
-        l2 = 0.0
         for i, s in enumerate(crit):
-            v = eng.slot_view(s, "out")[:n, 0]
-            ret = batch.ret[i] if perm is None else batch.ret[i][perm.long()]
-            td = v - ret
-            dout = eng.slot_view(s, "dout")
-            dout[:n].zero_()
-            dout[:n, 0] = 2.0 * td / n
+            self._sums.zero_()
+            _lib.check(_lib.lib.fsrl_mse_head(eng.slot_view(s, "out").data_ptr(), batch.ret[i].data_ptr(),
+                                              None if perm is None else perm.data_ptr(), n,
+                                              eng.slot_view(s, "dout").data_ptr(), self._sums.data_ptr(), self._s()))
             th = self.arena.theta[s.offset:s.offset + s.size]
-            reg = float((th * th).sum().item()) * self._l2_reg
-            stats["loss/vf" + str(i)] = float((td * td).mean().item()) + reg
+            reg = (self._dotp(th, th) * self._l2_reg) if self._l2_reg else 0.0
+            stats["loss/vf" + str(i)] = float(self._sums[0].item()) / n + reg
         eng.backward(crit, n)
         eng.wgrad(crit, inp, n)
         self._critic_t += 1

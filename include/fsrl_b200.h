@@ -319,6 +319,11 @@ int fsrl_cpo_hvp(const fsrl_cpo_t* d, const float* v, float* v_w2n_scratch, floa
 int fsrl_vec_dot(const float* a, const float* b, long long n, double* out_dev, void* stream);
 int fsrl_vec_axpby(double a, const float* x, double b, float* y, long long n, void* stream);
 int fsrl_vec_add_scaled(const float* a, double s, const float* b, float* out, long long n, void* stream);
+/* critic regression head (cpo.py:147-157, trpo_lag.py:135-146): dout[i][0] = 2 (V_i - ret_i) / N,
+ * sums_dev[0] += sum td^2;  fsrl_standardize: x <- (x - mean) / std (unbiased), cpo.py:127-131 */
+int fsrl_mse_head(const float* out, const float* ret, const int* perm, long long N, float* dout,
+                  double* sums_dev, void* stream);
+int fsrl_standardize(float* x, long long n, void* stream);
 int fsrl_engine_wgrad_to(const fsrl_engine_t* e, const fsrl_netlist_t* net1, const fsrl_eng_input_t* in,
                          long long B, float* dst, void* stream);
 
