@@ -401,7 +401,7 @@ __global__ void ppo_gather_kernel(const fsrl_ppo_update_t u, long long n) {
 // ------------------------------------------------------------------------------------------
 constexpr int WG_TPB = 256, WG_T = 64, WG_TKT = 32, WG_RC = 128, WG_LD = WG_T + 4;
 // shared memory of a weight-gradient role: 2 stages x (L chunk + G chunk), each [WG_RC][WG_LD]
-constexpr size_t WG_SMEM_FLOATS = 2 * 2 * (size_t)WG_RC * WG_LD;
+constexpr size_t WG_SMEM_FLOATS = 2 * 2 * (size_t)WG_RC * WG_LD + 65 * WG_T + (4 * 16 + 4) * WG_T;
 
 // Adam hyper-parameters of one optimiser step (torch.optim.Adam scalars, python doubles -> f32)
 struct AdamStep {
@@ -561,14 +561,16 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         // ---- layer 1: dW1t[d][o] = sum_r x[r][d] * dz1[r][o];  db1[o] = sum_r dz1[r][o] ---------
         const int D = u.D;
         const int o0 = (bx - NT) * WG_T;
-        const int o = tid % WG_T, dg = tid / WG_T;          // 4 d-groups of 8 per pass
-        // one sweep over up to 64 inputs: thread (o, dg) owns d = 16*dg + q, q < 16 (statically indexed
-        // accumulators: they must live in registers across the grid barrier of the fused variant)
-        float acc[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+        const int o = tid % WG_T;
+        // thread (o, rg): column o of the tile, row group rg = tid / 64 (rows rr = rg mod 4): all four
+        // warp pairs work even when D is tiny.  Inputs are processed in blocks of 16 (statically indexed
+        // accumulators); the four row-group partials are summed through shared memory into fin[d][o],
+        // which survives the grid barrier of the fused variant.
+        const int rg = tid / WG_T;
         float bsum = 0.f;
         const int dw = (D + 3) & ~3;                        // staged input width (multiple of 4, <= 64)
+        float* fin = smem + 4 * WG_CHUNK;                   // [64][WG_T] final gradients (+ [WG_T] bias)
+        float* part = fin + 65 * WG_T;                      // [4][16][WG_T] row-group partials
         auto stage1 = [&](int ch, int buf) {
             const int rb = ch * WG_RC;
             float* xs_ = sLp(buf);
@@ -586,59 +588,71 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
             }
             __pipeline_commit();
         };
-        // columns >= dw of the x stage are never written: zero them once (both buffers)
-        for (int i = tid; i < 2 * WG_RC * WG_T; i += WG_TPB) {
-            const int bsel = i / (WG_RC * WG_T), r2 = (i / WG_T) % WG_RC, c2 = i % WG_T;
-            if (c2 >= dw) sLp(bsel)[(size_t)r2 * WG_LD + c2] = 0.f;
-        }
-        const bool active = 16 * dg < D;                    // this d-group has real inputs
-        stage1(0, 0);
-        for (int ch = 0; ch < nchunk; ++ch) {
-            if (ch + 1 < nchunk) { stage1(ch + 1, (ch + 1) & 1); __pipeline_wait_prior(1); }
-            else __pipeline_wait_prior(0);
-            __syncthreads();
-            const float* X = sLp(ch & 1);
-            const float* G = sGp(ch & 1);
-            if (active) {
+        const int npass = (D + 15) / 16;
+        for (int ps = 0; ps < npass; ++ps) {
+            const int d0 = 16 * ps;
+            float acc[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+            stage1(0, 0);
+            for (int ch = 0; ch < nchunk; ++ch) {
+                if (ch + 1 < nchunk) { stage1(ch + 1, (ch + 1) & 1); __pipeline_wait_prior(1); }
+                else __pipeline_wait_prior(0);
+                __syncthreads();
+                const float* X = sLp(ch & 1);
+                const float* G = sGp(ch & 1);
 #pragma unroll 4
-                for (int rr = 0; rr < WG_RC; ++rr) {
+                for (int rr = rg; rr < WG_RC; rr += 4) {
                     const float g = G[(size_t)rr * WG_LD + o];
-                    const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg);
-                    const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg + 4);
-                    const float4 x2 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg + 8);
-                    const float4 x3 = *reinterpret_cast<const float4*>(X + (size_t)rr * WG_LD + 16 * dg + 12);
-                    acc[0] = fmaf(x0.x, g, acc[0]); acc[1] = fmaf(x0.y, g, acc[1]); acc[2] = fmaf(x0.z, g, acc[2]); acc[3] = fmaf(x0.w, g, acc[3]);
-                    acc[4] = fmaf(x1.x, g, acc[4]); acc[5] = fmaf(x1.y, g, acc[5]); acc[6] = fmaf(x1.z, g, acc[6]); acc[7] = fmaf(x1.w, g, acc[7]);
-                    acc[8] = fmaf(x2.x, g, acc[8]); acc[9] = fmaf(x2.y, g, acc[9]); acc[10] = fmaf(x2.z, g, acc[10]); acc[11] = fmaf(x2.w, g, acc[11]);
-                    acc[12] = fmaf(x3.x, g, acc[12]); acc[13] = fmaf(x3.y, g, acc[13]); acc[14] = fmaf(x3.z, g, acc[14]); acc[15] = fmaf(x3.w, g, acc[15]);
-                    bsum += g;
+                    const float* xr = X + (size_t)rr * WG_LD + d0;
+#pragma unroll
+                    for (int q4 = 0; q4 < 16; q4 += 4) {
+                        if (d0 + q4 < dw) {
+                            const float4 x4 = *reinterpret_cast<const float4*>(xr + q4);
+                            acc[q4] = fmaf(x4.x, g, acc[q4]); acc[q4 + 1] = fmaf(x4.y, g, acc[q4 + 1]);
+                            acc[q4 + 2] = fmaf(x4.z, g, acc[q4 + 2]); acc[q4 + 3] = fmaf(x4.w, g, acc[q4 + 3]);
+                        }
+                    }
+                    if (ps == 0) bsum += g;
                 }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) part[((size_t)rg * 16 + q) * WG_T + o] = acc[q];
+            if (ps == 0) part[(size_t)(4 * 16) * WG_T + rg * WG_T + o] = bsum;
+            __syncthreads();
+            for (int i = tid; i < 16 * WG_T; i += WG_TPB) {
+                const int q = i / WG_T, oo = i % WG_T;
+                fin[(size_t)(d0 + q) * WG_T + oo] = part[((size_t)0 * 16 + q) * WG_T + oo] + part[((size_t)1 * 16 + q) * WG_T + oo] +
+                                                   part[((size_t)2 * 16 + q) * WG_T + oo] + part[((size_t)3 * 16 + q) * WG_T + oo];
+            }
+            if (ps == 0 && tid < WG_T) {
+                const float* bp = part + (size_t)(4 * 16) * WG_T;
+                fin[(size_t)64 * WG_T + tid] = bp[tid] + bp[WG_T + tid] + bp[2 * WG_T + tid] + bp[3 * WG_T + tid];
             }
             __syncthreads();
         }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) if (16 * dg + q < D) sq += acc[q] * acc[q];
-        if (dg == 0) sq += bsum * bsum;
+        // every thread now owns the outputs (d, o) with d = rg, rg + 4, ... < D; bias: rg == 0
+        for (int d = rg; d < D; d += 4) { const float g = fin[(size_t)d * WG_T + o]; sq += g * g; }
+        if (rg == 0) { const float g = fin[(size_t)64 * WG_T + o]; sq += g * g; }
         finish();
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int d = 16 * dg + q;
-            if (d < D) {
-                if (!FUSED) nv.g_w1t[(size_t)d * H + o0 + o] = acc[q];
-                else {
-                    const long long idx = pbase + (long long)d * H + o0 + o;
-                    float m = u.adam_m[idx], v = u.adam_v[idx];
-                    u.theta[idx] = adam_one(u.theta[idx], acc[q] * gscale, m, v, ad);
-                    u.adam_m[idx] = m; u.adam_v[idx] = v;
-                }
+        for (int d = rg; d < D; d += 4) {
+            const float g = fin[(size_t)d * WG_T + o];
+            if (!FUSED) nv.g_w1t[(size_t)d * H + o0 + o] = g;
+            else {
+                const long long idx = pbase + (long long)d * H + o0 + o;
+                float m = u.adam_m[idx], v = u.adam_v[idx];
+                u.theta[idx] = adam_one(u.theta[idx], g * gscale, m, v, ad);
+                u.adam_m[idx] = m; u.adam_v[idx] = v;
             }
         }
-        if (dg == 0) {
-            if (!FUSED) nv.g_b1[o0 + o] = bsum;
+        if (rg == 0) {
+            const float g = fin[(size_t)64 * WG_T + o];
+            if (!FUSED) nv.g_b1[o0 + o] = g;
             else {
                 const long long idx = pbase + (long long)D * H + o0 + o;
                 float m = u.adam_m[idx], v = u.adam_v[idx];
-                u.theta[idx] = adam_one(u.theta[idx], bsum * gscale, m, v, ad);
+                u.theta[idx] = adam_one(u.theta[idx], g * gscale, m, v, ad);
                 u.adam_m[idx] = m; u.adam_v[idx] = v;
             }
         }
