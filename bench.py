@@ -184,6 +184,8 @@ def run_ours(args):
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_wall0 = time.time()
+    from fsrl_b200 import _lib as _fl
+    launches0 = int(_fl.lib.fsrl_launch_count())
     ev0.record()
     collect_s = 0.0
     for _ in range(args.steps):
@@ -193,6 +195,7 @@ def run_ours(args):
     ev1.record()
     torch.cuda.synchronize()
     t_wall = time.time() - t_wall0
+    launches = int(_fl.lib.fsrl_launch_count()) - launches0
     ms = ev0.elapsed_time(ev1)
     if dist is not None:
         t = torch.tensor([ms], device=device)
@@ -222,7 +225,6 @@ def run_ours(args):
     ach = flops_a / ((ph[0] + ph[1]) * 1e-3) / 1e12
     gms, gn = gae_time(buf, agent.policy)
     gae_bytes = gn * 42
-    launches = args.steps * (T * 2 + 2 + 6 + REPEAT * n_mb * 3 + 4)
     out = {
         "metric": "env-steps/sec (collect+update) SafetyCarCircle-v0 PPO-Lag",
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -243,7 +245,7 @@ def run_ours(args):
         "roofline": {"kernel": "ppo_fwd_kernel<256> + ppo_bwd_kernel<256>", "bound": "tensor", "achieved": ach,
                      "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
                      "traffic": None, "peak_source": how + " bf16 burst",
-                     "note": "fp32 SIMT FMA kernel (no tensor cores yet); flops = fwd+bwd of 3 MLPs on a 256-row minibatch",
+                     "note": "fp32-faithful 3xTF32 split-operand mma.sync (legacy tensor path, 3 MMAs per fp32 product); flops = algorithmic fwd+bwd of 3 MLPs on a 256-row minibatch; latency-bound (9600 dependent optimiser steps of 256 rows)",
                      "phase_ms": {"fwd": ph[0], "bwd": ph[1], "wgrad": ph[2], "adam": ph[3]}},
         "roofline_gae": {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm",
                          "achieved": gae_bytes / (gms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",

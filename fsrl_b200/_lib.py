@@ -155,6 +155,7 @@ SIGNATURES = {
     "fsrl_abi_version": (c_int, []),
     "fsrl_abi_sizeof": (c_size, [c_int]),
     "fsrl_sm_count": (c_int, []),
+    "fsrl_launch_count": (ctypes.c_ulonglong, []),
     "fsrl_gae_dual_workspace_bytes": (c_size, [c_i64]),
     "fsrl_gae_dual": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_f64, c_f64,
                               c_f32p, c_f32p, c_i64, c_i64, c_int, c_vp, c_size, c_vp]),

@@ -29,6 +29,8 @@ int sm_count() {
 
 extern "C" const char* fsrl_last_error(void) { return fsrl::g_err; }
 extern "C" int fsrl_abi_version(void) { return 1; }
+namespace fsrl { unsigned long long g_launches = 0; }
+extern "C" unsigned long long fsrl_launch_count(void) { return fsrl::g_launches; }
 extern "C" int fsrl_sm_count(void) { return fsrl::sm_count(); }
 
 // sizes of the descriptor structs, checked against the ctypes mirrors at import time

@@ -33,6 +33,7 @@ void set_error(const char* fmt, ...);
 
 #define FSRL_LAUNCH_CHECK()                                                            \
     do {                                                                               \
+        ++::fsrl::g_launches;                                                          \
         cudaError_t e__ = cudaGetLastError();                                          \
         if (e__ != cudaSuccess) {                                                      \
             ::fsrl::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__,         \
@@ -40,6 +41,8 @@ void set_error(const char* fmt, ...);
             return FSRL_ECUDA;                                                         \
         }                                                                              \
     } while (0)
+
+extern unsigned long long g_launches;  // kernels launched by this library (host-side count)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

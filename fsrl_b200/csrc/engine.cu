@@ -551,6 +551,7 @@ int eng_wgrad_roles(const fsrl_engine_t* e, const fsrl_netlist_t* nl, const fsrl
         // start from zero and let every part accumulate (atomically when the rows are split)
         FSRL_REQUIRE(roles.dst == nullptr || nl->n == 1, "engine_wgrad: dst override needs a single net");
         eng_zero_grad_kernel<<<dim3(64, nl->n), 256, 0, s>>>(*e, *nl, roles.dst);
+        ++g_launches;
         accumulate = 1;
     }
     ENG_DISPATCH_H(nl->nets[0].H, {

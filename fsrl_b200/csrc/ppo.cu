@@ -936,6 +936,7 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
         int mo = mb_off, bb = B, sl = slot;
         unsigned long long* barp = u.barrier;
         void* args[] = {&uu, &mo, &bb, &ad, &barp, &target, &sl};
+        ++g_launches;
         FSRL_CUDA(cudaLaunchCooperativeKernel((void*)ppo_wgrad_adam_kernel<H>, gB, dim3(WG_TPB), args, smemW, s));
         return FSRL_OK;
     }

@@ -34,6 +34,9 @@ const char* fsrl_last_error(void);
 int fsrl_abi_version(void);
 size_t fsrl_abi_sizeof(int which); /* sizeof() of the descriptor structs, for binding self-checks */
 int fsrl_sm_count(void);
+/* Number of kernels this library has launched so far in this process (host-side counter,
+ * one per checked launch). bench.py reports the difference across its timed region. */
+unsigned long long fsrl_launch_count(void);
 
 /* ---- a6/a7: dual GAE(lambda) -------------------------------------------------------
  * Replaces fsrl/policy/base_policy.py:524-540 (gae_return, numba) together with the
