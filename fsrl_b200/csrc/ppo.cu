@@ -34,8 +34,24 @@ constexpr int DOUT_LD = 16;   // scratch row stride of dOut (cols [A, 2A) carry 
 
 __device__ long long g_dbg_clock[16];
 __device__ long long g_dbg_cta[512];
+#ifdef FSRL_DEBUG_CLOCKS   // per-phase clock64() stamps of CTA 0 (tools/kbench.py reads them back)
 #define DBG_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
 #define DBG_W(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
+#define DBG_CTA(i, v) do { if ((i) < 512) g_dbg_cta[i] = (v); } while (0)
+#else
+#define DBG_T(i) do { } while (0)
+#define DBG_W(i) do { } while (0)
+#define DBG_CTA(i, v) do { } while (0)
+#endif
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor in the stream is still running; everything it reads
+// that the predecessor writes must come after pdl_wait() (= predecessor complete + flushed).
+// pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as SM resources free up.  Every
+// kernel of the minibatch chain triggers only AFTER its own wait, so "predecessor complete"
+// is transitive along the chain.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ int slot_mb(const fsrl_ppo_update_t& u, int mb_off) { return mb_off / u.batch_size; }
 
@@ -108,12 +124,15 @@ ppo_fwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     float* xs = smem;                                   // [R][inp]
     float* h1 = xs + (size_t)TT::R * inp;               // [R][LDA]
     float* bs = h1 + (size_t)TT::R * TT::LDA;           // [H][SLAB_LDB]  (aliased by the reduce buffer)
-    if (net == 0 && slab == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by the previous step's Adam
-    slab_load<H>(nv.m.w2t, H, c0, bs);                  // in flight during layer 1
+    // observations are constant during a repeat: loaded while the previous optimiser step drains
     for (int i = tid; i < TT::R * inp; i += MLP_TPB) {
         const int r = i / inp, k = i % inp;
         xs[i] = (r0 + r < B && k < D) ? u.obs[(size_t)row_of(u, mb_off, r0 + r) * D + k] : 0.f;
     }
+    pdl_wait();                                         // parameters of the previous step are final
+    pdl_trigger();
+    if (net == 0 && slab == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by the previous step's Adam
+    slab_load<H>(nv.m.w2t, H, c0, bs);                  // in flight during layer 1
     __syncthreads();
     float c[TT::MT][TT::NT][4];
     tc_init_bias<H>(c, nv.m.b1);
@@ -171,14 +190,8 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
     __shared__ float s_red[MLP_TPB / 32];
     __shared__ float s_mean[2], s_rstd[2];
     DBG_T(0);
-    // h2 tile first (needed first), then the W2 slab: both in flight while the scalars below load
-    for (int el = tid; el < TT::R * (H / 4); el += MLP_TPB) {
-        const int row = el / (H / 4), k4 = (el % (H / 4)) * 4;
-        float* dst = h2 + (size_t)row * TT::LDA + k4;
-        if (r0 + row < B) __pipeline_memcpy_async(dst, nv.s_h2 + (size_t)(r0 + row) * H + k4, 16);
-        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __pipeline_commit();
+    // everything that does not depend on the forward launch (weights, per-row loss inputs) is
+    // requested before pdl_wait(): it overlaps the forward kernel's tail
     slab_load<H>(nv.w2n, H, c0, bs);                    // W2 in [out][in] layout: rows o, columns k-slab
     for (int i = tid; i < H * wout; i += MLP_TPB) w3s[i] = __ldg(nv.m.w3t + i);
     // per-row scalars of the loss: issued now, consumed after the head
@@ -208,7 +221,16 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         s_mean[tid] = ms[0];
         s_rstd[tid] = ms[1];
     }
-    __pipeline_wait_prior(1);                            // h2 tile landed (the slab may still be in flight)
+    pdl_wait();                                          // h1 / h2 of this minibatch are complete
+    pdl_trigger();
+    for (int el = tid; el < TT::R * (H / 4); el += MLP_TPB) {
+        const int row = el / (H / 4), k4 = (el % (H / 4)) * 4;
+        float* dst = h2 + (size_t)row * TT::LDA + k4;
+        if (r0 + row < B) __pipeline_memcpy_async(dst, nv.s_h2 + (size_t)(r0 + row) * H + k4, 16);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);                            // slab (requested long ago) and h2 tile landed
     __syncthreads();
 
     DBG_T(2);
@@ -468,15 +490,18 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         }
         __pipeline_commit();
     };
+    pdl_wait();            // dz1 / dz2 / dout of this minibatch are complete
+    pdl_trigger();
     float gscale = 1.0f;   // clip coefficient (FUSED)
     const long long t_start = clock64();
+    (void)t_start;
     auto finish = [&]() {  // norm contribution (+ barrier and clip scale when fused)
-        if (FUSED && tid == 0) { const int c = bx + 40 * net; if (c < 256) g_dbg_cta[c] = clock64() - t_start; }
+        if (FUSED && tid == 0) { const int c = bx + 40 * net; DBG_CTA(c, clock64() - t_start); }
         const float tot = block_sum_256(sq, s_red);
         if (tid == 0 && tot != 0.f) atomicAdd(u.norm_sq, tot);
         if (FUSED) {
             grid_barrier(bar, bar_target);
-            if (tid == 0) { const int c = bx + 40 * net; if (c < 256) g_dbg_cta[256 + c] = clock64() - t_start; }
+            if (tid == 0) { const int c = bx + 40 * net; DBG_CTA(256 + c, clock64() - t_start); }
             const float nsq = __ldcg(u.norm_sq);
             if (u.max_grad_norm > 0.f) gscale = fminf(u.max_grad_norm / (sqrtf(nsq) + 1e-6f), 1.0f);
             if (bx == 0 && net == 0 && tid == 0 && u.stats && slot >= 0)
@@ -722,8 +747,9 @@ ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     extern __shared__ __align__(16) float smem[];
     AdamStep ad = {};
     const long long t0 = clock64();
+    (void)t0;
     ppo_wgrad_role<H, false>(u, mb_off, B, blockIdx.x, blockIdx.y, smem, ad, nullptr, 0ULL, -1);
-    if (threadIdx.x == 0 && blockIdx.x + gridDim.x * blockIdx.y < 512) g_dbg_cta[blockIdx.x + gridDim.x * blockIdx.y] = clock64() - t0;
+    if (threadIdx.x == 0) DBG_CTA(blockIdx.x + gridDim.x * blockIdx.y, clock64() - t0);
 }
 
 // weight gradients + clip_grad_norm_ + Adam in one cooperative launch (single-GPU path)
@@ -893,23 +919,42 @@ __global__ void __launch_bounds__(256) ppo_adv_stats_kernel(const fsrl_ppo_updat
 extern "C" int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
 extern "C" int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
 
+// One link of the per-minibatch kernel chain: programmatic dependent launch (see pdl_wait), plus
+// the cooperative attribute for the kernel that contains the grid barrier.
+template <class... KArgs, class... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                bool cooperative, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+    if (cooperative) { at[n].id = cudaLaunchAttributeCooperative; at[n].val.cooperative = 1; ++n; }
+    cfg.attrs = at; cfg.numAttrs = n;
+    ++g_launches;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int H>
 static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, int slot,
                                 long long adam_t, long long bar_count, cudaStream_t s) {
     using TT = MlpTile<H>;
     const size_t smemF = sizeof(float) * ((size_t)TT::R * TT::in_pad(u.D) + (size_t)TT::R * TT::LDA + slab_buf_floats<H>());
-    const size_t smemB = sizeof(float) * (2 * (size_t)TT::R * TT::LDA + slab_buf_floats<H>() + (size_t)H * MLP_MAX_OUT + (size_t)TT::R * DOUT_LD);
-    static bool attr_done = false;
-    if (!attr_done) {
+    const size_t smemB = sizeof(float) * (2 * (size_t)TT::R * TT::LDA + slab_buf_floats<H>() + (size_t)H * (u.actor_out > 1 ? u.actor_out : 1) + (size_t)TT::R * DOUT_LD);
+    static size_t setF = 0, setB = 0;                   // largest opt-in so far (D / actor_out vary per policy)
+    if (smemF > setF) {
         FSRL_CUDA(cudaFuncSetAttribute(ppo_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
+        setF = smemF;
+    }
+    if (smemB > setB) {
         FSRL_CUDA(cudaFuncSetAttribute(ppo_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        attr_done = true;
+        setB = smemB;
     }
     const dim3 gA((B + TT::R - 1) / TT::R, H / SLAB_NS, u.n_nets);
-    ppo_fwd_kernel<H><<<gA, MLP_TPB, smemF, s>>>(u, mb_off, B);
-    FSRL_LAUNCH_CHECK();
-    ppo_bwd_kernel<H><<<gA, MLP_TPB, smemB, s>>>(u, mb_off, B, slot);
-    FSRL_LAUNCH_CHECK();
+    FSRL_CUDA(launch_chain(ppo_fwd_kernel<H>, gA, dim3(MLP_TPB), smemF, s, false, u, mb_off, B));
+    FSRL_CUDA(launch_chain(ppo_bwd_kernel<H>, gA, dim3(MLP_TPB), smemB, s, false, u, mb_off, B, slot));
     constexpr int NTT = H / WG_T;
     const dim3 gB((H / WG_TKT) * NTT + 2 * NTT, u.n_nets);
     const size_t smemW = sizeof(float) * WG_SMEM_FLOATS;
@@ -932,16 +977,11 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
         // single GPU: gradients never leave the registers -- tiles -> norm -> barrier -> clip + Adam
         AdamStep ad = {(float)(1.0 - b1), (float)b2, (float)(1.0 - b2), bc2s, (float)u.adam_eps, neg_step};
         unsigned long long target = (unsigned long long)(bar_count + 1) * gB.x * gB.y;
-        fsrl_ppo_update_t uu = u;
-        int mo = mb_off, bb = B, sl = slot;
-        unsigned long long* barp = u.barrier;
-        void* args[] = {&uu, &mo, &bb, &ad, &barp, &target, &sl};
-        ++g_launches;
-        FSRL_CUDA(cudaLaunchCooperativeKernel((void*)ppo_wgrad_adam_kernel<H>, gB, dim3(WG_TPB), args, smemW, s));
+        FSRL_CUDA(launch_chain(ppo_wgrad_adam_kernel<H>, gB, dim3(WG_TPB), smemW, s, true, u, mb_off, B, ad, u.barrier,
+                               target, slot));
         return FSRL_OK;
     }
-    ppo_wgrad_kernel<H><<<gB, WG_TPB, smemW, s>>>(u, mb_off, B);
-    FSRL_LAUNCH_CHECK();
+    FSRL_CUDA(launch_chain(ppo_wgrad_kernel<H>, gB, dim3(WG_TPB), smemW, s, false, u, mb_off, B));
     if (u.world > 1) {
         // data parallel: ONE all-reduce of the flat gradient buffer per optimiser step, then the
         // global norm of the reduced gradient (the local partial norms are meaningless now)
@@ -1079,7 +1119,7 @@ static int ppo_time_phases(const fsrl_ppo_update_t& u0, int B, int iters, float*
     using TT = MlpTile<H>;
     fsrl_ppo_update_t u = u0;
     const size_t smemF = sizeof(float) * ((size_t)TT::R * TT::in_pad(u.D) + (size_t)TT::R * TT::LDA + slab_buf_floats<H>());
-    const size_t smemB = sizeof(float) * (2 * (size_t)TT::R * TT::LDA + slab_buf_floats<H>() + (size_t)H * MLP_MAX_OUT + (size_t)TT::R * DOUT_LD);
+    const size_t smemB = sizeof(float) * (2 * (size_t)TT::R * TT::LDA + slab_buf_floats<H>() + (size_t)H * (u.actor_out > 1 ? u.actor_out : 1) + (size_t)TT::R * DOUT_LD);
     FSRL_CUDA(cudaFuncSetAttribute(ppo_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
     FSRL_CUDA(cudaFuncSetAttribute(ppo_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     cudaEvent_t e[5];
