@@ -66,14 +66,18 @@ struct MlpTile {
     }
 };
 
+// x = hi + lo with hi, lo representable in TF32 (10 explicit mantissa bits).  Round-to-nearest,
+// ties away from zero -- the result of cvt.rna.tf32.f32 -- done with integer ops: the cvt runs on
+// the quarter-rate conversion pipe and was the bound of every split-operand GEMM here
+// (measured: tools/micro/mma_rate.cu, profiles/r1_mma_rate.txt).
+__device__ __forceinline__ uint32_t round_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = round_tf32(x);
+    lo = round_tf32(x - __uint_as_float(hi));
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -142,11 +146,11 @@ __device__ __forceinline__ void tc_gemm(float (&c)[MlpTile<H>::MT][MlpTile<H>::N
                     split_tf32(a[4], ah[2], al[2]);
                     split_tf32(a[(size_t)8 * lda + 4], ah[3], al[3]);
 #pragma unroll
-                    for (int nt = 0; nt < TT::NT; ++nt) {
-                        mma_tf32(c[mt][nt], al, bh[nt]);
-                        mma_tf32(c[mt][nt], ah, bl[nt]);
-                        mma_tf32(c[mt][nt], ah, bh[nt]);
-                    }
+                    for (int nt = 0; nt < TT::NT; ++nt) mma_tf32(c[mt][nt], al, bh[nt]);   // small terms first; the three
+#pragma unroll
+                    for (int nt = 0; nt < TT::NT; ++nt) mma_tf32(c[mt][nt], ah, bl[nt]);   // passes keep dependent MMAs
+#pragma unroll
+                    for (int nt = 0; nt < TT::NT; ++nt) mma_tf32(c[mt][nt], ah, bh[nt]);   // TT::NT instructions apart
                 }
             }
         }
@@ -248,13 +252,14 @@ __device__ __forceinline__ void slab_gemm(const float* A, int lda, const float* 
             split_tf32(a[4], ah[2], al[2]);
             split_tf32(a[(size_t)8 * lda + 4], ah[3], al[3]);
 #pragma unroll
-            for (int nt = 0; nt < NTS; ++nt) {
-                mma_tf32(c[mt][nt], al, bh[nt]);
-                mma_tf32(c[mt][nt], ah, bl[nt]);
-                mma_tf32(c[mt][nt], ah, bh[nt]);
-            }
+            for (int nt = 0; nt < NTS; ++nt) mma_tf32(c[mt][nt], al, bh[nt]);   // small terms first; the three
+#pragma unroll
+            for (int nt = 0; nt < NTS; ++nt) mma_tf32(c[mt][nt], ah, bl[nt]);   // passes keep dependent MMAs
+#pragma unroll
+            for (int nt = 0; nt < NTS; ++nt) mma_tf32(c[mt][nt], ah, bh[nt]);   // NTS instructions apart
         }
     }
+    __pipeline_wait_prior(0);                      // callers may have async copies for the epilogue in flight
     __syncthreads();                               // all warps done reading bs (red may alias it)
     float* mine = red + (size_t)warp * TT::R * SLAB_LDR;
 #pragma unroll
@@ -304,11 +309,11 @@ __device__ __forceinline__ void tc_gemm_direct(float (&c)[MlpTile<H>::MT][MlpTil
             split_tf32(a[4], ah[2], al[2]);
             split_tf32(a[(size_t)8 * lda + 4], ah[3], al[3]);
 #pragma unroll
-            for (int nt = 0; nt < TT::NT; ++nt) {
-                mma_tf32(c[mt][nt], al, bh[nt]);
-                mma_tf32(c[mt][nt], ah, bl[nt]);
-                mma_tf32(c[mt][nt], ah, bh[nt]);
-            }
+            for (int nt = 0; nt < TT::NT; ++nt) mma_tf32(c[mt][nt], al, bh[nt]);   // small terms first; the three
+#pragma unroll
+            for (int nt = 0; nt < TT::NT; ++nt) mma_tf32(c[mt][nt], ah, bl[nt]);   // passes keep dependent MMAs
+#pragma unroll
+            for (int nt = 0; nt < TT::NT; ++nt) mma_tf32(c[mt][nt], ah, bh[nt]);   // TT::NT instructions apart
         }
     }
 }

@@ -32,7 +32,7 @@ constexpr int ST_ACTOR_REW = 0, ST_ACTOR_SAFETY = 1, ST_KL = 2, ST_VF0 = 3, ST_V
 constexpr float LOG_SQRT_2PI_P = 0.9189385332046727f;
 constexpr int DOUT_LD = 16;   // scratch row stride of dOut (cols [A, 2A) carry dlog_sigma)
 
-__device__ long long g_dbg_clock[16];
+__device__ long long g_dbg_clock[32];
 __device__ long long g_dbg_cta[512];
 #ifdef FSRL_DEBUG_CLOCKS   // per-phase clock64() stamps of CTA 0 (tools/kbench.py reads them back)
 #define DBG_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
@@ -124,16 +124,20 @@ ppo_fwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     float* xs = smem;                                   // [R][inp]
     float* h1 = xs + (size_t)TT::R * inp;               // [R][LDA]
     float* bs = h1 + (size_t)TT::R * TT::LDA;           // [H][SLAB_LDB]  (aliased by the reduce buffer)
+    DBG_T(16);
     // observations are constant during a repeat: loaded while the previous optimiser step drains
     for (int i = tid; i < TT::R * inp; i += MLP_TPB) {
         const int r = i / inp, k = i % inp;
         xs[i] = (r0 + r < B && k < D) ? u.obs[(size_t)row_of(u, mb_off, r0 + r) * D + k] : 0.f;
     }
+    DBG_T(17);
     pdl_wait();                                         // parameters of the previous step are final
     pdl_trigger();
+    DBG_T(18);
     if (net == 0 && slab == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by the previous step's Adam
     slab_load<H>(nv.m.w2t, H, c0, bs);                  // in flight during layer 1
     __syncthreads();
+    DBG_T(19);
     float c[TT::MT][TT::NT][4];
     tc_init_bias<H>(c, nv.m.b1);
     tc_gemm_direct<H>(c, xs, inp, D, nv.m.w1t);
@@ -142,14 +146,17 @@ ppo_fwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
         *reinterpret_cast<float2*>(h1 + (size_t)row * TT::LDA + col) = h;
         if (slab == 0 && r0 + row < u.bmax) *reinterpret_cast<float2*>(nv.s_h1 + (size_t)(r0 + row) * H + col) = h;
     });
+    DBG_T(20);
     __pipeline_wait_prior(0);
     __syncthreads();
+    DBG_T(21);
     slab_gemm<H>(h1, TT::LDA, bs, bs, [&](int row, int c4, float4 v) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(nv.m.b2 + c0 + c4));
         if (r0 + row < u.bmax)
             *reinterpret_cast<float4*>(nv.s_h2 + (size_t)(r0 + row) * H + c0 + c4) =
                 make_float4(fmaxf(v.x + b.x, 0.f), fmaxf(v.y + b.y, 0.f), fmaxf(v.z + b.z, 0.f), fmaxf(v.w + b.w, 0.f));
     });
+    DBG_T(22);
 }
 
 // per-row head dot product  out[j] = sum_k h2[k] * w3s[k][j]  over this lane's k subset, with the
@@ -187,8 +194,7 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
     float* bs = dz + (size_t)TT::R * TT::LDA;           // [H][SLAB_LDB]
     float* w3s = bs + slab_buf_floats<H>();             // [H][out]
     float* sdout = w3s + (size_t)H * wout;              // [R][DOUT_LD]
-    __shared__ float s_red[MLP_TPB / 32];
-    __shared__ float s_mean[2], s_rstd[2];
+    __shared__ float s_mean[2], s_rstd[2], s_b3[MLP_MAX_OUT], s_ls[8];
     DBG_T(0);
     // everything that does not depend on the forward launch (weights, per-row loss inputs) is
     // requested before pdl_wait(): it overlaps the forward kernel's tail
@@ -221,6 +227,8 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         s_mean[tid] = ms[0];
         s_rstd[tid] = ms[1];
     }
+    if (tid >= 32 && tid < 32 + wout) s_b3[tid - 32] = __ldg(nv.m.b3 + tid - 32);
+    if (net == 0 && tid >= 64 && tid < 64 + u.A) s_ls[tid - 64] = nv.log_sigma[tid - 64];
     pdl_wait();                                          // h1 / h2 of this minibatch are complete
     pdl_trigger();
     for (int el = tid; el < TT::R * (H / 4); el += MLP_TPB) {
@@ -252,7 +260,7 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
             float v = out[j];
 #pragma unroll
             for (int o = TT::PARTS / 2; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, TT::PARTS);
-            out[j] = v + __ldg(nv.m.b3 + j);
+            out[j] = v + s_b3[j];
         }
     }
 
@@ -274,9 +282,9 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
                         const float t = tanhf(out[j]);
                         const float mu = u.bounded ? u.max_action * t : out[j];
                         dmu[j] = u.bounded ? u.max_action * (1.0f - t * t) : 1.0f;
-                        sg[j] = expf(nv.log_sigma[j]);
+                        sg[j] = expf(s_ls[j]);
                         zz[j] = (p_act[j] - mu) / sg[j];
-                        logp += -0.5f * zz[j] * zz[j] - nv.log_sigma[j] - LOG_SQRT_2PI_P;
+                        logp += -0.5f * zz[j] * zz[j] - s_ls[j] - LOG_SQRT_2PI_P;
                     }
                 }
                 const float lpo = p_lpo;
@@ -345,22 +353,24 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
         }
     }
     DBG_T(4);
-    // minibatch statistics (loss/actor_rew, actor_safety, kl, vf_i): one atomic per row-tile CTA
+    // minibatch statistics (loss/actor_rew, actor_safety, kl, vf_i): warp-level partial sums and one
+    // fire-and-forget reduction per warp -- no block barrier on the critical path
     if (slab == 0) {
         float* stat = u.stats + (size_t)slot * FSRL_PPO_STATS;
+        const int lane = tid & 31;
         if (net == 0) {
-            const float a = block_sum_256(st_a, s_red), b = block_sum_256(st_b, s_red), c = block_sum_256(st_c, s_red);
-            if (tid == 0) {
+            const float a = warp_sum(st_a), b = warp_sum(st_b), c = warp_sum(st_c);
+            if (lane == 0) {
                 atomicAdd(stat + ST_ACTOR_REW, a); atomicAdd(stat + ST_ACTOR_SAFETY, b); atomicAdd(stat + ST_KL, c);
-                if (blockIdx.x == 0) {
-                    float ent = 0.f;
-                    for (int j = 0; j < u.A; ++j) ent += 0.5f + LOG_SQRT_2PI_P + nv.log_sigma[j];
-                    stat[ST_ENTROPY] = ent;
-                }
+            }
+            if (blockIdx.x == 0 && tid == 0) {
+                float ent = 0.f;
+                for (int j = 0; j < u.A; ++j) ent += 0.5f + LOG_SQRT_2PI_P + s_ls[j];
+                stat[ST_ENTROPY] = ent;
             }
         } else {
-            const float d = block_sum_256(st_d, s_red);
-            if (tid == 0) atomicAdd(stat + ST_VF0 + (net - 1), d);
+            const float d = warp_sum(st_d);
+            if (lane == 0) atomicAdd(stat + ST_VF0 + (net - 1), d);
         }
     }
     __syncthreads();
@@ -386,10 +396,18 @@ ppo_bwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B, int slot) {
     __pipeline_wait_prior(0);
     __syncthreads();
     DBG_T(7);
+    // the h2 tile is dead now: its space receives this slab's h1 columns (ReLU-1 mask of the epilogue)
+    // while the GEMM runs (slab_gemm waits for outstanding async copies before its first barrier)
+    for (int el = tid; el < TT::R * (SLAB_NS / 4); el += MLP_TPB) {
+        const int row = el / (SLAB_NS / 4), c4 = (el % (SLAB_NS / 4)) * 4;
+        if (r0 + row < u.bmax)
+            __pipeline_memcpy_async(h2 + (size_t)row * SLAB_NS + c4, nv.s_h1 + (size_t)(r0 + row) * H + c0 + c4, 16);
+    }
+    __pipeline_commit();
     // ---- backward through layer 2: dH1[:, slab] = dZ2 . W2[:, slab], then ReLU 1 -------------------
     slab_gemm<H>(dz, TT::LDA, bs, bs, [&](int row, int c4, float4 v) {
         if (r0 + row < u.bmax) {
-            const float4 hv = __ldcg(reinterpret_cast<const float4*>(nv.s_h1 + (size_t)(r0 + row) * H + c0 + c4));
+            const float4 hv = *reinterpret_cast<const float4*>(h2 + (size_t)row * SLAB_NS + c4);
             *reinterpret_cast<float4*>(nv.s_dz1 + (size_t)(r0 + row) * H + c0 + c4) =
                 make_float4(hv.x > 0.f ? v.x : 0.f, hv.y > 0.f ? v.y : 0.f, hv.z > 0.f ? v.z : 0.f, hv.w > 0.f ? v.w : 0.f);
         }
@@ -421,9 +439,77 @@ __global__ void ppo_gather_kernel(const fsrl_ppo_update_t u, long long n) {
 // ------------------------------------------------------------------------------------------
 // Phase B: weight gradients
 // ------------------------------------------------------------------------------------------
-constexpr int WG_TPB = 256, WG_T = 64, WG_TKT = 32, WG_RC = 128, WG_LD = WG_T + 4;
-// shared memory of a weight-gradient role: 2 stages x (L chunk + G chunk), each [WG_RC][WG_LD]
-constexpr size_t WG_SMEM_FLOATS = 2 * 2 * (size_t)WG_RC * WG_LD + 65 * WG_T + (4 * 16 + 4) * WG_T;
+constexpr int WG_TPB = 256, WG_T = 64, WG_TKT = 32, WG_RC = 128, WG_NST = 2, WG_LD = WG_T + 8;   // LD = 8 mod 32: conflict-free fragments
+// shared memory of a weight-gradient role: WG_NST stages x (L chunk + G chunk), each [WG_RC][WG_LD]
+// (re-used as the cross-warp reduce buffer), then fin[80][WG_T] (layer-1 results) and 256 partials.
+// (measured: 64-row chunks x 3 stages, 132 KB, which would let a forward CTA co-reside, is 4% slower)
+constexpr size_t WG_SMEM_FLOATS = 2 * WG_NST * (size_t)WG_RC * WG_LD + 80 * WG_T + 256;
+static_assert(2 * WG_NST * WG_RC * WG_LD >= 8 * 32 * (WG_T + 8), "reduce buffer must fit in the staging area");
+
+// One staged chunk of the weight-gradient contraction  C[m][n] += sum_r L[r][m] * G[r][n]
+// (m < 16 MT, n < 8 NT; r over the WG_RC rows of the chunk, 8 rows per k-step, k-steps dealt
+// round-robin to the 8 warps) as split-TF32 MMAs.  A = L^T is read "column-major" straight from
+// the row-major chunk: with LD = 8 (mod 32) both fragment loads are bank-conflict free.
+template <int MT, int NT>
+__device__ __forceinline__ void wg_mma_chunk(const float* __restrict__ L, const float* __restrict__ G,
+                                             float (&c)[MT][NT][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < WG_RC / 64; ++ks) {
+        const int r = (ks * 8 + warp) * 8;
+        const float* g0 = G + (size_t)(r + t) * WG_LD + g;
+        const float* l0 = L + (size_t)(r + t) * WG_LD + g;
+        uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            split_tf32(g0[8 * nt], bh[nt][0], bl[nt][0]);
+            split_tf32(g0[(size_t)4 * WG_LD + 8 * nt], bh[nt][1], bl[nt][1]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            uint32_t ah[4], al[4];
+            split_tf32(l0[16 * mt], ah[0], al[0]);
+            split_tf32(l0[16 * mt + 8], ah[1], al[1]);
+            split_tf32(l0[(size_t)4 * WG_LD + 16 * mt], ah[2], al[2]);
+            split_tf32(l0[(size_t)4 * WG_LD + 16 * mt + 8], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[mt][nt], al, bh[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[mt][nt], ah, bl[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32(c[mt][nt], ah, bh[nt]);
+        }
+    }
+}
+
+// this warp's partial C tile -> red[warp][16 MT][8 NT + 8]
+template <int MT, int NT>
+__device__ __forceinline__ void wg_store_partial(float* red, const float (&c)[MT][NT][4]) {
+    constexpr int LDR = 8 * NT + 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float* mine = red + (size_t)warp * 16 * MT * LDR;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            *reinterpret_cast<float2*>(mine + (size_t)(16 * mt + g) * LDR + 8 * nt + 2 * t) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+            *reinterpret_cast<float2*>(mine + (size_t)(16 * mt + g + 8) * LDR + 8 * nt + 2 * t) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+        }
+}
+// sum over the 8 warps of 4 consecutive columns of the reduced tile
+template <int MT, int NT>
+__device__ __forceinline__ float4 wg_reduced4(const float* red, int m, int n4) {
+    constexpr int LDR = 8 * NT + 8;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(red + ((size_t)w * 16 * MT + m) * LDR + n4);
+        s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    }
+    return s4;
+}
 
 // Adam hyper-parameters of one optimiser step (torch.optim.Adam scalars, python doubles -> f32)
 struct AdamStep {
@@ -490,6 +576,19 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         }
         __pipeline_commit();
     };
+    // WG_NST-deep cp.async pipeline over the row chunks: stg(chunk, buffer) issues one commit group,
+    // body(buffer) consumes a landed chunk
+    auto pipeline = [&](auto&& stg, auto&& body) {
+        for (int p = 0; p < WG_NST - 1; ++p) { if (p < nchunk) stg(p, p); else __pipeline_commit(); }
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int nx = ch + WG_NST - 1;
+            if (nx < nchunk) stg(nx, nx % WG_NST); else __pipeline_commit();
+            __pipeline_wait_prior(WG_NST - 1);
+            __syncthreads();
+            body(ch % WG_NST);
+            __syncthreads();
+        }
+    };
     pdl_wait();            // dz1 / dz2 / dout of this minibatch are complete
     pdl_trigger();
     float gscale = 1.0f;   // clip coefficient (FUSED)
@@ -515,34 +614,36 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         const int k0 = (bx / NTT) * WG_TKT, o0 = (bx % NTT) * WG_T;
         const int tk = tid / 16, to = tid % 16;
         const bool do_bias = (k0 == 0);
+        float c[2][8][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) { c[mt][nt][0] = c[mt][nt][1] = c[mt][nt][2] = c[mt][nt][3] = 0.f; }
+        float bpart = 0.f;                                  // db2: thread (o = tid % 64, row group tid / 64)
+        DBG_W(10);
+        pipeline([&](int ch, int buf) { stage(ch, buf, nv.s_h1, H, k0, WG_TKT, nv.s_dz2, H, o0, WG_T); },
+                 [&](int buf) {
+                     wg_mma_chunk<2, 8>(sLp(buf), sGp(buf), c);
+                     if (do_bias) {
+                         const float* G = sGp(buf) + (tid % WG_T);
+#pragma unroll 8
+                         for (int rr = tid / WG_T; rr < WG_RC; rr += WG_TPB / WG_T) bpart += G[(size_t)rr * WG_LD];
+                     }
+                 });
+        DBG_W(11);
+        float* red = smem;                                  // staging is dead: cross-warp reduction buffer
+        float* bred = smem + 2 * WG_NST * WG_CHUNK + 80 * WG_T;      // [4][WG_T] bias partials
+        wg_store_partial<2, 8>(red, c);
+        if (do_bias) bred[tid] = bpart;
+        __syncthreads();
         float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-        float bsum = 0.f;
-        DBG_W(10);
-        stage(0, 0, nv.s_h1, H, k0, WG_TKT, nv.s_dz2, H, o0, WG_T);
-        DBG_W(11);
-        for (int ch = 0; ch < nchunk; ++ch) {
-            if (ch + 1 < nchunk) { stage(ch + 1, (ch + 1) & 1, nv.s_h1, H, k0, WG_TKT, nv.s_dz2, H, o0, WG_T); __pipeline_wait_prior(1); }
-            else __pipeline_wait_prior(0);
-            __syncthreads();
-            const float* L = sLp(ch & 1);
-            const float* G = sGp(ch & 1);
-#pragma unroll 16
-            for (int rr = 0; rr < WG_RC; ++rr) {
-                const float2 l = *reinterpret_cast<const float2*>(L + (size_t)rr * WG_LD + 2 * tk);
-                const float4 g = *reinterpret_cast<const float4*>(G + (size_t)rr * WG_LD + 4 * to);
-                acc[0][0] = fmaf(l.x, g.x, acc[0][0]); acc[0][1] = fmaf(l.x, g.y, acc[0][1]);
-                acc[0][2] = fmaf(l.x, g.z, acc[0][2]); acc[0][3] = fmaf(l.x, g.w, acc[0][3]);
-                acc[1][0] = fmaf(l.y, g.x, acc[1][0]); acc[1][1] = fmaf(l.y, g.y, acc[1][1]);
-                acc[1][2] = fmaf(l.y, g.z, acc[1][2]); acc[1][3] = fmaf(l.y, g.w, acc[1][3]);
-            }
-            if (do_bias && tid < WG_T) {
-#pragma unroll 8
-                for (int rr = 0; rr < WG_RC; ++rr) bsum += G[(size_t)rr * WG_LD + tid];
-            }
-            __syncthreads();
+        for (int i = 0; i < 2; ++i) {
+            const float4 v = wg_reduced4<2, 8>(red, 2 * tk + i, 4 * to);
+            acc[i][0] = v.x; acc[i][1] = v.y; acc[i][2] = v.z; acc[i][3] = v.w;
         }
+        float bsum = 0.f;
+        if (do_bias && tid < WG_T) bsum = bred[tid] + bred[WG_T + tid] + bred[2 * WG_T + tid] + bred[3 * WG_T + tid];
 #pragma unroll
         for (int i = 0; i < 2; ++i) sq += acc[i][0] * acc[i][0] + acc[i][1] * acc[i][1] + acc[i][2] * acc[i][2] + acc[i][3] * acc[i][3];
         if (do_bias && tid < WG_T) sq += bsum * bsum;
@@ -584,26 +685,32 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         }
     } else if (bx < NT + NTT) {
         // ---- layer 1: dW1t[d][o] = sum_r x[r][d] * dz1[r][o];  db1[o] = sum_r dz1[r][o] ---------
+        // Inputs go through the MMA in passes of 16 "virtual" columns v: v < D is observation column v,
+        // v == D is a column of ones (its output row is the bias gradient), the rest is zero padding.
+        // Results land in fin[v][o] (shared), which survives the grid barrier of the fused variant.
         const int D = u.D;
         const int o0 = (bx - NT) * WG_T;
         const int o = tid % WG_T;
-        // thread (o, rg): column o of the tile, row group rg = tid / 64 (rows rr = rg mod 4): all four
-        // warp pairs work even when D is tiny.  Inputs are processed in blocks of 16 (statically indexed
-        // accumulators); the four row-group partials are summed through shared memory into fin[d][o],
-        // which survives the grid barrier of the fused variant.
         const int rg = tid / WG_T;
-        float bsum = 0.f;
-        const int dw = (D + 3) & ~3;                        // staged input width (multiple of 4, <= 64)
-        float* fin = smem + 4 * WG_CHUNK;                   // [64][WG_T] final gradients (+ [WG_T] bias)
-        float* part = fin + 65 * WG_T;                      // [4][16][WG_T] row-group partials
-        auto stage1 = [&](int ch, int buf) {
+        float* fin = smem + 2 * WG_NST * WG_CHUNK;                   // [16 npass][WG_T]
+        auto stage1 = [&](int ch, int buf, int v0) {
             const int rb = ch * WG_RC;
             float* xs_ = sLp(buf);
             float* gs_ = sGp(buf);
-            for (int i = tid; i < WG_RC * dw; i += WG_TPB) {
-                const int rr = i / dw, dd = i % dw;
-                xs_[(size_t)rr * WG_LD + dd] =
-                    (rb + rr < B && dd < D) ? __ldg(u.obs + (size_t)row_of(u, mb_off, rb + rr) * D + dd) : 0.f;
+            if ((D & 3) == 0) {            // 16-byte segments: a segment is entirely data or entirely padding
+                for (int i = tid; i < WG_RC * 4; i += WG_TPB) {
+                    const int rr = i / 4, v = v0 + 4 * (i % 4);
+                    float* dst = xs_ + (size_t)rr * WG_LD + 4 * (i % 4);
+                    if (rb + rr < B && v < D) __pipeline_memcpy_async(dst, u.obs + (size_t)row_of(u, mb_off, rb + rr) * D + v, 16);
+                    else *reinterpret_cast<float4*>(dst) = make_float4((rb + rr < B && v == D) ? 1.0f : 0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                for (int i = tid; i < WG_RC * 16; i += WG_TPB) {
+                    const int rr = i / 16, v = v0 + (i % 16);
+                    float* dst = xs_ + (size_t)rr * WG_LD + (i % 16);
+                    if (rb + rr < B && v < D) __pipeline_memcpy_async(dst, u.obs + (size_t)row_of(u, mb_off, rb + rr) * D + v, 4);
+                    else *dst = (rb + rr < B && v == D) ? 1.0f : 0.f;
+                }
             }
             for (int i = tid; i < WG_RC * (WG_T / 4); i += WG_TPB) {
                 const int rr = i / (WG_T / 4), c4 = (i % (WG_T / 4)) * 4;
@@ -613,53 +720,25 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
             }
             __pipeline_commit();
         };
-        const int npass = (D + 15) / 16;
+        const int npass = (D + 1 + 15) / 16;
         for (int ps = 0; ps < npass; ++ps) {
-            const int d0 = 16 * ps;
-            float acc[16];
+            float c[1][8][4];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-            stage1(0, 0);
-            for (int ch = 0; ch < nchunk; ++ch) {
-                if (ch + 1 < nchunk) { stage1(ch + 1, (ch + 1) & 1); __pipeline_wait_prior(1); }
-                else __pipeline_wait_prior(0);
-                __syncthreads();
-                const float* X = sLp(ch & 1);
-                const float* G = sGp(ch & 1);
-#pragma unroll 4
-                for (int rr = rg; rr < WG_RC; rr += 4) {
-                    const float g = G[(size_t)rr * WG_LD + o];
-                    const float* xr = X + (size_t)rr * WG_LD + d0;
-#pragma unroll
-                    for (int q4 = 0; q4 < 16; q4 += 4) {
-                        if (d0 + q4 < dw) {
-                            const float4 x4 = *reinterpret_cast<const float4*>(xr + q4);
-                            acc[q4] = fmaf(x4.x, g, acc[q4]); acc[q4 + 1] = fmaf(x4.y, g, acc[q4 + 1]);
-                            acc[q4 + 2] = fmaf(x4.z, g, acc[q4 + 2]); acc[q4 + 3] = fmaf(x4.w, g, acc[q4 + 3]);
-                        }
-                    }
-                    if (ps == 0) bsum += g;
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) part[((size_t)rg * 16 + q) * WG_T + o] = acc[q];
-            if (ps == 0) part[(size_t)(4 * 16) * WG_T + rg * WG_T + o] = bsum;
+            for (int nt = 0; nt < 8; ++nt) { c[0][nt][0] = c[0][nt][1] = c[0][nt][2] = c[0][nt][3] = 0.f; }
+            pipeline([&](int ch, int buf) { stage1(ch, buf, 16 * ps); },
+                     [&](int buf) { wg_mma_chunk<1, 8>(sLp(buf), sGp(buf), c); });
+            float* red = smem;
+            wg_store_partial<1, 8>(red, c);
             __syncthreads();
-            for (int i = tid; i < 16 * WG_T; i += WG_TPB) {
-                const int q = i / WG_T, oo = i % WG_T;
-                fin[(size_t)(d0 + q) * WG_T + oo] = part[((size_t)0 * 16 + q) * WG_T + oo] + part[((size_t)1 * 16 + q) * WG_T + oo] +
-                                                   part[((size_t)2 * 16 + q) * WG_T + oo] + part[((size_t)3 * 16 + q) * WG_T + oo];
-            }
-            if (ps == 0 && tid < WG_T) {
-                const float* bp = part + (size_t)(4 * 16) * WG_T;
-                fin[(size_t)64 * WG_T + tid] = bp[tid] + bp[WG_T + tid] + bp[2 * WG_T + tid] + bp[3 * WG_T + tid];
+            {
+                const int m = tid / 16, n4 = (tid % 16) * 4;        // 16 x 64 outputs, 4 per thread
+                *reinterpret_cast<float4*>(fin + (size_t)(16 * ps + m) * WG_T + n4) = wg_reduced4<1, 8>(red, m, n4);
             }
             __syncthreads();
         }
         // every thread now owns the outputs (d, o) with d = rg, rg + 4, ... < D; bias: rg == 0
         for (int d = rg; d < D; d += 4) { const float g = fin[(size_t)d * WG_T + o]; sq += g * g; }
-        if (rg == 0) { const float g = fin[(size_t)64 * WG_T + o]; sq += g * g; }
+        if (rg == 0) { const float g = fin[(size_t)D * WG_T + o]; sq += g * g; }
         finish();
         for (int d = rg; d < D; d += 4) {
             const float g = fin[(size_t)d * WG_T + o];
@@ -672,7 +751,7 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
             }
         }
         if (rg == 0) {
-            const float g = fin[(size_t)64 * WG_T + o];
+            const float g = fin[(size_t)D * WG_T + o];
             if (!FUSED) nv.g_b1[o0 + o] = g;
             else {
                 const long long idx = pbase + (long long)D * H + o0 + o;
@@ -687,27 +766,35 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
         const int A = u.A;
         const int k0 = (bx - NT - NTT) * WG_T;
         const int k = tid % WG_T, jg = tid / WG_T;          // j = 4*jg + q
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        float csum = 0.f;                                   // column sum of dout (threads < 16)
-        stage(0, 0, nv.s_h2, H, k0, WG_T, nv.s_dout, DOUT_LD, 0, DOUT_LD);
-        for (int ch = 0; ch < nchunk; ++ch) {
-            if (ch + 1 < nchunk) { stage(ch + 1, (ch + 1) & 1, nv.s_h2, H, k0, WG_T, nv.s_dout, DOUT_LD, 0, DOUT_LD); __pipeline_wait_prior(1); }
-            else __pipeline_wait_prior(0);
-            __syncthreads();
-            const float* Hh = sLp(ch & 1);
-            const float* Dd = sGp(ch & 1);
-#pragma unroll 8
-            for (int rr = 0; rr < WG_RC; ++rr) {
-                const float h = Hh[(size_t)rr * WG_LD + k];
-                const float4 da = *reinterpret_cast<const float4*>(Dd + (size_t)rr * WG_LD + 4 * jg);
-                acc[0] = fmaf(h, da.x, acc[0]); acc[1] = fmaf(h, da.y, acc[1]);
-                acc[2] = fmaf(h, da.z, acc[2]); acc[3] = fmaf(h, da.w, acc[3]);
-            }
-            if (k0 == 0 && tid < DOUT_LD) {
-#pragma unroll 8
-                for (int rr = 0; rr < WG_RC; ++rr) csum += Dd[(size_t)rr * WG_LD + tid];
-            }
-            __syncthreads();
+        float c[4][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { c[mt][nt][0] = c[mt][nt][1] = c[mt][nt][2] = c[mt][nt][3] = 0.f; }
+        float cpart = 0.f;                                  // column sums of dout: thread (j = tid % 16, row group tid / 16)
+        pipeline([&](int ch, int buf) { stage(ch, buf, nv.s_h2, H, k0, WG_T, nv.s_dout, DOUT_LD, 0, DOUT_LD); },
+                 [&](int buf) {
+                     wg_mma_chunk<4, 2>(sLp(buf), sGp(buf), c);
+                     if (k0 == 0) {
+                         const float* Dd = sGp(buf) + (tid % DOUT_LD);
+#pragma unroll
+                         for (int rr = tid / DOUT_LD; rr < WG_RC; rr += WG_TPB / DOUT_LD) cpart += Dd[(size_t)rr * WG_LD];
+                     }
+                 });
+        float* red = smem;
+        float* cred = smem + 2 * WG_NST * WG_CHUNK + 80 * WG_T;      // [16][DOUT_LD] column-sum partials
+        wg_store_partial<4, 2>(red, c);
+        if (k0 == 0) cred[tid] = cpart;
+        __syncthreads();
+        float acc[4];
+        {
+            const float4 v = wg_reduced4<4, 2>(red, k, 4 * jg);
+            acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
+        }
+        float csum = 0.f;
+        if (k0 == 0 && tid < DOUT_LD) {
+#pragma unroll
+            for (int q = 0; q < WG_TPB / DOUT_LD; ++q) csum += cred[q * DOUT_LD + tid];
         }
         const bool own_b3 = (k0 == 0) && tid < out;
         const bool own_ls = (k0 == 0) && net == 0 && u.head_indep && tid >= A && tid < 2 * A && tid < DOUT_LD;
@@ -1165,8 +1252,8 @@ extern "C" int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters
     }
 }
 
-extern "C" int fsrl_debug_clocks(long long* out16) {
-    FSRL_CUDA(cudaMemcpyFromSymbol(out16, fsrl::g_dbg_clock, sizeof(long long) * 16));
+extern "C" int fsrl_debug_clocks(long long* out32) {
+    FSRL_CUDA(cudaMemcpyFromSymbol(out32, fsrl::g_dbg_clock, sizeof(long long) * 32));
     return FSRL_OK;
 }
 extern "C" int fsrl_debug_cta_cycles(long long* out512) {

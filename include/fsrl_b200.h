@@ -191,7 +191,7 @@ int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total, int batch_
  * `iters` launches on the first B rows of u->perm; weights are left untouched (lr = 0) */
 /* tuning aid: clock64() stamps taken by CTA (0,0) at the phase boundaries of the last
  * ppo_fwdbwd launch (host array of 16) */
-int fsrl_debug_clocks(long long* out16);
+int fsrl_debug_clocks(long long* out32);   /* 32 stamps; only written by -DFSRL_DEBUG_CLOCKS builds */
 int fsrl_debug_cta_cycles(long long* out512); /* per-CTA cycle counts of the last ppo_wgrad launch */
 int fsrl_ppo_phase_times(const fsrl_ppo_update_t* u, int B, int iters, float* ms_out, void* stream);
 

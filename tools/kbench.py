@@ -61,11 +61,13 @@ def bench_ppo(iters):
     print(json.dumps({"phase_ms(fwd,bwd,wgrad,adam)": bench.phase_times(agent, col, buf, iters=iters)}))
     import ctypes
     from fsrl_b200 import _lib
-    ck = (ctypes.c_longlong * 16)()
+    ck = (ctypes.c_longlong * 32)()
     _lib.check(_lib.lib.fsrl_debug_clocks(ck))
     c = list(ck)
     print("ppo_bwd CTA(0,0,0) cycles [loads, advstats, sync, head, lossgrad, stats, dz2, wait_slab, slab_gemm]:",
           [c[i + 1] - c[i] for i in range(8)], "total", c[8] - c[0])
+    print("ppo_fwd CTA(0,0,0) cycles [obs load, (pdl wait), slab issue+sync, layer1, wait_slab, slab_gemm]:",
+          [c[i + 1] - c[i] for i in range(16, 22)], "total", c[22] - c[16])
     cc = (ctypes.c_longlong * 512)()
     _lib.check(_lib.lib.fsrl_debug_cta_cycles(cc))
     cc = list(cc)[:120]
