@@ -130,7 +130,8 @@ class OffPolicy(ctypes.Structure):
                 ("w_logp", c_vp), ("w_keep", c_vp),
                 ("actor_out", c_vp), ("actor_old_out", c_vp), ("actor_dout", c_vp),
                 ("q_out", c_vp * 4), ("q_dout", c_vp * 4), ("q_dx", c_vp * 4), ("q_old_out", c_vp * 4),
-                ("alpha", c_vp), ("alpha_state", c_vp)]
+                ("alpha", c_vp), ("alpha_state", c_vp),
+                ("comm", c_vp), ("world", c_int), ("pad1", c_int)]
 
 
 class Cpo(ctypes.Structure):
@@ -176,6 +177,7 @@ SIGNATURES = {
     "fsrl_comm_init": (c_int, [ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_vp)]),
     "fsrl_comm_destroy": (c_int, [c_vp]),
     "fsrl_allreduce_fused": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp]),
+    "fsrl_allreduce_ranges": (c_int, [c_vp, c_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), c_int, c_vp]),
     "fsrl_allreduce_f64": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_cpo_head": (c_int, [ctypes.POINTER(Cpo), c_int, c_vp, c_vp]),
     "fsrl_cpo_hvp": (c_int, [ctypes.POINTER(Cpo), c_vp, c_vp, c_vp, c_f64, c_vp]),

@@ -57,3 +57,16 @@ extern "C" int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* st
                             static_cast<cudaStream_t>(stream)));
     return FSRL_OK;
 }
+
+extern "C" int fsrl_allreduce_ranges(void* comm, float* base, const long long* offs, const long long* counts,
+                                     int n_ranges, void* stream) {
+    FSRL_REQUIRE(comm && base && offs && counts && n_ranges >= 0, "allreduce_ranges: bad arguments");
+    FSRL_NCCL(ncclGroupStart());
+    for (int i = 0; i < n_ranges; ++i) {
+        if (counts[i] <= 0) continue;
+        FSRL_NCCL(ncclAllReduce(base + offs[i], base + offs[i], (size_t)counts[i], ncclFloat, ncclSum,
+                                static_cast<ncclComm_t>(comm), static_cast<cudaStream_t>(stream)));
+    }
+    FSRL_NCCL(ncclGroupEnd());
+    return FSRL_OK;
+}

@@ -244,10 +244,14 @@ __global__ void ddpg_action_kernel(const fsrl_offpolicy_t d, const float* __rest
 }
 
 // automatic entropy tuning (sac_lag.py:237-250): one Adam step on log_alpha, alpha = exp(.)
-__global__ void alpha_step_kernel(const fsrl_offpolicy_t d, const float* __restrict__ stat, float* __restrict__ stat_out) {
+__global__ void alpha_step_kernel(const fsrl_offpolicy_t d, const float* __restrict__ stat, float* __restrict__ stat_out,
+                                  float inv_world) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float* st = d.alpha_state;     // [log_alpha, m, v, t]
-    const float mean_lp = stat[FSRL_OFF_ST_LOGP];
+    if (inv_world != 1.0f) {       // the row was summed over the ranks: back to the global-batch means
+        for (int i = 0; i <= FSRL_OFF_ST_LOGP; ++i) stat_out[i] = stat[i] * inv_world;
+    }
+    const float mean_lp = stat_out[FSRL_OFF_ST_LOGP];
     const float g = -(mean_lp + d.target_entropy);             // d/d log_alpha of -(log_alpha*(logp+H)).mean()
     const float la = st[0];
     stat_out[FSRL_OFF_ST_ALPHA_LOSS] = -la * (mean_lp + d.target_entropy);
@@ -263,6 +267,10 @@ __global__ void alpha_step_kernel(const fsrl_offpolicy_t d, const float* __restr
     stat_out[FSRL_OFF_ST_ALPHA] = expf(nla);
 }
 
+static inline long long net_params(const fsrl_netref_t& r) {
+    return (long long)r.D * r.H + r.H + (long long)r.H * r.H + r.H + (long long)r.H * r.out + r.out + r.n_extra;
+}
+
 static inline fsrl_eng_input_t mk_in(const float* xa, const int* ia, int Da, const float* xb, const int* ib, int Db) {
     fsrl_eng_input_t in;
     in.xa = xa; in.ia = ia; in.xb = xb; in.ib = ib; in.Da = Da; in.Db = Db;
@@ -274,6 +282,17 @@ static inline fsrl_eng_input_t mk_in(const float* xa, const int* ia, int Da, con
 using namespace fsrl;
 
 #define OFF_CHECK(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
+
+extern "C" int fsrl_allreduce_ranges(void* comm, float* base, const long long* offs, const long long* counts,
+                                     int n_ranges, void* stream);
+extern "C" int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
+
+// data parallel: sum the gradient slices of a net list over the ranks (averaged by Adam's grad_scale)
+static int allreduce_grads(const fsrl_offpolicy_t* d, const fsrl_netlist_t* nl, void* stream) {
+    long long offs[FSRL_ENG_MAX_NETS], counts[FSRL_ENG_MAX_NETS];
+    for (int i = 0; i < nl->n; ++i) { offs[i] = nl->nets[i].off; counts[i] = net_params(nl->nets[i]); }
+    return fsrl_allreduce_ranges(d->comm, d->eng.grad, offs, counts, nl->n, stream);
+}
 
 extern "C" int fsrl_nstep_prepare(const fsrl_offpolicy_t* d, const int* idx, int B, void* stream) {
     FSRL_REQUIRE(d && idx, "nstep: null pointer");
@@ -294,9 +313,12 @@ extern "C" int fsrl_offpolicy_steps(const fsrl_offpolicy_t* d, const int* idx_al
     FSRL_REQUIRE(d->algo == FSRL_ALGO_SAC || d->algo == FSRL_ALGO_DDPG, "offpolicy: unknown algo %d", d->algo);
     FSRL_REQUIRE(B >= 2 && B <= d->eng.bmax, "offpolicy: B=%d out of range (bmax %d)", B, d->eng.bmax);
     FSRL_REQUIRE(d->A >= 1 && d->A <= 8 && d->C >= 1 && d->C <= 2, "offpolicy: A/C out of range");
+    FSRL_REQUIRE(d->world <= 1 || d->comm != nullptr, "offpolicy: world=%d needs a communicator", d->world);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int T = 128, G = (B + T - 1) / T;
     const bool sac = d->algo == FSRL_ALGO_SAC;
+    const bool dp = d->world > 1;
+    const double gscale = dp ? 1.0 / d->world : 1.0;
     const int D = d->D, A = d->A;
     for (int it = 0; it < n_steps; ++it) {
         const int* idx = idx_all + (size_t)it * B;
@@ -324,7 +346,8 @@ extern "C" int fsrl_offpolicy_steps(const fsrl_offpolicy_t* d, const int* idx_al
             FSRL_LAUNCH_CHECK();
             OFF_CHECK(fsrl_engine_backward(&d->eng, &d->critics, B, 0, stream));
             OFF_CHECK(fsrl_engine_wgrad(&d->eng, &d->critics, &in, B, 0, nullptr, stream));
-            OFF_CHECK(fsrl_engine_adam(&d->eng, &d->critics, d->critic_lr, 0.9, 0.999, 1e-8, critic_t0 + it + 1, 1.0, 0.0, nullptr, 0.0, stream));
+            if (dp) OFF_CHECK(allreduce_grads(d, &d->critics, stream));
+            OFF_CHECK(fsrl_engine_adam(&d->eng, &d->critics, d->critic_lr, 0.9, 0.999, 1e-8, critic_t0 + it + 1, gscale, 0.0, nullptr, 0.0, stream));
         }
         // ---- policy_loss (sac_lag.py:212-258 / ddpg_lag.py:191-213) ----------------------------------
         {
@@ -342,9 +365,11 @@ extern "C" int fsrl_offpolicy_steps(const fsrl_offpolicy_t* d, const int* idx_al
             FSRL_LAUNCH_CHECK();
             OFF_CHECK(fsrl_engine_backward(&d->eng, &d->actor, B, 0, stream));
             OFF_CHECK(fsrl_engine_wgrad(&d->eng, &d->actor, &in, B, 0, nullptr, stream));
-            OFF_CHECK(fsrl_engine_adam(&d->eng, &d->actor, d->actor_lr, 0.9, 0.999, 1e-8, actor_t0 + it + 1, 1.0, 0.0, nullptr, 0.0, stream));
+            if (dp) OFF_CHECK(allreduce_grads(d, &d->actor, stream));
+            OFF_CHECK(fsrl_engine_adam(&d->eng, &d->actor, d->actor_lr, 0.9, 0.999, 1e-8, actor_t0 + it + 1, gscale, 0.0, nullptr, 0.0, stream));
             if (sac && d->auto_alpha) {
-                alpha_step_kernel<<<1, 32, 0, s>>>(*d, stat, stat);
+                if (dp) OFF_CHECK(fsrl_allreduce_fused(d->comm, stat, FSRL_OFF_ST_LOGP + 1, stream));
+                alpha_step_kernel<<<1, 32, 0, s>>>(*d, stat, stat, (float)gscale);
                 FSRL_LAUNCH_CHECK();
             }
         }

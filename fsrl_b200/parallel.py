@@ -11,6 +11,12 @@ identical on all ranks by
                 (csrc/ppo.cu) between the weight-gradient and Adam kernels;
 * per repeat  : the KL early-stop statistic is averaged so that all ranks stop together.
 
+Off-policy learners (SAC / DDPG): every rank samples its own replay shard; the C loop
+(csrc/offpolicy.cu) all-reduces the critics' and the actor's gradient slices once per gradient
+step and the entropy-tuning statistic, so parameters, targets and alpha stay identical.
+Trust-region learners (CPO / TRPO): gradient vectors, every Hessian-vector product and the
+batch sums of the line search are combined with weights n_r / sum(n) (policy/trust_region.py).
+
 The reference has no distributed code; this file is the new engine's design.
 Host-side scalar reductions go through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
 tests); gradients go through our own NCCL communicator created from a broadcast unique id.
@@ -51,6 +57,11 @@ class DataParallel:
         self.dist.all_reduce(t)
         return t.cpu().numpy()
 
+    def all_max(self, values) -> np.ndarray:
+        t = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
     def reduce_collect_stats(self, stats: Dict) -> Dict:
         """Global view of one collect: episodic means over ALL ranks' episodes."""
         n_ep, n_st = stats["n/ep"], stats["n/st"]
@@ -85,6 +96,8 @@ def attach(policy, dist, device=None) -> DataParallel:
     if hasattr(policy, "_mirror_dirty"):
         policy._mirror_dirty = True
     policy._dp = dp
+    if hasattr(policy, "_upd_seed"):      # off-policy rsample / exploration noise: one stream per rank
+        policy._upd_seed = shard_seed(policy._upd_seed, dp.rank)
     inner = policy.pre_update_fn
 
     def pre_update_fn(stats_train, **kw):

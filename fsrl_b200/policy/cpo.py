@@ -70,7 +70,7 @@ class CPO(TrustRegionMixin, BasePolicy):
         batch = self.compute_gae_returns(batch, buffer, indices, self._lambda)          # :126
         if self._norm_adv:                                                             # :127-131
             for c in range(self.critics_num):
-                _lib.check(_lib.lib.fsrl_standardize(batch.adv[c].data_ptr(), batch.n, self._stream()))
+                self._standardize(batch.adv[c], batch.n)
         # old distribution (:133-144): mean from one actor pass; std is state independent
         z = self.net_forward(0, batch.obs)
         mu = self.actor._max * torch.tanh(z) if not self.actor._unbounded else z
@@ -89,14 +89,17 @@ class CPO(TrustRegionMixin, BasePolicy):
         e, nl = eng.engine(), eng.netlist([a])
         theta_a = self.arena.theta[a.offset:a.offset + P]
 
+        n_g = self._dp_begin(n)          # rows of the global minibatch (== n on one GPU)
+
         def sums():
-            return self._sums.cpu().numpy()
+            return self._gsums()
 
         def grad_into(mode, dst):
             self._head(d, mode)
             sm = sums()
             eng.backward([a], n)
             _lib.check(lib.fsrl_engine_wgrad_to(ctypes.byref(e), ctypes.byref(nl), ctypes.byref(inp), n, dst.data_ptr(), s))
+            self._gvec(dst)
             return sm
 
         # entropy of the state-independent Gaussian BEFORE the step (:239)
@@ -104,10 +107,10 @@ class CPO(TrustRegionMixin, BasePolicy):
         eng.forward([a], inp, n, save=True)
         sm = grad_into(1, v["g"])                                                   # :252
         adv_c = batch.adv[1] if perm is None else batch.adv[1][perm.long()]
-        mean_adv_c = float(adv_c.mean().item())
-        objective = np.float32(sm[0] / n)
-        cost_surrogate = np.float32(self._ave_cost_return + sm[1] / n - mean_adv_c)  # :169-175
-        kl = np.float32(sm[2] / n)
+        mean_adv_c = self._gscalar(float(adv_c.sum().item())) / n_g if self._dpw is not None else float(adv_c.mean().item())
+        objective = np.float32(sm[0] / n_g)
+        cost_surrogate = np.float32(self._ave_cost_return + sm[1] / n_g - mean_adv_c)  # :169-175
+        kl = np.float32(sm[2] / n_g)
         grad_into(2, v["b"])                                                         # :253
         self._head(d, 3)                                                             # :254 (graph of grad kl)
         eng.backward([a], n)
@@ -173,9 +176,9 @@ class CPO(TrustRegionMixin, BasePolicy):
                 eng.forward([a], inp, n, save=False)
                 self._head(d, 0)
                 sm2 = sums()
-                new_kl = f32(sm2[2] / n)
-                new_obj = f32(sm2[0] / n)
-                new_cost = f32(self._ave_cost_return + sm2[1] / n - mean_adv_c)
+                new_kl = f32(sm2[2] / n_g)
+                new_obj = f32(sm2[0] / n_g)
+                new_cost = f32(self._ave_cost_return + sm2[1] / n_g - mean_adv_c)
                 if new_kl <= self._delta and (new_obj > objective if optim_case > 1 else True) and \
                         new_cost - cost_surrogate <= max(-float(c_value), 0):
                     break
@@ -201,6 +204,7 @@ class CPO(TrustRegionMixin, BasePolicy):
                     if merge_last and i + 2 * batch_size >= n_all:
                         chunks.append(perm_all[i:]); break
                     chunks.append(perm_all[i:i + batch_size])
+                self._dp_same_count(len(chunks), "minibatch count")
                 for ch in chunks:
                     perm = torch.as_tensor(ch.astype(np.int32), device=self.device)
                     n = len(ch)

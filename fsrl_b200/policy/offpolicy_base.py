@@ -107,6 +107,9 @@ class OffPolicyLagrangian(LagrangianPolicy):
             d.q_dx[i] = eng.slot_view(s, "dx").data_ptr()
         for i, s in enumerate(g["critics_old"]):
             d.q_old_out[i] = eng.slot_view(s, "out").data_ptr()
+        dp = getattr(self, "_dp", None)
+        if dp is not None and dp.world > 1:
+            d.comm, d.world = dp.comm, dp.world
         self._fill_algo(d)
         return d
 

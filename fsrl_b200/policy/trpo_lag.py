@@ -55,7 +55,7 @@ class TRPOLagrangian(TrustRegionMixin, LagrangianPolicy):
         batch = self.compute_gae_returns(batch, buffer, indices, self._lambda)
         if self._norm_adv:                                                   # :129-133
             for c in range(self.critics_num):
-                _lib.check(_lib.lib.fsrl_standardize(batch.adv[c].data_ptr(), batch.n, self._stream()))
+                self._standardize(batch.adv[c], batch.n)
         batch.mean_old = torch.empty((batch.n, self.arena.slots[0].out), dtype=torch.float32, device=self.device)
         batch.std_old = torch.empty_like(batch.mean_old)
         return batch
@@ -85,6 +85,7 @@ class TRPOLagrangian(TrustRegionMixin, LagrangianPolicy):
                     if merge_last and i + 2 * batch_size >= n_all:
                         chunks.append(perm_all[i:]); break
                     chunks.append(perm_all[i:i + batch_size])
+                self._dp_same_count(len(chunks), "minibatch count")
                 for ch in chunks:
                     perm = torch.as_tensor(ch.astype(np.int32), device=self.device)
                     n = len(ch)
@@ -95,17 +96,21 @@ class TRPOLagrangian(TrustRegionMixin, LagrangianPolicy):
                     inp = eng.make_input(batch.obs, perm)
                     e, nl = eng.engine(), eng.netlist([a])
 
+                    n_g = self._dp_begin(n)     # rows of the global minibatch (== n on one GPU)
+
                     def loss_of(sm):            # policy_loss (:158-180) from the batch sums
-                        return resc * (-(sm[0] / n) + lag * (sm[1] / n))
+                        return resc * (-(sm[0] / n_g) + lag * (sm[1] / n_g))
 
                     eng.forward([a], inp, n, save=True)
                     self._head(d, 1)
-                    sm = self._sums.cpu().numpy()
+                    sm = self._gsums()
                     eng.backward([a], n)
                     _lib.check(lib.fsrl_engine_wgrad_to(ctypes.byref(e), ctypes.byref(nl), ctypes.byref(inp), n, v["g"].data_ptr(), s))
+                    self._gvec(v["g"])
                     self._head(d, 2)
                     eng.backward([a], n)
                     _lib.check(lib.fsrl_engine_wgrad_to(ctypes.byref(e), ctypes.byref(nl), ctypes.byref(inp), n, v["b"].data_ptr(), s))
+                    self._gvec(v["b"])
                     loss_actor = loss_of(sm)
                     # flat_grads = rescaling * (-grad objective + lambda * grad cost ratio term)
                     flat = v["step"]
@@ -125,8 +130,8 @@ class TRPOLagrangian(TrustRegionMixin, LagrangianPolicy):
                         _lib.check(lib.fsrl_vec_add_scaled(v["theta0"].data_ptr(), step_size, sd.data_ptr(), theta_a.data_ptr(), P, s))
                         eng.forward([a], inp, n, save=False)
                         self._head(d, 0)
-                        sm2 = self._sums.cpu().numpy()
-                        kl = float(sm2[2] / n)
+                        sm2 = self._gsums()
+                        kl = float(sm2[2] / n_g)
                         if kl < self._delta and loss_of(sm2) < loss_actor:
                             break
                         elif i < self._max_backtracks - 1:
@@ -140,12 +145,12 @@ class TRPOLagrangian(TrustRegionMixin, LagrangianPolicy):
                         stats_critic = self.critics_loss(batch, perm, n)
                         self.gradient_steps += 1
                     ent = float((0.5 + 0.5 * np.log(2 * np.pi) + self.actor.sigma_param.detach().flatten()).sum().item())
-                    stats = {"loss/actor_rew": float(-(sm[0] / n)), "loss/actor_total": float(loss_actor),
+                    stats = {"loss/actor_rew": float(-(sm[0] / n_g)), "loss/actor_total": float(loss_actor),
                              "loss/rescaling": resc, "loss/kl": kl, "loss/step_size": step_size,
                              "loss/entropy": ent, **stats_critic}
                     if self.use_lagrangian:
                         stats["loss/lagrangian"] = lag
-                        stats["loss/actor_safety"] = float(lag * sm[1] / n)
+                        stats["loss/actor_safety"] = float(lag * sm[1] / n_g)
                     for k, val in stats.items():
                         self.last_stats.setdefault(k, []).append(val)
                         tab, key = k.split("/", 1)

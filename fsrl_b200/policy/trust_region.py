@@ -33,6 +33,56 @@ class TrustRegionMixin:
             self._dot = torch.zeros(1, dtype=torch.float64, device=dev)
         return self._eng
 
+    # ---- data parallel: the global minibatch is the union of the ranks' minibatches ----
+    # Every batch quantity of the trust-region step is a mean over the minibatch, so rank r's local
+    # means are combined with the weights n_r / sum(n): sums are all-reduced as sums, gradient /
+    # Hessian-vector products as weighted vectors (g, b and each Hv: P floats, ~22 x per update).
+    # All ranks then run the SAME conjugate-gradient iterates, dual case analysis and line search.
+    _dpw: Optional[float] = None
+
+    def _dp_begin(self, n: int) -> int:
+        """Start a minibatch step of n local rows; returns the global row count."""
+        dp = getattr(self, "_dp", None)
+        if dp is None or dp.world == 1:
+            self._dpw = None
+            return n
+        n_g = int(round(float(dp.all_sum([n])[0])))
+        self._dpw = n / n_g
+        return n_g
+
+    def _gsums(self) -> np.ndarray:
+        sm = self._sums.cpu().numpy()
+        return sm if self._dpw is None else self._dp.all_sum(sm)
+
+    def _gscalar(self, x: float) -> float:
+        return float(x) if self._dpw is None else float(self._dp.all_sum([x])[0])
+
+    def _gvec(self, t: torch.Tensor) -> None:
+        if self._dpw is not None:
+            t.mul_(self._dpw)
+            self._dp.dist.all_reduce(t)
+
+    def _standardize(self, x: torch.Tensor, n: int) -> None:
+        """x <- (x - mean) / std (unbiased) over the whole collect (cpo.py:127-131); under data
+        parallelism the moments are those of the union of all ranks' collects."""
+        dp = getattr(self, "_dp", None)
+        if dp is None or dp.world == 1:
+            _lib.check(_lib.lib.fsrl_standardize(x.data_ptr(), n, self._stream()))
+            return
+        xd = x[:n].double()
+        s1, s2, cnt = dp.all_sum([float(xd.sum().item()), float((xd * xd).sum().item()), float(n)])
+        mean = s1 / cnt
+        var = max((s2 - cnt * mean * mean) / max(cnt - 1.0, 1.0), 0.0)
+        x[:n].sub_(mean).div_(float(np.sqrt(var)))
+
+    def _dp_same_count(self, c: int, what: str) -> None:
+        dp = getattr(self, "_dp", None)
+        if dp is not None and dp.world > 1:
+            lo_hi = dp.all_max([c, -c])
+            if int(lo_hi[0]) != -int(lo_hi[1]):
+                raise RuntimeError(f"data-parallel {what}: ranks disagree ({int(-lo_hi[1])}..{int(lo_hi[0])}); "
+                                   "use batch_size >= the per-rank collect size")
+
     # ---- device helpers -----------------------------------------------------------------------------------
     def _s(self):
         return torch.cuda.current_stream().cuda_stream
@@ -66,6 +116,7 @@ class TrustRegionMixin:
     def _hvp(self, d, v, out):
         _lib.check(_lib.lib.fsrl_cpo_hvp(ctypes.byref(d), v.data_ptr(), self._v_w2n.data_ptr(), out.data_ptr(),
                                          float(self._damping_coeff), self._s()))
+        self._gvec(out)      # H = sum_r w_r H_r (the damping term carries through: sum_r w_r = 1)
 
     def _cg(self, d, rhs: torch.Tensor, out: torch.Tensor, nsteps: int = 10, residual_tol: float = 1e-8):
         """cpo.py:184-204, vectors on the device, two scalars per iteration on the host."""
@@ -91,6 +142,7 @@ class TrustRegionMixin:
         eng = self._eng
         crit = self.arena.slots[1:1 + self.critics_num]
         inp = eng.make_input(batch.obs, perm)
+        n_g = self._dp_begin(n)
         eng.forward(crit, inp, n, save=True)
         stats = {}
         for i, s in enumerate(crit):
@@ -100,9 +152,12 @@ class TrustRegionMixin:
                                               eng.slot_view(s, "dout").data_ptr(), self._sums.data_ptr(), self._s()))
             th = self.arena.theta[s.offset:s.offset + s.size]
             reg = (self._dotp(th, th) * self._l2_reg) if self._l2_reg else 0.0
-            stats["loss/vf" + str(i)] = float(self._sums[0].item()) / n + reg
+            stats["loss/vf" + str(i)] = self._gscalar(float(self._sums[0].item())) / n_g + reg
         eng.backward(crit, n)
         eng.wgrad(crit, inp, n)
+        if self._dpw is not None:
+            for s in crit:
+                self._gvec(self.arena.grad[s.offset:s.offset + s.size])
         self._critic_t += 1
         g = self.optim.param_groups[0]
         eng.adam(crit, g["lr"], self._critic_t, betas=g["betas"], eps=g["eps"], l2_reg=self._l2_reg)

@@ -285,6 +285,11 @@ typedef struct fsrl_offpolicy {
     float *q_out[4], *q_dout[4], *q_dx[4], *q_old_out[4];
     float* alpha;        /* device scalar */
     float* alpha_state;  /* device [log_alpha, adam_m, adam_v, adam_t] */
+    /* data parallel (world > 1): every rank samples its own replay shard; per gradient step the
+     * critics' and the actor's gradients are all-reduced (one grouped NCCL call each) and averaged,
+     * and the entropy-tuning statistic is all-reduced so that alpha stays identical on all ranks */
+    void* comm;
+    int world, pad1;
 } fsrl_offpolicy_t;
 
 int fsrl_nstep_prepare(const fsrl_offpolicy_t* d, const int* idx, int B, void* stream);
@@ -339,6 +344,10 @@ int fsrl_comm_init(const char* id128, int rank, int world, void** comm_out);
 int fsrl_comm_destroy(void* comm);
 int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
 int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
+/* in-place sum of `n_ranges` sub-ranges [base + offs[i], base + offs[i] + counts[i]) in ONE grouped
+ * NCCL call (the gradient slices of a net list inside the flat gradient buffer) */
+int fsrl_allreduce_ranges(void* comm, float* base, const long long* offs, const long long* counts,
+                          int n_ranges, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,3 +57,106 @@ def test_two_rank_update_keeps_parameters_identical():
     assert np.array_equal(t0, t1), np.abs(t0 - t1).max()
     assert lag0 == lag1
     assert d0 > 0 and np.isfinite(t0).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPO / TRPO-Lag / SAC-Lag / DDPG-Lag under data parallelism
+# ---------------------------------------------------------------------------------------------------
+def _build_algo(algo, device, seed=10, n_env=4):
+    from fsrl_b200 import envs
+    from fsrl_b200.agent import CPOAgent, DDPGLagAgent, SACLagAgent, TRPOLagAgent
+    from fsrl_b200.data import FastCollector, VectorReplayBuffer
+    task = "SafetyCarRun-v0" if algo in ("sac", "ddpg") else "SafetyCarCircle-v0"
+    env = envs.make(task)
+    hs = (64, 64)
+    if algo == "cpo":
+        agent = CPOAgent(env, seed=seed, hidden_sizes=hs, device=device, optim_critic_iters=3)
+    elif algo == "trpo":
+        agent = TRPOLagAgent(env, seed=seed, hidden_sizes=hs, device=device, optim_critic_iters=3, target_kl=0.001)
+    elif algo == "sac":
+        agent = SACLagAgent(env, seed=seed, hidden_sizes=hs, device=device, unbounded=True, n_step=2, tau=0.05)
+    else:
+        agent = DDPGLagAgent(env, seed=seed, hidden_sizes=hs, device=device, n_step=2, tau=0.05)
+    venv = envs.DeviceVectorEnv(task, n_env, seed=seed + 2, device=device)
+    buf = VectorReplayBuffer(n_env * env.spec.max_episode_steps, n_env, device=device)
+    col = FastCollector(agent.policy, venv, buf, exploration_noise=True)
+    return agent.policy, venv, buf, col
+
+
+def _run_update(algo, policy, buf, col, env_seed, act_seed):
+    col.env.seed(env_seed); col.reset_env()
+    policy.set_action_seed(act_seed)
+    stats = col.collect(n_episode=4)
+    policy.pre_update_fn(stats_train=stats)
+    np.random.seed(77)
+    if algo in ("sac", "ddpg"):
+        policy.update_many(6, 64, buf)
+    else:
+        idx = buf.sample_indices(0)
+        batch = policy.process_fn(None, buf, idx)
+        policy.learn(batch, batch_size=99999, repeat=1)
+    torch.cuda.synchronize()
+    return policy.arena.theta.detach().cpu().numpy().copy()
+
+
+def _algo_worker(rank, world, port, q, algo, replicated):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fsrl_b200 import parallel
+    policy, venv, buf, col = _build_algo(algo, dev)
+    theta_init = policy.arena.theta.detach().cpu().numpy().copy()
+    base_upd = getattr(policy, "_upd_seed", 0)
+    parallel.attach(policy, dist, device=dev)
+    if replicated:
+        # both ranks see IDENTICAL data and noise: the union-batch update must equal the single-GPU one
+        if hasattr(policy, "_upd_seed"):
+            policy._upd_seed = base_upd
+        theta = _run_update(algo, policy, buf, col, 12, 11)
+        ref_policy, _, rbuf, rcol = _build_algo(algo, dev)
+        theta_ref = _run_update(algo, ref_policy, rbuf, rcol, 12, 11)
+        q.put((rank, theta, theta_ref, theta_init))
+    else:
+        theta = _run_update(algo, policy, buf, col, parallel.shard_seed(12, rank), parallel.shard_seed(11, rank))
+        q.put((rank, theta, None, theta_init))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _spawn(algo, replicated):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000) + (hash((algo, replicated)) % 50)
+    procs = [ctx.Process(target=_algo_worker, args=(r, 2, port, q, algo, replicated)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("algo", ["cpo", "trpo", "sac", "ddpg"])
+def test_two_rank_sharded_update_stays_in_lock_step(algo):
+    (_, t0, _, init), (_, t1, _, _) = _spawn(algo, replicated=False)
+    assert np.isfinite(t0).all()
+    assert np.array_equal(t0, t1), np.abs(t0 - t1).max()      # bit-identical parameters on both ranks
+    assert np.abs(t0 - init).max() > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("algo", ["cpo", "trpo", "sac", "ddpg"])
+def test_two_rank_replicated_data_equals_single_gpu_update(algo):
+    (_, t0, ref0, init), (_, t1, _, _) = _spawn(algo, replicated=True)
+    assert np.array_equal(t0, t1)
+    moved = np.abs(ref0 - init).max()
+    assert moved > 0
+    # averaging two identical shards = the single-GPU update (only the reduction order differs)
+    assert np.abs(t0 - ref0).max() <= 2e-2 * moved + 2e-6, (np.abs(t0 - ref0).max(), moved)
