@@ -90,7 +90,9 @@ class PpoUpdate(ctypes.Structure):
                 ("use_lagrangian", c_int),
                 ("lr", c_f64), ("beta1", c_f64), ("beta2", c_f64), ("adam_eps", c_f64),
                 ("comm", c_vp), ("moments_w", c_vp), ("moments", c_vp), ("world", c_int),
-                ("batch_size", c_int), ("gather", c_vp), ("mb_stats", c_vp), ("barrier", c_vp)]
+                ("batch_size", c_int), ("gather", c_vp), ("mb_stats", c_vp), ("barrier", c_vp),
+                ("p2p_xg", (c_vp * 8) * 2), ("p2p_flags", c_vp * 8), ("p2p_err", c_vp), ("p2p_part", c_vp),
+                ("p2p_rank", c_int), ("p2p_on", c_int)]
 
 
 
@@ -178,6 +180,13 @@ SIGNATURES = {
     "fsrl_comm_destroy": (c_int, [c_vp]),
     "fsrl_allreduce_fused": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_allreduce_ranges": (c_int, [c_vp, c_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), c_int, c_vp]),
+    "fsrl_p2p_stride": (ctypes.c_longlong, [ctypes.c_longlong]),
+    "fsrl_p2p_block_bytes": (ctypes.c_longlong, [ctypes.c_longlong]),
+    "fsrl_p2p_alloc": (c_int, [ctypes.c_longlong, ctypes.POINTER(c_vp), ctypes.c_char_p]),
+    "fsrl_p2p_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "fsrl_p2p_close": (c_int, [c_vp]),
+    "fsrl_p2p_free": (c_int, [c_vp]),
+    "fsrl_p2p_poll_error": (c_int, [c_vp, ctypes.POINTER(c_int)]),
     "fsrl_allreduce_f64": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_cpo_head": (c_int, [ctypes.POINTER(Cpo), c_int, c_vp, c_vp]),
     "fsrl_cpo_hvp": (c_int, [ctypes.POINTER(Cpo), c_vp, c_vp, c_vp, c_f64, c_vp]),

@@ -70,3 +70,45 @@ extern "C" int fsrl_allreduce_ranges(void* comm, float* base, const long long* o
     FSRL_NCCL(ncclGroupEnd());
     return FSRL_OK;
 }
+
+// ---- peer-memory exchange blocks (CUDA IPC; one process per GPU) ------------------------------------
+extern "C" long long fsrl_p2p_stride(long long n) { return (n + 63) / 64 * 64; }
+extern "C" long long fsrl_p2p_block_bytes(long long n) {
+    return 2 * fsrl_p2p_stride(n) * (long long)sizeof(float) + FSRL_P2P_MAX_RANKS * 8 + 64 + FSRL_P2P_PARTIALS * (long long)sizeof(float);
+}
+extern "C" int fsrl_p2p_alloc(long long n_floats, void** base_out, char* ipc64_out) {
+    FSRL_REQUIRE(n_floats > 0 && base_out && ipc64_out, "p2p_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size changed");
+    void* p = nullptr;
+    const size_t bytes = (size_t)fsrl_p2p_block_bytes(n_floats);
+    FSRL_CUDA(cudaMalloc(&p, bytes));
+    FSRL_CUDA(cudaMemset(p, 0, bytes));
+    FSRL_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    FSRL_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(ipc64_out, &h, 64);
+    *base_out = p;
+    return FSRL_OK;
+}
+extern "C" int fsrl_p2p_open(const char* ipc64, void** peer_base_out) {
+    FSRL_REQUIRE(ipc64 && peer_base_out, "p2p_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc64, 64);
+    void* p = nullptr;
+    FSRL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_base_out = p;
+    return FSRL_OK;
+}
+extern "C" int fsrl_p2p_close(void* peer_base) {
+    if (peer_base) FSRL_CUDA(cudaIpcCloseMemHandle(peer_base));
+    return FSRL_OK;
+}
+extern "C" int fsrl_p2p_free(void* base) {
+    if (base) FSRL_CUDA(cudaFree(base));
+    return FSRL_OK;
+}
+extern "C" int fsrl_p2p_poll_error(const int* err_dev, int* out_host) {
+    FSRL_REQUIRE(err_dev && out_host, "p2p_poll_error: null pointer");
+    FSRL_CUDA(cudaMemcpy(out_host, err_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    return FSRL_OK;
+}

@@ -597,7 +597,7 @@ __device__ __forceinline__ void ppo_wgrad_role(const fsrl_ppo_update_t& u, int m
     auto finish = [&]() {  // norm contribution (+ barrier and clip scale when fused)
         if (FUSED && tid == 0) { const int c = bx + 40 * net; DBG_CTA(c, clock64() - t_start); }
         const float tot = block_sum_256(sq, s_red);
-        if (tid == 0 && tot != 0.f) atomicAdd(u.norm_sq, tot);
+        if (tid == 0 && tot != 0.f && u.world <= 1) atomicAdd(u.norm_sq, tot);   // DP: the norm of the REDUCED gradient is taken later
         if (FUSED) {
             grid_barrier(bar, bar_target);
             if (tid == 0) { const int c = bx + 40 * net; DBG_CTA(256 + c, clock64() - t_start); }
@@ -863,9 +863,19 @@ __global__ void __launch_bounds__(256)
 adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s, float eps,
             float neg_step, int slot, int n_plain_blocks) {
     __shared__ float tile[32][33];
+    __shared__ float nred[8];
     const float gs = (u.world > 1) ? 1.0f / (float)u.world : 1.0f;     // average the summed gradients
     float scale = gs;
-    const float nsq = *u.norm_sq * gs * gs;
+    float nsq_raw;
+    if (u.world > 1 && u.p2p_on) {       // deterministic (rank-identical) sum of the per-CTA partials
+        const int nblk = (int)((u.n_params + 1023) / 1024);
+        float sp = 0.f;
+        for (int i = threadIdx.x; i < nblk; i += 256) sp += __ldcg(u.p2p_part + i);
+        nsq_raw = block_sum_256(sp, nred);
+    } else {
+        nsq_raw = *u.norm_sq;
+    }
+    const float nsq = nsq_raw * gs * gs;
     if (u.max_grad_norm > 0.f) {
         const float coef = u.max_grad_norm / (sqrtf(nsq) + 1e-6f);
         scale = gs * fminf(coef, 1.0f);
@@ -915,6 +925,66 @@ adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s,
             mir[(size_t)(o0 + oo) * H + k0 + lx] = tile[lx][oo];
         }
     }
+}
+
+// Data-parallel gradient exchange over peer memory (NVLink), fused with the norm of the reduced
+// gradient: every rank's weight-gradient kernel wrote its local gradient into its own exchange
+// buffer (parity id & 1); this kernel (1) tells every peer "my step `id` is complete" by a
+// system-scope release store into the peer's flag array, (2) waits until all ranks' flags reached
+// `id`, (3) sums the ranks' buffers in rank order -- one 16-byte load per rank and element group,
+// all in flight together -- into u.grad and accumulates sum g^2.  Every rank computes the same
+// sum in the same order: parameters stay bit-identical without a broadcast.  Two buffers suffice:
+// a rank can only overwrite parity b again after the barrier of step id + 1, which every peer
+// joins after it has finished reading step id.
+constexpr long long P2P_TIMEOUT_CYCLES = 40000000000LL;     // ~20 s: a missing peer must not hang the GPU
+__global__ void __launch_bounds__(256) ppo_dp_reduce_kernel(const fsrl_ppo_update_t u, unsigned long long id) {
+    __shared__ float red[8];
+    pdl_wait();                       // the local weight gradients are complete
+    pdl_trigger();
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid < u.world) {
+        __threadfence_system();
+        unsigned long long* f = u.p2p_flags[tid] + u.p2p_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(id) : "memory");
+    }
+    if (tid < u.world) {
+        const unsigned long long* f = u.p2p_flags[u.p2p_rank] + tid;
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        } while (v < id && clock64() - t0 < P2P_TIMEOUT_CYCLES);
+        if (v < id) *u.p2p_err = 1;
+    }
+    __syncthreads();
+    const int par = (int)(id & 1ULL);
+    const long long i4 = ((long long)blockIdx.x * 256 + tid) * 4;
+    float sq = 0.f;
+    if (i4 < u.n_params) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v[FSRL_P2P_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < FSRL_P2P_MAX_RANKS; ++r) {
+            if (r < u.world) {
+                const float* src = u.p2p_xg[par][r] + i4;      // buffers are padded: the float4 never leaves them
+                asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w) : "l"(src));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < FSRL_P2P_MAX_RANKS; ++r) {
+            if (r < u.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        }
+        if (i4 + 3 < u.n_params) {
+            *reinterpret_cast<float4*>(u.grad + i4) = acc;
+            sq = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+        } else {
+            const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+            for (int q = 0; q < 4 && i4 + q < u.n_params; ++q) { u.grad[i4 + q] = a[q]; sq += a[q] * a[q]; }
+        }
+    }
+    const float tot = block_sum_256(sq, red);
+    if (tid == 0) u.p2p_part[blockIdx.x] = tot;     // no atomics: the Adam kernel sums these in a fixed order
 }
 
 // sum of squares of the (all-reduced) gradient buffer -> *u.norm_sq
@@ -1068,8 +1138,18 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
                                target, slot));
         return FSRL_OK;
     }
+    if (u.world > 1 && u.p2p_on) {
+        // data parallel over peer memory: wgrad -> own exchange buffer, then signal / wait / sum / norm
+        const unsigned long long id = (unsigned long long)adam_t;
+        fsrl_ppo_update_t ux = u;
+        ux.grad = const_cast<float*>(u.p2p_xg[id & 1ULL][u.p2p_rank]);
+        FSRL_CUDA(launch_chain(ppo_wgrad_kernel<H>, gB, dim3(WG_TPB), smemW, s, false, ux, mb_off, B));
+        const unsigned nblk = (unsigned)((u.n_params + 1023) / 1024);
+        FSRL_CUDA(launch_chain(ppo_dp_reduce_kernel, dim3(nblk), dim3(256), (size_t)0, s, false, u, id));
+    } else {
     FSRL_CUDA(launch_chain(ppo_wgrad_kernel<H>, gB, dim3(WG_TPB), smemW, s, false, u, mb_off, B));
-    if (u.world > 1) {
+    }
+    if (u.world > 1 && !u.p2p_on) {
         // data parallel: ONE all-reduce of the flat gradient buffer per optimiser step, then the
         // global norm of the reduced gradient (the local partial norms are meaningless now)
         int rc = fsrl_allreduce_fused(u.comm, u.grad, u.n_params, s);
@@ -1110,6 +1190,13 @@ static int check_update(const fsrl_ppo_update_t* u) {
     FSRL_REQUIRE(u->n_nets >= 1 && u->n_nets <= 3 && u->C == u->n_nets - 1, "ppo: n_nets/C inconsistent");
     FSRL_REQUIRE(u->A >= 1 && u->A <= 8, "ppo: action dim %d out of range", u->A);
     FSRL_REQUIRE(u->theta && u->grad && u->adam_m && u->adam_v && u->w2n && u->scratch && u->norm_sq, "ppo: null buffer");
+    if (u->world > 1 && u->p2p_on) {
+        FSRL_REQUIRE(u->world <= FSRL_P2P_MAX_RANKS && u->p2p_rank >= 0 && u->p2p_rank < u->world && u->p2p_err && u->p2p_part,
+                     "ppo: peer exchange needs world <= %d, a valid rank, an error flag and the partials", FSRL_P2P_MAX_RANKS);
+        FSRL_REQUIRE(u->n_params <= 1024LL * FSRL_P2P_PARTIALS, "ppo: %lld parameters exceed the peer-exchange limit", u->n_params);
+        for (int r = 0; r < u->world; ++r)
+            FSRL_REQUIRE(u->p2p_xg[0][r] && u->p2p_xg[1][r] && u->p2p_flags[r], "ppo: peer %d is not mapped", r);
+    }
     return FSRL_OK;
 }
 

@@ -7,8 +7,10 @@ identical on all ranks by
                 mean episodic cost);
 * per repeat  : one all-reduce of the per-minibatch advantage moments, so the per-minibatch
                 normalisation (ppo_lag.py:178-182) is over the GLOBAL minibatch;
-* per step    : ONE NCCL all-reduce of the flat gradient buffer, issued from the C update loop
-                (csrc/ppo.cu) between the weight-gradient and Adam kernels;
+* per step    : the flat gradient buffers are exchanged over PEER MEMORY (CUDA-IPC mapped blocks,
+                NVLink): ppo_dp_reduce_kernel signals, waits and sums all ranks' buffers in rank
+                order, fused with the gradient norm -- no NCCL launch on the step path (NCCL
+                all-reduce remains as the fallback when peer mapping is unavailable);
 * per repeat  : the KL early-stop statistic is averaged so that all ranks stop together.
 
 Off-policy learners (SAC / DDPG): every rank samples its own replay shard; the C loop
@@ -51,6 +53,66 @@ class DataParallel:
                 _lib.check(_lib.lib.fsrl_comm_init(idb, self.rank, self.world, ctypes.byref(comm)))
             self.comm = comm
 
+    # ---- peer-memory gradient exchange (csrc/ppo.cu::ppo_dp_reduce_kernel) -----------------------
+    def enable_p2p(self, n_floats: int) -> bool:
+        """Allocate this rank's exchange block, swap CUDA-IPC handles with the peers and map their
+        blocks.  Returns False (NCCL stays in use) if the world is too large or mapping fails."""
+        from . import _lib
+        lib = _lib.lib
+        if self.world < 2 or self.world > 8 or n_floats > 4096 * 1024 or getattr(self, "p2p", None) is not None:
+            return getattr(self, "p2p", None) is not None
+        with torch.cuda.device(self.device):
+            base = ctypes.c_void_p()
+            raw = ctypes.create_string_buffer(64)
+            _lib.check(lib.fsrl_p2p_alloc(int(n_floats), ctypes.byref(base), raw))
+            mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).to(self.device)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+            self.dist.all_gather(allh, mine)
+            bases, ok = [], 1
+            for r in range(self.world):
+                if r == self.rank:
+                    bases.append(base.value)
+                    continue
+                pb = ctypes.c_void_p()
+                rc = lib.fsrl_p2p_open(bytes(allh[r].cpu().numpy().tobytes()), ctypes.byref(pb))
+                if rc != 0:
+                    ok = 0
+                bases.append(pb.value)
+            ok = int(self.all_max([-ok])[0]) == -1          # everybody mapped everybody?
+        if not ok:
+            return False
+        stride = int(lib.fsrl_p2p_stride(int(n_floats)))
+        self.p2p = {"bases": bases, "n": int(n_floats), "stride": stride,
+                    "xg": [[b + par * stride * 4 for b in bases] for par in (0, 1)],
+                    "flags": [b + 2 * stride * 4 for b in bases],
+                    "err": base.value + 2 * stride * 4 + 8 * 8,
+                    "part": base.value + 2 * stride * 4 + 8 * 8 + 64}
+        return True
+
+    def fill_p2p(self, u) -> None:
+        """Hand the mapped exchange blocks to an update descriptor (fsrl_ppo_update_t)."""
+        p = getattr(self, "p2p", None)
+        if p is None:
+            u.p2p_on = 0
+            return
+        for par in (0, 1):
+            for r in range(self.world):
+                u.p2p_xg[par][r] = p["xg"][par][r]
+        for r in range(self.world):
+            u.p2p_flags[r] = p["flags"][r]
+        u.p2p_err, u.p2p_part, u.p2p_rank, u.p2p_on = p["err"], p["part"], self.rank, 1
+
+    def p2p_check(self) -> None:
+        p = getattr(self, "p2p", None)
+        if p is None:
+            return
+        from . import _lib
+        err = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.fsrl_p2p_poll_error(p["err"], ctypes.byref(err)))
+        if err.value:
+            raise RuntimeError("data-parallel gradient exchange: a peer rank never arrived (timed out)")
+
     # ---- host-side scalar reductions -----------------------------------------------------------
     def all_sum(self, values) -> np.ndarray:
         t = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self.device)
@@ -87,7 +149,7 @@ def shard_seed(seed: int, rank: int) -> int:
     return (int(seed) + 1000003 * int(rank)) & 0xFFFFFFFF
 
 
-def attach(policy, dist, device=None) -> DataParallel:
+def attach(policy, dist, device=None, p2p: bool = True) -> DataParallel:
     """Make `policy` data parallel: broadcast rank 0's parameters, hook the collect-statistics
     reduction into pre_update_fn, and hand the NCCL communicator to the update descriptor."""
     device = device if device is not None else policy.device
@@ -96,6 +158,9 @@ def attach(policy, dist, device=None) -> DataParallel:
     if hasattr(policy, "_mirror_dirty"):
         policy._mirror_dirty = True
     policy._dp = dp
+    from .policy.ppo_lag import PPOLagrangian
+    if p2p and dp.world > 1 and isinstance(policy, PPOLagrangian):
+        dp.enable_p2p(policy.arena.theta.numel())       # PPO-Lag: gradients over peer memory
     if hasattr(policy, "_upd_seed"):      # off-policy rsample / exploration noise: one stream per rank
         policy._upd_seed = shard_seed(policy._upd_seed, dp.rank)
     inner = policy.pre_update_fn

@@ -140,6 +140,7 @@ class PPOLagrangian(LagrangianPolicy):
                 self._moments = torch.zeros(4 * n_mb, dtype=torch.float64, device=ar.device)
             u.comm, u.world, u.batch_size = dp.comm, dp.world, self._dp_batch
             u.moments_w = u.moments = self._moments.data_ptr()
+            dp.fill_p2p(u)
         return u
 
     # -----------------------------------------------------------------------------------------------
@@ -203,6 +204,8 @@ class PPOLagrangian(LagrangianPolicy):
                 if approx_kl > 1.5 * self._target_kl:
                     self.logger.print("Early stop at step %d due to reaching max kl." % step)
                     break
+        if getattr(self, "_dp", None) is not None:
+            self._dp.p2p_check()             # raises if a peer rank never joined a gradient exchange
         self._log_stats(np.concatenate(rows, axis=0), u)
         self.logger.store(gradient_steps=self.gradient_steps, tab="update")
 

@@ -177,6 +177,18 @@ typedef struct fsrl_ppo_update {
     float* mb_stats;
     /* device u64 ticket counter of the in-kernel grid barrier (fused wgrad + Adam launch) */
     unsigned long long* barrier;
+    /* peer-memory gradient exchange (world > 1, optional; NCCL all-reduce when p2p_on == 0):
+     * rank r's exchange block (fsrl_p2p_alloc) mapped into this process -- p2p_xg[b][r] its
+     * gradient buffer of step parity b, p2p_flags[r] its arrival flags [FSRL_P2P_MAX_RANKS] --
+     * entries [.][p2p_rank] are this rank's own block.  The weight-gradient kernel writes into the
+     * local buffer; ppo_dp_reduce_kernel signals the peers, waits for their flags and sums all
+     * ranks' buffers over NVLink in rank order (bit-identical result everywhere). */
+    const float* p2p_xg[2][8];
+    unsigned long long* p2p_flags[8];
+    int* p2p_err;                  /* local: set to 1 if a peer never arrived (wait timed out) */
+    float* p2p_part;               /* local [FSRL_P2P_PARTIALS]: per-CTA sums of g^2 (summed in a fixed
+                                    * order by the Adam kernel: atomics would break rank lock-step) */
+    int p2p_rank, p2p_on;
 } fsrl_ppo_update_t;
 
 size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax);
@@ -344,6 +356,18 @@ int fsrl_comm_init(const char* id128, int rank, int world, void** comm_out);
 int fsrl_comm_destroy(void* comm);
 int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
 int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
+/* Peer-memory exchange block of one rank: [xg0 | xg1 | flags | err | partials], each gradient buffer padded
+ * to fsrl_p2p_stride(n) floats.  alloc: cudaMalloc + zero + IPC handle (64 bytes) for the other
+ * processes; open / close: map / unmap a peer's block; free: release the own block. */
+#define FSRL_P2P_MAX_RANKS 8
+#define FSRL_P2P_PARTIALS 4096   /* one per 1024 parameters: peer exchange handles up to 4M parameters */
+long long fsrl_p2p_stride(long long n_floats);
+long long fsrl_p2p_block_bytes(long long n_floats);
+int fsrl_p2p_alloc(long long n_floats, void** base_out, char* ipc64_out);
+int fsrl_p2p_open(const char* ipc64, void** peer_base_out);
+int fsrl_p2p_close(void* peer_base);
+int fsrl_p2p_free(void* base);
+int fsrl_p2p_poll_error(const int* err_dev, int* out_host); /* 1 = a peer never arrived */
 /* in-place sum of `n_ranges` sub-ranges [base + offs[i], base + offs[i] + counts[i]) in ONE grouped
  * NCCL call (the gradient slices of a net list inside the flat gradient buffer) */
 int fsrl_allreduce_ranges(void* comm, float* base, const long long* offs, const long long* counts,

@@ -11,20 +11,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
-    import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+def _ppo_update(rank, dist, p2p):
     from helpers import build_ppo
     from fsrl_b200 import parallel
     policy, venv, buf, col = build_ppo("SafetyBallCircle-v0", hidden=(64, 64), n_env=4, seed=10,
                                        device=f"cuda:{rank}", max_grad_norm=0.5)
     venv.seed(parallel.shard_seed(12, rank)); col.reset_env()
     policy.set_action_seed(parallel.shard_seed(11, rank))
-    dp = parallel.attach(policy, dist, device=f"cuda:{rank}")
+    dp = parallel.attach(policy, dist, device=f"cuda:{rank}", p2p=p2p)
+    assert (getattr(dp, "p2p", None) is not None) == p2p
     stats = col.collect(n_episode=4)
     policy.pre_update_fn(stats_train=stats)
     idx = buf.sample_indices(0)
@@ -32,10 +27,22 @@ def _worker(rank, world, port, q):
     policy._target_kl = 1e9
     np.random.seed(100 + rank)
     theta0 = policy.arena.theta.clone()
-    policy.learn(batch, batch_size=100, repeat=1)
+    policy.learn(batch, batch_size=100, repeat=2)
     theta = policy.arena.theta.cpu().numpy()
-    q.put((rank, theta, policy.lagrangians()[0], float(np.mean(policy.last_stats["loss/kl"])),
-           float((policy.arena.theta - theta0).abs().max().item())))
+    return (theta, policy.lagrangians()[0], float(np.mean(policy.last_stats["loss/kl"])),
+            float((policy.arena.theta - theta0).abs().max().item()))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    peer = _ppo_update(rank, dist, p2p=True)        # gradients summed over peer memory (NVLink loads)
+    nccl = _ppo_update(rank, dist, p2p=False)       # same data through the NCCL all-reduce fallback
+    q.put((rank, peer, nccl))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,10 +60,13 @@ def test_two_rank_update_keeps_parameters_identical():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    (_, t0, lag0, kl0, d0), (_, t1, lag1, kl1, d1) = res
-    assert np.array_equal(t0, t1), np.abs(t0 - t1).max()
-    assert lag0 == lag1
-    assert d0 > 0 and np.isfinite(t0).all()
+    (_, peer0, nccl0), (_, peer1, nccl1) = res
+    for (t0, lag0, kl0, d0), (t1, lag1, kl1, d1) in ((peer0, peer1), (nccl0, nccl1)):
+        assert np.array_equal(t0, t1), np.abs(t0 - t1).max()       # lock-step on both exchange paths
+        assert lag0 == lag1
+        assert d0 > 0 and np.isfinite(t0).all()
+    # peer-memory sum (rank order) vs NCCL's reduction order: same update up to fp32 rounding
+    assert np.abs(peer0[0] - nccl0[0]).max() <= 1e-2 * peer0[3] + 1e-6, np.abs(peer0[0] - nccl0[0]).max()
 
 
 # ---------------------------------------------------------------------------------------------------
