@@ -182,11 +182,11 @@ def install(force: bool = False) -> List[str]:
         f_net_cont = _mod("fsrl.utils.net.continuous", DoubleCritic=_nets.DoubleCritic, SingleCritic=_nets.SingleCritic)
         f_net = _mod("fsrl.utils.net", common=f_net_common, continuous=f_net_cont)
         f_logger = _mod("fsrl.utils.logger", BaseLogger=_logger.BaseLogger, DummyLogger=_logger.DummyLogger,
-                        TensorboardLogger=_logger.BaseLogger, WandbLogger=_logger.BaseLogger)
+                        TensorboardLogger=_logger.TensorboardLogger, WandbLogger=_logger.WandbLogger)
         sys.modules["fsrl.utils.exp_util"] = _exp_util
         sys.modules["fsrl.utils.optim_util"] = _optim_util
         f_utils = _mod("fsrl.utils", BaseLogger=_logger.BaseLogger, DummyLogger=_logger.DummyLogger,
-                       TensorboardLogger=_logger.BaseLogger, WandbLogger=_logger.BaseLogger,
+                       TensorboardLogger=_logger.TensorboardLogger, WandbLogger=_logger.WandbLogger,
                        exp_util=_exp_util, optim_util=_optim_util, net=f_net, logger=f_logger)
         cfgs = {}
         for key in ("ppol", "cpo", "sacl", "ddpgl"):

@@ -178,3 +178,76 @@ class DummyLogger(BaseLogger):
 
     def print(self, *args, **kwargs) -> None:
         pass
+
+
+class TensorboardLogger(BaseLogger):
+    """BaseLogger + a tensorboard event file under ``<log_dir>/tb`` (reference:
+    fsrl/utils/logger/tb_logger.py:10-81): every ``write`` also emits one scalar per stored
+    key, and ``restore_data`` recovers (epoch, env_step, gradient_step) from the event file
+    of an earlier run so that ``agent.learn(resume=True)`` continues the counters."""
+
+    def __init__(self, log_dir: str = None, log_txt: bool = True, name: str = None) -> None:
+        super().__init__(log_dir, log_txt, name)
+        from torch.utils.tensorboard import SummaryWriter
+        self.summary_writer = SummaryWriter(os.path.join(self.log_dir, "tb"))
+        self.last_save_step = self.last_log_test_step = -1
+        self.last_log_update_step = self.last_log_train_step = -1
+
+    def write(self, step: int, display: bool = True, display_keys: Iterable[str] = None) -> None:
+        self.store(tab="update", env_step=step)
+        self.write_without_reset(step)
+        return super().write(step, display, display_keys)
+
+    def write_without_reset(self, step: int) -> None:
+        for key in self.logger_keys:
+            self.summary_writer.add_scalar(key, self.get_mean(key), step)
+        self.summary_writer.flush()
+
+    def restore_data(self):
+        from tensorboard.backend.event_processing import event_accumulator
+        acc = event_accumulator.EventAccumulator(self.summary_writer.log_dir)
+        acc.Reload()
+
+        def last_step(tag):
+            return acc.scalars.Items(tag)[-1].step
+
+        epoch = gradient_step = env_step = 0
+        try:
+            epoch = last_step("update/episode")
+            self.last_save_step = self.last_log_test_step = epoch
+            gradient_step = last_step("update/gradient_steps")
+            self.last_log_update_step = gradient_step
+        except KeyError:
+            epoch, gradient_step = 0, 0
+        try:
+            env_step = last_step("update/env_step")
+            self.last_log_train_step = env_step
+        except KeyError:
+            env_step = 0
+        return epoch, env_step, gradient_step
+
+
+class WandbLogger(BaseLogger):
+    """BaseLogger + Weights & Biases (reference: fsrl/utils/logger/wandb_logger.py:9-73): a run is
+    opened (or the already active one adopted) at construction and the per-key means are sent
+    with every ``write``.  The container has no network: pass ``WANDB_MODE=offline``."""
+
+    def __init__(self, config: dict = {}, project: str = "fsrl", group: str = "test", name: str = None,
+                 log_dir: str = "log", log_txt: bool = True) -> None:
+        super().__init__(log_dir, log_txt, name)
+        import uuid
+        import wandb
+        self._wandb = wandb
+        self.wandb_run = wandb.run if wandb.run else wandb.init(
+            project=project, group=group, name=name, id=str(uuid.uuid4()), resume="allow", config=config)
+
+    def write(self, step: int, display: bool = True, display_keys: Iterable[str] = None) -> None:
+        self.store(tab="update", env_step=step)
+        self.write_without_reset(step)
+        return super().write(step, display, display_keys)
+
+    def write_without_reset(self, step: int) -> None:
+        self._wandb.log(self.stats_mean, step=step)
+
+    def restore_data(self) -> None:
+        """The reference does not restore W&B runs either (wandb_logger.py:72-73)."""

@@ -111,6 +111,25 @@ def test_logger_formats(tmp_path):
     assert cfg["task"] == "SafetyCarCircle-v0" and torch.equal(model["model"]["w"], torch.ones(2))
 
 
+def test_tensorboard_logger_round_trip(tmp_path):
+    """TensorboardLogger writes scalars per key and restores (epoch, env_step, gradient_step) from
+    its own event file (tb_logger.py:45-81: resume=True reads them back)."""
+    pytest.importorskip("tensorboard")
+    from fsrl_b200.utils.logger import TensorboardLogger
+    lg = TensorboardLogger(str(tmp_path), log_txt=True, name="tb_run")
+    for epoch, (env_step, grad_step) in enumerate([(1000, 40), (2000, 80)], start=1):
+        lg.store(tab="update", episode=epoch, gradient_steps=grad_step)
+        lg.store(tab="train", reward=float(epoch))
+        lg.write(env_step, display=False)
+    lg.summary_writer.close()
+    lg2 = TensorboardLogger(str(tmp_path), log_txt=False, name="tb_run")
+    epoch, env_step, gradient_step = lg2.restore_data()
+    # the reference reads the STEP of the last item (the x axis = env steps), tb_logger.py:66-77
+    assert (epoch, env_step, gradient_step) == (2000, 2000, 2000)
+    lines = open(os.path.join(tmp_path, "tb_run", "progress.txt")).read().strip().split("\n")
+    assert lines[0].split("\t")[0] == "Steps" and len(lines) == 3
+
+
 def test_env_registry_and_dims_without_gpu():
     from fsrl_b200 import envs
     for task, (D, A, T) in {"SafetyCarCircle-v0": (8, 2, 300), "SafetyCarRun-v0": (7, 2, 200),
