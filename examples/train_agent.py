@@ -19,8 +19,8 @@ import bullet_safety_gym  # noqa: E402,F401  (task registration side effect in t
 import gymnasium as gym  # noqa: E402
 from tianshou.env import ShmemVectorEnv, SubprocVectorEnv  # noqa: E402,F401
 
-from fsrl.agent import CPOAgent, DDPGLagAgent, PPOLagAgent, SACLagAgent  # noqa: E402
-from fsrl.config import cpo_cfg, ddpgl_cfg, ppol_cfg, sacl_cfg  # noqa: E402
+from fsrl.agent import CPOAgent, DDPGLagAgent, FOCOPSAgent, PPOLagAgent, SACLagAgent, TRPOLagAgent  # noqa: E402
+from fsrl.config import cpo_cfg, ddpgl_cfg, focosp_cfg, ppol_cfg, sacl_cfg, trpol_cfg  # noqa: E402
 from fsrl.utils import BaseLogger  # noqa: E402
 from fsrl.utils.exp_util import auto_name  # noqa: E402
 
@@ -40,6 +40,17 @@ ALGOS = {
              auto_alpha="auto_alpha", alpha_lr="alpha_lr", alpha="alpha", tau="tau", n_step="n_step",
              conditioned_sigma="conditioned_sigma", unbounded="unbounded", last_layer_scale="last_layer_scale",
              use_lagrangian="use_lagrangian", lagrangian_pid="lagrangian_pid", rescaling="rescaling", gamma="gamma")),
+    "trpol": (trpol_cfg, TRPOLagAgent, dict(lr="lr", hidden_sizes="hidden_sizes", unbounded="unbounded",
+              last_layer_scale="last_layer_scale", target_kl="target_kl", backtrack_coeff="backtrack_coeff",
+              max_backtracks="max_backtracks", optim_critic_iters="optim_critic_iters", gae_lambda="gae_lambda",
+              advantage_normalization="norm_adv", use_lagrangian="use_lagrangian", lagrangian_pid="lagrangian_pid",
+              rescaling="rescaling", gamma="gamma", max_batchsize="max_batchsize", reward_normalization="rew_norm")),
+    "focops": (focosp_cfg, FOCOPSAgent, dict(actor_lr="actor_lr", critic_lr="critic_lr", hidden_sizes="hidden_sizes",
+               unbounded="unbounded", last_layer_scale="last_layer_scale", auto_nu="auto_nu", nu="nu", nu_max="nu_max",
+               nu_lr="nu_lr", l2_reg="l2_reg", delta="delta", eta="eta", tem_lambda="tem_lambda",
+               gae_lambda="gae_lambda", max_grad_norm="max_grad_norm", advantage_normalization="norm_adv",
+               recompute_advantage="recompute_adv", gamma="gamma", max_batchsize="max_batchsize",
+               reward_normalization="rew_norm")),
     "ddpgl": (ddpgl_cfg, DDPGLagAgent, dict(actor_lr="actor_lr", critic_lr="critic_lr", hidden_sizes="hidden_sizes",
               tau="tau", exploration_noise="exploration_noise", n_step="n_step", use_lagrangian="use_lagrangian",
               lagrangian_pid="lagrangian_pid", rescaling="rescaling", gamma="gamma")),

@@ -4,5 +4,6 @@ from .ddpg_lag_agent import DDPGLagAgent
 from .ppo_lag_agent import PPOLagAgent
 from .sac_lag_agent import SACLagAgent
 from .trpo_lag_agent import TRPOLagAgent
+from .focops_agent import FOCOPSAgent
 
-__all__ = ["BaseAgent", "OffpolicyAgent", "OnpolicyAgent", "PPOLagAgent", "SACLagAgent", "DDPGLagAgent", "CPOAgent", "TRPOLagAgent"]
+__all__ = ["BaseAgent", "OffpolicyAgent", "OnpolicyAgent", "PPOLagAgent", "SACLagAgent", "DDPGLagAgent", "CPOAgent", "TRPOLagAgent", "FOCOPSAgent"]

@@ -1,5 +1,5 @@
 """Training configurations with the reference's field names and defaults
-(/root/reference/fsrl/config/{ppol,cpo,sacl,ddpgl}_cfg.py), generated from
+(/root/reference/fsrl/config/{ppol,cpo,sacl,ddpgl,trpol,focosp}_cfg.py), generated from
 one compact table so that the CLI/YAML surface of ``examples/`` keeps working.  Pure data."""
 from __future__ import annotations
 
@@ -37,6 +37,21 @@ _TABLES: Dict[str, Dict[str, Any]] = {
                   rescaling=True, gamma=0.97, deterministic_eval=True, action_scaling=True,
                   action_bound_method="clip", epoch=200, episode_per_collect=2, step_per_epoch=10000,
                   update_per_step=0.2, training_num=10, batch_size=256, prefix="ddpgl", **_COMMON_TAIL),
+    "trpol": dict(_HEAD, lr=5e-4, hidden_sizes=(128, 128), unbounded=False, last_layer_scale=False,
+                  target_kl=0.001, backtrack_coeff=0.8, max_backtracks=10, optim_critic_iters=20,
+                  gae_lambda=0.95, norm_adv=True, use_lagrangian=True, lagrangian_pid=(0.05, 0.0005, 0.1),
+                  rescaling=True, gamma=0.99, max_batchsize=99999, rew_norm=False, deterministic_eval=True,
+                  action_scaling=True, action_bound_method="clip", epoch=200, episode_per_collect=20,
+                  step_per_epoch=10000, repeat_per_collect=4, training_num=20, batch_size=99999,
+                  prefix="trpol", **_COMMON_TAIL),
+    # the reference spells this module `focosp_cfg` (fsrl/config/focosp_cfg.py); both names resolve
+    "focops": dict(_HEAD, actor_lr=5e-4, critic_lr=1e-3, hidden_sizes=(128, 128), unbounded=False,
+                   last_layer_scale=False, auto_nu=True, nu=0, nu_max=2.0, nu_lr=1e-2, l2_reg=0.001,
+                   delta=0.02, eta=0.02, max_grad_norm=0.5, tem_lambda=0.95, gae_lambda=0.95, norm_adv=True,
+                   recompute_adv=False, gamma=0.99, max_batchsize=100000, rew_norm=False,
+                   deterministic_eval=True, action_scaling=True, action_bound_method="clip", epoch=200,
+                   episode_per_collect=20, step_per_epoch=10000, repeat_per_collect=4, training_num=20,
+                   batch_size=256, prefix="focops", **_COMMON_TAIL),
 }
 # per-suite overrides (class name -> changed fields); off-policy Mujoco adds gamma / n_step / buffer
 _ON_MUJOCO = dict(task="SafetyPointCircle1Gymnasium-v0", epoch=250, cost_limit=25, episode_per_collect=20,
@@ -59,11 +74,13 @@ def _module(key: str) -> types.ModuleType:
     m.TrainCfg = base
     for nm, ep in (("Bullet1MCfg", 100), ("Bullet5MCfg", 500), ("Bullet10MCfg", 1000)):
         setattr(m, nm, _dc(nm, {"epoch": ep}, base))
-    mj = _dc("MujocoBaseCfg", _ON_MUJOCO if key in ("ppol", "cpo") else _OFF_MUJOCO, base)
+    mj = _dc("MujocoBaseCfg", _ON_MUJOCO if key in ("ppol", "cpo", "trpol", "focops") else _OFF_MUJOCO, base)
     m.MujocoBaseCfg = mj
     for nm, ep in (("Mujoco2MCfg", 100), ("Mujoco10MCfg", 500), ("Mujoco20MCfg", 1000)):
         setattr(m, nm, _dc(nm, {"epoch": ep}, mj))
     return m
 
 
-ppol_cfg, cpo_cfg, sacl_cfg, ddpgl_cfg = (_module(k) for k in ("ppol", "cpo", "sacl", "ddpgl"))
+ppol_cfg, cpo_cfg, sacl_cfg, ddpgl_cfg, trpol_cfg, focops_cfg = (
+    _module(k) for k in ("ppol", "cpo", "sacl", "ddpgl", "trpol", "focops"))
+focosp_cfg = focops_cfg

@@ -100,6 +100,75 @@ __global__ void cpo_head_kernel(const fsrl_cpo_t d, long long N, int mode, doubl
     }
 }
 
+// FOCOPS actor head (reference fsrl/policy/focops.py:188-215):
+//   L_i = (KL(new || old)_i - (1/lambda) ratio_i (A^r_i - nu A^c_i)) * 1[KL_i <= eta]   (indicator detached)
+// loss = mean_i L_i.  sums[0] += L_i, sums[1] += KL_i, sums[2] += indicator;  dout = d loss / d(z, log sigma).
+// d.adv holds the per-minibatch-normalised advantages of the rows in d.perm.
+__global__ void focops_head_kernel(const fsrl_cpo_t d, long long N, float inv_lambda, float nu, float eta,
+                                   double* __restrict__ sums) {
+    __shared__ double red[3][8];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s_loss = 0.0, s_kl = 0.0, s_cnt = 0.0;
+    if (i < N) {
+        const long long r = d.perm ? (long long)d.perm[i] : i;
+        const int A = d.A;
+        const float invN = 1.0f / (float)N;
+        float logp = 0.f, kl = 0.f;
+        float mup[8], z_[8], sg[8], dklmu[8], dklls[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < A) {
+                const float z = d.out[(size_t)i * 16 + j];
+                const float t = tanhf(z);
+                const float mu = d.bounded ? d.max_action * t : z;
+                mup[j] = d.bounded ? d.max_action * (1.0f - t * t) : 1.0f;
+                const float ls = d.log_sigma[j];
+                sg[j] = expf(ls);
+                z_[j] = (d.act[(size_t)r * A + j] - mu) / sg[j];
+                logp += -0.5f * z_[j] * z_[j] - ls - LOG_SQRT_2PI_C;
+                // kl_divergence(Normal(mu, s), Normal(mu_old, s_old))  (torch formula, p = new, q = old)
+                const float so = d.std_old[(size_t)r * A + j], mo = d.mean_old[(size_t)r * A + j];
+                const float vr = (sg[j] / so) * (sg[j] / so);
+                const float t1 = ((mu - mo) / so) * ((mu - mo) / so);
+                kl += 0.5f * (vr + t1 - 1.0f - logf(vr));
+                dklmu[j] = (mu - mo) / (so * so);
+                dklls[j] = vr - 1.0f;
+            }
+        }
+        const float ratio = expf(logp - d.logp_old[r]);
+        const float adv = d.adv[r] - nu * d.adv[(size_t)d.ld + r];
+        const float keep = (kl <= eta) ? 1.0f : 0.0f;
+        s_loss = (double)((kl - inv_lambda * ratio * adv) * keep);
+        s_kl = (double)kl;
+        s_cnt = (double)keep;
+        float dd[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dd[j] = 0.f;
+        const float gr = -inv_lambda * adv * ratio;          // d L / d logp (before mask and 1/N)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < A) {
+                dd[j] = keep * invN * (dklmu[j] + gr * (z_[j] / sg[j])) * mup[j];
+                dd[A + j] = keep * invN * (dklls[j] + gr * (z_[j] * z_[j] - 1.0f));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(d.dout + (size_t)i * 16 + j) = make_float4(dd[j], dd[j + 1], dd[j + 2], dd[j + 3]);
+    }
+    double v[3] = {s_loss, s_kl, s_cnt};
+    for (int k = 0; k < 3; ++k) {
+        const double t = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+        atomicAdd(sums + threadIdx.x, t);
+    }
+}
+
 // R-head: Re and the log-sigma Hessian contributions from z, Rz and the tangent of log-sigma
 __global__ void cpo_rhead_kernel(const fsrl_cpo_t d, long long N, const float* __restrict__ rz,
                                  const float* __restrict__ vs, float* __restrict__ rdout) {
@@ -339,6 +408,18 @@ extern "C" int fsrl_cpo_head(const fsrl_cpo_t* d, int mode, double* sums, void* 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     FSRL_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), s));
     cpo_head_kernel<<<(unsigned)((d->N + 255) / 256), 256, 0, s>>>(*d, d->N, mode, sums);
+    FSRL_LAUNCH_CHECK();
+    return FSRL_OK;
+}
+
+extern "C" int fsrl_focops_head(const fsrl_cpo_t* d, double inv_lambda, double nu, double eta, double* sums_dev4,
+                                void* stream) {
+    int rc = cpo_check(d);
+    if (rc) return rc;
+    FSRL_REQUIRE(sums_dev4 != nullptr, "focops_head: null sums");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FSRL_CUDA(cudaMemsetAsync(sums_dev4, 0, 4 * sizeof(double), s));
+    focops_head_kernel<<<(unsigned)((d->N + 255) / 256), 256, 0, s>>>(*d, d->N, (float)inv_lambda, (float)nu, (float)eta, sums_dev4);
     FSRL_LAUNCH_CHECK();
     return FSRL_OK;
 }

@@ -153,6 +153,9 @@ def attach(policy, dist, device=None, p2p: bool = True) -> DataParallel:
     """Make `policy` data parallel: broadcast rank 0's parameters, hook the collect-statistics
     reduction into pre_update_fn, and hand the NCCL communicator to the update descriptor."""
     device = device if device is not None else policy.device
+    if type(policy).__name__ == "FOCOPS":
+        raise NotImplementedError("FOCOPS has no data-parallel update yet (SURVEY.md 8e covers PPO-Lag, CPO, "
+                                  "TRPO-Lag, SAC-Lag, DDPG-Lag)")
     dp = DataParallel(dist, device)
     dp.broadcast_(policy.arena.theta)
     if hasattr(policy, "_mirror_dirty"):

@@ -334,6 +334,11 @@ typedef struct fsrl_cpo {
 } fsrl_cpo_t;
 
 int fsrl_cpo_head(const fsrl_cpo_t* d, int mode, double* sums_dev4, void* stream);
+/* FOCOPS actor head (fsrl/policy/focops.py:188-215): loss = mean((KL(new||old) - ratio (A_r - nu A_c) /
+ * lambda) * 1[KL <= eta]); d->adv = per-minibatch-normalised advantages; writes d->dout, and
+ * sums_dev4 = [sum loss_i, sum KL_i, #rows inside the trust region, 0] */
+int fsrl_focops_head(const fsrl_cpo_t* d, double inv_lambda, double nu, double eta, double* sums_dev4,
+                     void* stream);
 int fsrl_cpo_hvp(const fsrl_cpo_t* d, const float* v, float* v_w2n_scratch, float* hv, double damping,
                  void* stream);
 int fsrl_vec_dot(const float* a, const float* b, long long n, double* out_dev, void* stream);

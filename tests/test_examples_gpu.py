@@ -19,6 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ("cpo", ["--repeat_per_collect", "1", "--max_backtracks", "10", "--optim_critic_iters", "2"]),
     ("sacl", ["--update_per_step", "0.05"]),
     ("ddpgl", ["--update_per_step", "0.05"]),
+    ("trpol", ["--repeat_per_collect", "1", "--optim_critic_iters", "2"]),
+    ("focops", ["--repeat_per_collect", "2", "--batch_size", "256"]),
 ])
 def test_agents_train_through_reference_imports(algo, extra, tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "examples"))
