@@ -154,6 +154,29 @@ def gae_time(buf, policy, iters=20):
     return float(np.mean(ts)), n
 
 
+def gae_time_large(device, envs=ENVS * 16, T=300, iters=10):
+    """The same kernel on a 16x larger synthetic collect (SURVEY.md 8d asks for large-E sweeps where
+    the HBM bound is reachable): 412 MB of algorithmic traffic, larger than L2, flushed anyway."""
+    from fsrl_b200 import ops
+    from fsrl_b200.utils.synth import synth_gae_inputs
+    d = synth_gae_inputs(envs, T, seed=10)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    v, vn, r, c = dev(d["v"]), dev(d["vnext"]), dev(d["rew"]), dev(d["cost"])
+    end = dev((d["terminated"] | d["truncated"]).astype(np.uint8))
+    term = dev(d["terminated"].astype(np.uint8))
+    adv = torch.empty_like(v); ret = torch.empty_like(v)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    ts = []
+    for i in range(iters + 3):
+        flush.zero_()
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record(); ops.gae_dual(v, vn, r, c, end, term, 0.99, 0.95, out=(adv, ret)); e.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(s.elapsed_time(e))
+    return float(np.mean(ts)), envs * T
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +248,7 @@ def run_ours(args):
     ach = flops_a / ((ph[0] + ph[1]) * 1e-3) / 1e12
     gms, gn = gae_time(buf, agent.policy)
     gae_bytes = gn * 42
+    gms_l, gn_l = gae_time_large(device)
     out = {
         "metric": "env-steps/sec (collect+update) SafetyCarCircle-v0 PPO-Lag",
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -250,7 +274,11 @@ def run_ours(args):
         "roofline_gae": {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm",
                          "achieved": gae_bytes / (gms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": gae_bytes / (gms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gms,
-                         "bytes_per_transition": 42, "peak_source": how},
+                         "bytes_per_transition": 42, "peak_source": how, "transitions": gn,
+                         "note": "c2-sized collect (25.8 MB): launch + one latency chain per tile dominate",
+                         "large": {"transitions": gn_l, "ms": gms_l,
+                                   "achieved": gn_l * 42 / (gms_l * 1e-3) / 1e9,
+                                   "frac": gn_l * 42 / (gms_l * 1e-3) / 1e9 / pk["hbm_gbs"]}},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:

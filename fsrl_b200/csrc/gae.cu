@@ -62,7 +62,7 @@ struct GaeWorkspace {
 };
 
 template <int C, bool VEC>
-__global__ void __launch_bounds__(GAE_TPB, 2)
+__global__ void __launch_bounds__(GAE_TPB, 3)
 gae_dual_kernel(const float* __restrict__ v, const float* __restrict__ vnext,
                 const float* __restrict__ rew, const float* __restrict__ cost,
                 const uint8_t* __restrict__ end_flag, const uint8_t* __restrict__ terminated,
@@ -76,9 +76,15 @@ gae_dual_kernel(const float* __restrict__ v, const float* __restrict__ vnext,
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
 
+    // persistent CTAs: the grid is one resident wave (or fewer); every CTA keeps claiming tiles in
+    // scan order until the ticket counter runs out, so there is no partial second wave.  Look-back
+    // only ever waits on smaller tickets, which were claimed earlier by CTAs that are running.
+    for (;;) {
+    __syncthreads();                           // s_ticket / s_warp / s_carry of the previous tile are dead
     if (tid == 0) s_ticket = atomicAdd(&ws->ticket, 1u);
     __syncthreads();
     const int ticket = (int)s_ticket;          // scan-order tile index (0 = end of memory)
+    if (ticket >= num_tiles) break;
     const int m = num_tiles - 1 - ticket;      // memory tile index
     // thread t owns scan positions [t*ITEMS, (t+1)*ITEMS) of the tile == memory chunk
     // starting at base, walked backwards
@@ -129,22 +135,21 @@ gae_dual_kernel(const float* __restrict__ v, const float* __restrict__ vnext,
     }
 
     // ---- pass 1: per-thread aggregate with zero carry-in (scan order = j descending) ----
-    double dl[C][GAE_ITEMS];
-    double a[GAE_ITEMS];
+    // delta_j and a_j are recomputed in pass 2 (3 f64 ops each, bit-identical) instead of being kept
+    // in 48 registers: one more resident CTA per SM matters more to this HBM-bound kernel
+    auto delta = [&](int c, int j) {
+        // value_mask (:429): v_next * ~terminated, then delta = rew + v_next*gamma - v (:534)
+        const double vn = ft[j] ? 0.0 : (double)fvn[c][j];
+        return __dsub_rn(__dadd_rn((double)fm[c][j], __dmul_rn(vn, gamma)), (double)fv[c][j]);
+    };
     GaeState agg;
     agg.A = 1.0; agg.Br = 0.0; agg.Bc = 0.0;
 #pragma unroll
     for (int j = GAE_ITEMS - 1; j >= 0; --j) {
-        a[j] = fe[j] ? 0.0 : gl;   // (1.0 - end) * (gamma*lambda): exactly 0 or gl
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            // value_mask (:429): v_next * ~terminated, then delta = rew + v_next*gamma - v (:534)
-            const double vn = ft[j] ? 0.0 : (double)fvn[c][j];
-            dl[c][j] = __dsub_rn(__dadd_rn((double)fm[c][j], __dmul_rn(vn, gamma)), (double)fv[c][j]);
-        }
-        agg.Br = __dadd_rn(dl[0][j], __dmul_rn(a[j], agg.Br));
-        if (C > 1) agg.Bc = __dadd_rn(dl[C - 1][j], __dmul_rn(a[j], agg.Bc));
-        agg.A *= a[j];
+        const double aj = fe[j] ? 0.0 : gl;   // (1.0 - end) * (gamma*lambda): exactly 0 or gl
+        agg.Br = __dadd_rn(delta(0, j), __dmul_rn(aj, agg.Br));
+        if (C > 1) agg.Bc = __dadd_rn(delta(C - 1, j), __dmul_rn(aj, agg.Bc));
+        agg.A *= aj;
     }
 
     // ---- block scan of thread aggregates (inclusive, scan order = tid ascending) ---------
@@ -213,11 +218,12 @@ gae_dual_kernel(const float* __restrict__ v, const float* __restrict__ vnext,
     float oa[C][GAE_ITEMS], orr[C][GAE_ITEMS];
 #pragma unroll
     for (int j = GAE_ITEMS - 1; j >= 0; --j) {
-        gr = __dadd_rn(dl[0][j], __dmul_rn(a[j], gr));
+        const double aj = fe[j] ? 0.0 : gl;
+        gr = __dadd_rn(delta(0, j), __dmul_rn(aj, gr));
         oa[0][j] = (float)gr;
         orr[0][j] = (float)__dadd_rn(gr, (double)fv[0][j]);      // ret = adv + v (:441)
         if (C > 1) {
-            gc = __dadd_rn(dl[C - 1][j], __dmul_rn(a[j], gc));
+            gc = __dadd_rn(delta(C - 1, j), __dmul_rn(aj, gc));
             oa[C - 1][j] = (float)gc;
             orr[C - 1][j] = (float)__dadd_rn(gc, (double)fv[C - 1][j]);
         }
@@ -245,6 +251,7 @@ gae_dual_kernel(const float* __restrict__ v, const float* __restrict__ vnext,
             }
         }
     }
+    }   // next ticket
 }
 
 }  // namespace fsrl
@@ -283,8 +290,10 @@ extern "C" int fsrl_gae_dual(const float* v, const float* vnext, const float* re
                      (!terminated || (reinterpret_cast<uintptr_t>(terminated) & 7u) == 0);
     const double gl = gamma * gae_lambda;
     GaeWorkspace* ws = static_cast<GaeWorkspace*>(workspace);
+    const int wave = 3 * sm_count();                   // __launch_bounds__(GAE_TPB, 3)
+    const int grid = tiles < wave ? tiles : wave;
 #define LAUNCH(CC, VV)                                                                       \
-    gae_dual_kernel<CC, VV><<<tiles, GAE_TPB, 0, s>>>(v, vnext, rew, cost, end_flag, terminated, \
+    gae_dual_kernel<CC, VV><<<grid, GAE_TPB, 0, s>>>(v, vnext, rew, cost, end_flag, terminated, \
                                                      gamma, gl, adv, ret, (long long)N,      \
                                                      (long long)ld, tiles, ws)
     if (C == 2) { if (vec) LAUNCH(2, true); else LAUNCH(2, false); }
