@@ -268,13 +268,17 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"kernel": "ppo_fwd_kernel<256> + ppo_bwd_kernel<256>", "bound": "tensor", "achieved": ach,
                      "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                     "traffic": None, "peak_source": how + " bf16 burst",
+                     "traffic": 3.44e6, "traffic_unit": "DRAM bytes per fwd+bwd launch pair (ncu --set full, "
+                                                        "profiles/r1_ppo_update_ncu_summary.txt): the working set is L2 resident",
+                     "peak_source": how + " bf16 burst",
                      "note": "fp32-faithful 3xTF32 split-operand mma.sync (legacy tensor path, 3 MMAs per fp32 product); flops = algorithmic fwd+bwd of 3 MLPs on a 256-row minibatch; latency-bound (9600 dependent optimiser steps of 256 rows)",
                      "phase_ms": {"fwd": ph[0], "bwd": ph[1], "wgrad": ph[2], "adam": ph[3]}},
         "roofline_gae": {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm",
                          "achieved": gae_bytes / (gms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": gae_bytes / (gms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gms,
                          "bytes_per_transition": 42, "peak_source": how, "transitions": gn,
+                         "traffic": 16.0e6 + 9.8e6, "traffic_unit": "DRAM bytes per launch on the c2 collect: 16.0 MB read "
+                         "(ncu, = algorithmic 26 B/transition) + 9.8 MB of adv/ret written back from L2 after the kernel",
                          "note": "c2-sized collect (25.8 MB): launch + one latency chain per tile dominate",
                          "large": {"transitions": gn_l, "ms": gms_l,
                                    "achieved": gn_l * 42 / (gms_l * 1e-3) / 1e9,
