@@ -987,118 +987,6 @@ __global__ void __launch_bounds__(256) ppo_dp_reduce_kernel(const fsrl_ppo_updat
     if (tid == 0) u.p2p_part[blockIdx.x] = tot;     // no atomics: the Adam kernel sums these in a fixed order
 }
 
-// The same exchange fused with clip_grad_norm_ + Adam in ONE cooperative launch: the summed
-// gradient never touches memory.  Blocks [0, n_plain_blocks) own the parameters outside the W2
-// matrices (compact enumeration, 4 per thread), the rest own 32 x 32 tiles of a W2 (so that the
-// out-major mirror can be written transposed through shared memory).  Phases: signal / wait for the
-// peers -> sum all ranks' buffers in rank order into registers, per-CTA sum g^2 -> grid barrier ->
-// every CTA adds the partials in the same fixed order (rank-identical norm) -> clip + Adam.
-__global__ void __launch_bounds__(256)
-ppo_dp_adam_kernel(const fsrl_ppo_update_t u, unsigned long long id, AdamStep ad, unsigned long long* bar,
-                   unsigned long long bar_target, int slot, int n_plain_blocks) {
-    __shared__ float tile[32][33];
-    __shared__ float red[8];
-    pdl_wait();                       // the local weight gradients are complete
-    pdl_trigger();
-    const int tid = threadIdx.x;
-    if (blockIdx.x == 0 && tid < u.world) {
-        __threadfence_system();
-        unsigned long long* f = u.p2p_flags[tid] + u.p2p_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(id) : "memory");
-    }
-    if (tid < u.world) {
-        const unsigned long long* f = u.p2p_flags[u.p2p_rank] + tid;
-        const long long t0 = clock64();
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-        } while (v < id && clock64() - t0 < P2P_TIMEOUT_CYCLES);
-        if (v < id) *u.p2p_err = 1;
-    }
-    __syncthreads();
-    const int par = (int)(id & 1ULL);
-    const int H = u.H;
-    // ---- which parameters does this thread own? ------------------------------------------------------
-    long long idx[4];
-    bool own[4];
-    int tn = 0, k0 = 0, o0 = 0;
-    const int lx = tid % 32, ly = tid / 32;
-    if ((int)blockIdx.x < n_plain_blocks) {
-        long long c = ((long long)blockIdx.x * 256 + tid) * 4;       // compact index over the non-W2 parameters
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            long long cc = c + q;
-            own[q] = false; idx[q] = 0;
-            for (int n = 0; n < u.n_nets; ++n) {
-                const long long size = ((n + 1 < u.n_nets) ? u.net_off[n + 1] : u.n_params) - u.net_off[n];
-                const long long pre = (long long)u.D * H + H, post = size - pre - (long long)H * H;
-                if (cc < pre) { own[q] = true; idx[q] = u.net_off[n] + cc; break; }
-                cc -= pre;
-                if (cc < post) { own[q] = true; idx[q] = u.net_off[n] + pre + (long long)H * H + cc; break; }
-                cc -= post;
-            }
-        }
-    } else {
-        const int tpn = (H / 32) * (H / 32);
-        const int t = blockIdx.x - n_plain_blocks;
-        tn = t / tpn;
-        const int tt = t % tpn;
-        k0 = (tt / (H / 32)) * 32; o0 = (tt % (H / 32)) * 32;
-        const long long base = u.net_off[tn] + (long long)u.D * H + H;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { own[q] = true; idx[q] = base + (long long)(k0 + ly + 8 * q) * H + o0 + lx; }
-    }
-    // ---- sum over the ranks (rank order), all loads in flight together ---------------------------------
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-        float v[4][FSRL_P2P_MAX_RANKS];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int r = 0; r < FSRL_P2P_MAX_RANKS; ++r) {
-                v[q][r] = 0.f;
-                if (own[q] && r < u.world)
-                    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v[q][r]) : "l"(u.p2p_xg[par][r] + idx[q]));
-            }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int r = 0; r < FSRL_P2P_MAX_RANKS; ++r)
-                if (r < u.world) g[q] += v[q][r];
-    }
-    const float sq = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3];
-    const float tot = block_sum_256(sq, red);
-    if (tid == 0) u.p2p_part[blockIdx.x] = tot;
-    grid_barrier(bar, bar_target);
-    float sp = 0.f;
-    for (int i = tid; i < (int)gridDim.x; i += 256) sp += __ldcg(u.p2p_part + i);
-    const float gs = 1.0f / (float)u.world;                           // average the summed gradients
-    const float nsq = block_sum_256(sp, red) * gs * gs;
-    float scale = gs;
-    if (u.max_grad_norm > 0.f) scale = gs * fminf(u.max_grad_norm / (sqrtf(nsq) + 1e-6f), 1.0f);
-    if (blockIdx.x == 0 && tid == 0 && u.stats && slot >= 0)
-        u.stats[(size_t)slot * FSRL_PPO_STATS + ST_GRADNORM] = sqrtf(nsq);
-    // ---- Adam on the registers ---------------------------------------------------------------------------
-    float pn[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        pn[q] = 0.f;
-        if (own[q]) {
-            float m = u.adam_m[idx[q]], v = u.adam_v[idx[q]];
-            pn[q] = adam_one(u.theta[idx[q]], g[q] * scale, m, v, ad);
-            u.theta[idx[q]] = pn[q]; u.adam_m[idx[q]] = m; u.adam_v[idx[q]] = v;
-        }
-    }
-    if ((int)blockIdx.x >= n_plain_blocks) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tile[ly + 8 * q][lx] = pn[q];
-        __syncthreads();
-        float* mir = u.w2n + (size_t)tn * H * H;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) mir[(size_t)(o0 + ly + 8 * q) * H + k0 + lx] = tile[lx][ly + 8 * q];
-    }
-}
-
 // sum of squares of the (all-reduced) gradient buffer -> *u.norm_sq
 __global__ void __launch_bounds__(1024) grad_norm_kernel(const fsrl_ppo_update_t u) {
     __shared__ float red[32];
@@ -1256,26 +1144,6 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
         fsrl_ppo_update_t ux = u;
         ux.grad = const_cast<float*>(u.p2p_xg[id & 1ULL][u.p2p_rank]);
         FSRL_CUDA(launch_chain(ppo_wgrad_kernel<H>, gB, dim3(WG_TPB), smemW, s, false, ux, mb_off, B));
-        // fused exchange + norm + Adam when the whole grid is co-resident (cooperative launch)
-        long long plain = 0;
-        for (int n = 0; n < u.n_nets; ++n) {
-            const long long size = ((n + 1 < u.n_nets) ? u.net_off[n + 1] : u.n_params) - u.net_off[n];
-            plain += size - (long long)H * H;
-        }
-        const int n_plain_blocks = (int)((plain + 1023) / 1024);
-        const int grid = n_plain_blocks + u.n_nets * (H / 32) * (H / 32);
-        static int dp_fuse = -1, dp_per_sm = 0;
-        if (dp_fuse < 0) {
-            FSRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dp_per_sm, ppo_dp_adam_kernel, 256, 0));
-            dp_fuse = 1;
-        }
-        if (dp_per_sm * sm_count() >= grid && grid <= FSRL_P2P_PARTIALS && u.barrier != nullptr && u.mask == nullptr) {
-            AdamStep ad = {(float)(1.0 - b1), (float)b2, (float)(1.0 - b2), bc2s, (float)u.adam_eps, neg_step};
-            const unsigned long long target = (unsigned long long)(bar_count + 1) * (unsigned long long)grid;
-            FSRL_CUDA(launch_chain(ppo_dp_adam_kernel, dim3(grid), dim3(256), (size_t)0, s, true, u, id, ad, u.barrier,
-                                   target, slot, n_plain_blocks));
-            return FSRL_OK;
-        }
         const unsigned nblk = (unsigned)((u.n_params + 1023) / 1024);
         FSRL_CUDA(launch_chain(ppo_dp_reduce_kernel, dim3(nblk), dim3(256), (size_t)0, s, false, u, id));
     } else {
