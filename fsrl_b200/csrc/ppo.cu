@@ -864,6 +864,8 @@ adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s,
             float neg_step, int slot, int n_plain_blocks) {
     __shared__ float tile[32][33];
     __shared__ float nred[8];
+    pdl_wait();                        // gradients / norm partials of this step are complete
+    pdl_trigger();
     const float gs = (u.world > 1) ? 1.0f / (float)u.world : 1.0f;     // average the summed gradients
     float scale = gs;
     float nsq_raw;
@@ -884,13 +886,19 @@ adam_kernel(const fsrl_ppo_update_t u, float w1, float b2, float w2, float bc2s,
         u.stats[(size_t)slot * FSRL_PPO_STATS + ST_GRADNORM] = sqrtf(nsq);
     const int H = u.H;
     if ((int)blockIdx.x < n_plain_blocks) {
-        // everything except the W2 blocks (they are skipped here by range test)
-        const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-        if (i >= u.n_params) return;
+        // everything except the W2 matrices: compact enumeration (layer 1 + bias, then b2 / layer 3 / extras
+        // of each net), so only ceil(plain / 256) blocks are launched for it
+        long long cc = (long long)blockIdx.x * 256 + threadIdx.x;
+        long long i = -1;
         for (int n = 0; n < u.n_nets; ++n) {
-            const long long w2s = u.net_off[n] + (long long)u.D * H + H;
-            if (i >= w2s && i < w2s + (long long)H * H) return;
+            const long long size = ((n + 1 < u.n_nets) ? u.net_off[n + 1] : u.n_params) - u.net_off[n];
+            const long long pre = (long long)u.D * H + H, post = size - pre - (long long)H * H;
+            if (cc < pre) { i = u.net_off[n] + cc; break; }
+            cc -= pre;
+            if (cc < post) { i = u.net_off[n] + pre + (long long)H * H + cc; break; }
+            cc -= post;
         }
+        if (i < 0) return;
         float m = u.adam_m[i], v = u.adam_v[i];
         const float g = (u.mask && u.mask[i] == 0) ? 0.f : u.grad[i] * scale;
         if (u.mask && u.mask[i] == 0) return;
@@ -1076,6 +1084,12 @@ __global__ void __launch_bounds__(256) ppo_adv_stats_kernel(const fsrl_ppo_updat
 extern "C" int fsrl_allreduce_fused(void* comm, float* buf, long long n, void* stream);
 extern "C" int fsrl_allreduce_f64(void* comm, double* buf, long long n, void* stream);
 
+// blocks of adam_kernel that cover the parameters outside the W2 matrices (compact enumeration)
+static int adam_plain_blocks(const fsrl_ppo_update_t& u, int H) {
+    const long long plain = u.n_params - (long long)u.n_nets * H * H;
+    return (int)((plain + 255) / 256);
+}
+
 // One link of the per-minibatch kernel chain: programmatic dependent launch (see pdl_wait), plus
 // the cooperative attribute for the kernel that contains the grid barrier.
 template <class... KArgs, class... Args>
@@ -1157,11 +1171,10 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
         grad_norm_kernel<<<1, 1024, 0, s>>>(u);
         FSRL_LAUNCH_CHECK();
     }
-    const int n_plain = (int)((u.n_params + 255) / 256);
+    const int n_plain = adam_plain_blocks(u, H);
     const int n_tiles = u.n_nets * (H / 32) * (H / 32);
-    adam_kernel<<<n_plain + n_tiles, 256, 0, s>>>(u, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), bc2s,
-                                                  (float)u.adam_eps, neg_step, slot, n_plain);
-    FSRL_LAUNCH_CHECK();
+    FSRL_CUDA(launch_chain(adam_kernel, dim3(n_plain + n_tiles), dim3(256), (size_t)0, s, false, u, (float)(1.0 - b1),
+                           (float)b2, (float)(1.0 - b2), bc2s, (float)u.adam_eps, neg_step, slot, n_plain));
     return FSRL_OK;
 }
 
@@ -1303,7 +1316,7 @@ static int ppo_time_phases(const fsrl_ppo_update_t& u0, int B, int iters, float*
     const dim3 gB((H / WG_TKT) * NTT + 2 * NTT, u.n_nets);
     const size_t smemW = sizeof(float) * WG_SMEM_FLOATS;
     FSRL_CUDA(cudaFuncSetAttribute(ppo_wgrad_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW));
-    const int n_plain = (int)((u.n_params + 255) / 256);
+    const int n_plain = adam_plain_blocks(u, H);
     const int n_tiles = u.n_nets * (H / 32) * (H / 32);
     FSRL_CUDA(cudaEventRecord(e[0], s));
     for (int i = 0; i < iters; ++i) ppo_fwd_kernel<H><<<gA, MLP_TPB, smemF, s>>>(u, 0, B);
