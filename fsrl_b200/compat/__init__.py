@@ -128,18 +128,7 @@ def install(force: bool = False) -> List[str]:
                       ReplayBufferManager=_data.VectorReplayBuffer, VectorReplayBuffer=_data.VectorReplayBuffer,
                       to_numpy=_data.to_numpy, to_torch_as=_data.to_torch_as)
 
-        class RunningMeanStd:
-            def __init__(self, mean=0.0, std=1.0, clip_max=10.0, epsilon=np.finfo(np.float32).eps.item()):
-                self.mean, self.var, self.count, self.eps, self.clip_max = mean, std, 0, epsilon, clip_max
-
-            def update(self, x):
-                x = np.asarray(x)
-                bm, bv, bc = np.mean(x, axis=0), np.var(x, axis=0), len(x)
-                d = bm - self.mean
-                tot = self.count + bc
-                self.mean = self.mean + d * bc / tot
-                self.var = (self.var * self.count + bv * bc + d ** 2 * self.count * bc / tot) / tot
-                self.count = tot
+        RunningMeanStd = _optim_util.RunningMeanStd
 
         class MovAvg:
             def __init__(self, size=100):

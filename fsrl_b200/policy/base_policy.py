@@ -25,6 +25,7 @@ from ..data.batch import Batch, to_numpy
 from ..nets import Actor, ActorProb, Arena, Critic, slot_from_module, slots_from_module
 from ..spaces import Box, Discrete, MultiBinary, MultiDiscrete
 from ..utils.logger import BaseLogger, DummyLogger
+from ..utils.optim_util import RunningMeanStd
 
 
 class ActorCritic(nn.Module):
@@ -70,9 +71,7 @@ class BasePolicy(ABC, nn.Module):
         assert 0.0 <= gamma <= 1.0, "discount factor should be in [0, 1]."
         self._gamma = gamma
         self._rew_norm = reward_normalization
-        if reward_normalization:
-            raise NotImplementedError("reward_normalization=True (ret_rms) is not on the device path; "
-                                      "every reference config runs with False")
+        self.ret_rms = [RunningMeanStd() for _ in range(self.critics_num)]              # :111
         self._eps = 1e-8
         self._deterministic_eval = deterministic_eval
         self._max_batchsize = max_batchsize
@@ -332,8 +331,20 @@ class BasePolicy(ABC, nn.Module):
             if ends.numel():
                 ve = self.net_forward(1 + i, batch.obs_next, idx=ends).flatten()
                 vnext[i, ends.long()] = ve
-        adv, ret = ops.gae_dual(v, vnext, batch.rew, batch.cost if C > 1 else None, end_flag,
+        v_scan, vnext_scan = v, vnext
+        if self._rew_norm:
+            # un-normalise V(s), V(s') by the running std of the returns (no mean shift, :430-436)
+            scale = torch.tensor([float(np.sqrt(r.var + self._eps)) for r in self.ret_rms],
+                                 dtype=torch.float32, device=dev).view(C, 1)
+            v_scan, vnext_scan = v * scale, vnext * scale
+        adv, ret = ops.gae_dual(v_scan, vnext_scan, batch.rew, batch.cost if C > 1 else None, end_flag,
                                 batch.terminated, self._gamma, gae_lambda)
+        if self._rew_norm:
+            ret = ret / scale                                                           # :442-443
+            r64 = ret.double()
+            means, variances = r64.mean(dim=1).cpu().numpy(), r64.var(dim=1, unbiased=False).cpu().numpy()
+            for i in range(C):                                                          # :444
+                self.ret_rms[i].update_moments(float(means[i]), float(variances[i]), n)
         batch.v, batch.adv, batch.ret = v, adv, ret
         batch.values, batch.rets, batch.advs = v.t(), ret.t(), adv.t()
         return batch

@@ -40,3 +40,28 @@ class LagrangianOptimizer(object):
         self.error_old = params["error_old"]
         self.error_integral = params["error_integral"]
         self.lagrangian = params["lagrangian"]
+
+
+class RunningMeanStd:
+    """Running mean / variance of a data stream (tianshou.utils.RunningMeanStd, the statistic behind
+    ``reward_normalization`` in fsrl/policy/base_policy.py:111,434-444): parallel-variance update
+    of (mean, var, count) per call.  [tianshou 0.5.0 source absent: restated from its documented
+    behaviour, SURVEY.md 2.3]"""
+
+    def __init__(self, mean=0.0, std=1.0, clip_max=10.0, epsilon=float(np.finfo(np.float32).eps)):
+        self.mean, self.var = mean, std
+        self.clip_max = clip_max
+        self.count = 0
+        self.eps = epsilon
+
+    def update_moments(self, batch_mean, batch_var, batch_count) -> None:
+        delta = batch_mean - self.mean
+        total = self.count + batch_count
+        m2 = self.var * self.count + batch_var * batch_count + delta ** 2 * self.count * batch_count / total
+        self.mean = self.mean + delta * batch_count / total
+        self.var = m2 / total
+        self.count = total
+
+    def update(self, x) -> None:
+        x = np.asarray(x)
+        self.update_moments(np.mean(x, axis=0), np.var(x, axis=0), len(x))

@@ -137,3 +137,16 @@ def test_env_registry_and_dims_without_gpu():
                             "SafetyAntCircle-v0": (34, 8, 500), "SafetyPointGoal1Gymnasium-v0": (60, 2, 1000)}.items():
         e = envs.make(task)
         assert e.observation_space.shape == (D,) and e.action_space.shape == (A,) and e.spec.max_episode_steps == T
+
+
+def test_running_mean_std_matches_batch_statistics():
+    """Chunked updates reproduce the moments of the concatenated stream (parallel-variance update)."""
+    from fsrl_b200.utils.optim_util import RunningMeanStd
+    rng = np.random.default_rng(0)
+    xs = [rng.normal(3.0, 2.0, size=n) for n in (1, 7, 300, 4096)]
+    rms = RunningMeanStd()
+    for x in xs:
+        rms.update(x)
+    full = np.concatenate(xs)
+    assert rms.count == len(full)
+    assert rms.mean == pytest.approx(full.mean(), rel=1e-12) and rms.var == pytest.approx(full.var(), rel=1e-10)

@@ -65,7 +65,8 @@ def test_critic_forward_matches_torch():
 
 @pytest.mark.parametrize("hidden,task,lag", [((64, 64), "SafetyCarCircle-v0", 0.7),
                                              ((256, 256), "SafetyCarCircle-v0", 0.0),
-                                             ((128, 128), "SafetyAntCircle-v0", 1.3)])
+                                             ((128, 128), "SafetyAntCircle-v0", 1.3),
+                                             ((512, 512), "SafetyPointGoal1Gymnasium-v0", 0.4)])
 def test_ppo_update_matches_oracle(hidden, task, lag):
     from oracle import ppo as oppo
     E = 4
@@ -158,3 +159,37 @@ def test_kl_early_stop_and_merge_last():
     policy._target_kl = -1.0        # any kl triggers the stop after the first repeat
     policy.learn(batch, batch_size=128, repeat=4)
     assert len(policy.last_stats["loss/kl"]) == 2
+
+
+def test_reward_normalization_matches_oracle():
+    """reward_normalization=True (base_policy.py:430-444): two consecutive process_fn calls -- the second
+    one sees the running return variance left by the first."""
+    from oracle import returns as oret
+    from fsrl_b200.utils.optim_util import RunningMeanStd
+    E = 4
+    policy, venv, buf, col = build_ppo("SafetyCarCircle-v0", hidden=(64, 64), n_env=E, reward_normalization=True)
+    actor, critics = oracle_nets(policy, (64, 64))
+    rms = [RunningMeanStd(), RunningMeanStd()]
+    for it in range(2):
+        col.reset_buffer()
+        col.collect(n_episode=E)
+        idx = buf.sample_indices(0)
+        batch = policy.process_fn(None, buf, idx)
+        b = buffer_to_numpy(buf)
+        sel = idx.cpu().numpy()
+        with torch.no_grad():
+            v = np.stack([c(torch.from_numpy(b["obs"][sel])).flatten().numpy() for c in critics])
+            vn = np.stack([c(torch.from_numpy(b["obs_next"][sel])).flatten().numpy() for c in critics])
+        vals, rets, advs, moments = oret.dual_gae_rew_norm(
+            v, vn, b["rew"][sel], b["cost"][sel], b["terminated"][sel].astype(bool), b["truncated"][sel].astype(bool),
+            np.zeros(len(sel), bool), 0.99, 0.95, [r.var for r in rms])
+        for r, (m, var, cnt) in zip(rms, moments):
+            r.update_moments(m, var, cnt)
+        np.testing.assert_allclose(batch.values.cpu().numpy(), vals, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(batch.advs.cpu().numpy(), advs, rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(batch.rets.cpu().numpy(), rets, rtol=1e-4, atol=2e-5)
+        for i in range(2):
+            assert policy.ret_rms[i].count == rms[i].count
+            assert policy.ret_rms[i].var == pytest.approx(rms[i].var, rel=1e-4)
+            assert policy.ret_rms[i].mean == pytest.approx(rms[i].mean, rel=1e-4, abs=1e-6)
+    assert rms[0].var != 1.0
