@@ -390,8 +390,8 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    for _ in range(args.warmup):
-        cpu_reference(sample_envs=4, cycles=1)
+    for _ in range(args.warmup):                      # untimed warm-up steps (thread pools, allocator) on a small sample
+        cpu_reference(sample_envs=min(32, args.cpu_envs), cycles=1)
     t0 = time.time()
     vals = []
     for _ in range(args.steps):
@@ -418,7 +418,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cpu-envs", type=int, default=32)
+    ap.add_argument("--cpu-envs", type=int, default=512,
+                    help="envs of the bounded CPU sample (512 x 300 transitions ~ 10-15 s on 8 host cores)")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
