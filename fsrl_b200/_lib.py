@@ -11,7 +11,9 @@ import os
 import torch  # noqa: F401  (loads torch's bundled libnccl/cudart before ours resolve the same SONAMEs)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsrl_b200.so")
+# FSRL_B200_LIB selects another build of the same library (A/B runs of kernel variants); the default is
+# the in-tree build
+LIB_PATH = os.environ.get("FSRL_B200_LIB") or os.path.join(_HERE, "libfsrl_b200.so")
 
 FSRL_OK, FSRL_EINVAL, FSRL_ECUDA, FSRL_EWORKSPACE = 0, -1, -2, -3
 

@@ -41,7 +41,7 @@ __device__ long long g_dbg_cta[512];
 #else
 #define DBG_T(i) do { } while (0)
 #define DBG_W(i) do { } while (0)
-#define DBG_CTA(i, v) do { } while (0)
+#define DBG_CTA(i, v) do { (void)(i); } while (0)
 #endif
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
@@ -133,6 +133,8 @@ ppo_fwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     DBG_T(17);
     pdl_wait();                                         // parameters of the previous step are final
     pdl_trigger();
+    // bias of this thread's epilogue columns: requested now, consumed after the GEMM
+    const float4 b2v = __ldg(reinterpret_cast<const float4*>(nv.m.b2 + c0 + (tid % (SLAB_NS / 4)) * 4));
     DBG_T(18);
     if (net == 0 && slab == 0 && blockIdx.x == 0 && tid == 0) *u.norm_sq = 0.f;   // consumed by the previous step's Adam
     slab_load<H>(nv.m.w2t, H, c0, bs);                  // in flight during layer 1
@@ -151,7 +153,7 @@ ppo_fwd_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     __syncthreads();
     DBG_T(21);
     slab_gemm<H>(h1, TT::LDA, bs, bs, [&](int row, int c4, float4 v) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(nv.m.b2 + c0 + c4));
+        const float4 b = b2v;                           // c4 == (tid % 16) * 4 for every element this thread visits
         if (r0 + row < u.bmax)
             *reinterpret_cast<float4*>(nv.s_h2 + (size_t)(r0 + row) * H + c0 + c4) =
                 make_float4(fmaxf(v.x + b.x, 0.f), fmaxf(v.y + b.y, 0.f), fmaxf(v.z + b.z, 0.f), fmaxf(v.w + b.w, 0.f));
@@ -531,8 +533,11 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
         __threadfence();
         atomicAdd(counter, 1ULL);
         unsigned long long v;
+        const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter));
+            // a grid that is not co-resident would spin forever: fail loudly instead of hanging the GPU
+            if (v < target && clock64() - t0 > 20000000000LL) asm volatile("trap;");
         } while (v < target);
         __threadfence();
     }
@@ -839,7 +844,7 @@ ppo_wgrad_kernel(const fsrl_ppo_update_t u, int mb_off, int B) {
     if (threadIdx.x == 0) DBG_CTA(blockIdx.x + gridDim.x * blockIdx.y, clock64() - t0);
 }
 
-// weight gradients + clip_grad_norm_ + Adam in one cooperative launch (single-GPU path)
+// weight gradients + clip_grad_norm_ + Adam in one launch with a grid barrier (single-GPU path)
 template <int H>
 __global__ void __launch_bounds__(WG_TPB)
 ppo_wgrad_adam_kernel(const fsrl_ppo_update_t u, int mb_off, int B, AdamStep ad, unsigned long long* bar,
@@ -1148,7 +1153,12 @@ static int ppo_launch_minibatch(const fsrl_ppo_update_t& u, int mb_off, int B, i
         // single GPU: gradients never leave the registers -- tiles -> norm -> barrier -> clip + Adam
         AdamStep ad = {(float)(1.0 - b1), (float)b2, (float)(1.0 - b2), bc2s, (float)u.adam_eps, neg_step};
         unsigned long long target = (unsigned long long)(bar_count + 1) * gB.x * gB.y;
-        FSRL_CUDA(launch_chain(ppo_wgrad_adam_kernel<H>, gB, dim3(WG_TPB), smemW, s, true, u, mb_off, B, ad, u.barrier,
+        // Ordinary (not cooperative) launch: measured 4.6 % faster per cycle.  The grid barrier is still
+        // safe: fuse_ok guarantees grid <= SMs x CTAs/SM, every CTA of the grid becomes resident without
+        // waiting on anything but the barrier (the preceding bwd CTAs drain unconditionally, the next fwd
+        // CTAs are only scheduled after ALL of these have triggered), and grid_barrier traps after 20 s
+        // instead of spinning forever should that reasoning ever be violated.
+        FSRL_CUDA(launch_chain(ppo_wgrad_adam_kernel<H>, gB, dim3(WG_TPB), smemW, s, false, u, mb_off, B, ad, u.barrier,
                                target, slot));
         return FSRL_OK;
     }
