@@ -46,3 +46,67 @@ def test_collect_stats_and_pid_agree_across_ranks():
     assert l0 == l1 and l0 > 0                       # identical dual variable on both ranks
     assert k0 == k1 == pytest.approx(0.015)
     assert s0 != s1                                  # but independent env / noise streams
+
+
+def _tr_worker(rank, world, port, q):
+    """TrustRegionMixin's data-parallel combiners on CPU tensors over gloo: weighted vectors,
+    global batch sums and global advantage standardisation must equal the single-process result on
+    the union of the ranks' (unequally sized) batches."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fsrl_b200.parallel import DataParallel
+    from fsrl_b200.policy.trust_region import TrustRegionMixin
+
+    class Host(TrustRegionMixin):
+        device = torch.device("cpu")
+
+    h = Host()
+    h._dp = DataParallel(dist, with_nccl=False)
+    rng = np.random.default_rng(5)
+    sizes = [700, 1300]
+    data = [rng.normal(2.0, 3.0, size=n).astype(np.float32) for n in sizes]      # same on both ranks
+    grads = [rng.normal(size=16).astype(np.float32) for _ in sizes]              # per-rank local MEAN gradients
+    n = sizes[rank]
+    n_g = h._dp_begin(n)
+    v = torch.from_numpy(grads[rank].copy())
+    h._gvec(v)                                                                    # -> global-batch mean gradient
+    h._sums = torch.tensor([float(data[rank].sum()), float(n), 0.0, 0.0], dtype=torch.float64)
+    sums = h._gsums()
+    x = torch.from_numpy(data[rank].copy())
+    h._standardize(x, n)
+    h._dp_same_count(3, "minibatch count")                                       # equal counts: no error
+    try:
+        h._dp_same_count(3 + rank, "minibatch count")
+        mismatch_raises = False
+    except RuntimeError:
+        mismatch_raises = True
+    q.put((rank, n_g, v.numpy(), sums, x.numpy(), mismatch_raises))
+    dist.destroy_process_group()
+
+
+def test_trust_region_combiners_equal_union_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 777) % 2000)
+    procs = [ctx.Process(target=_tr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    sizes = [700, 1300]
+    data = [rng.normal(2.0, 3.0, size=n).astype(np.float32) for n in sizes]
+    grads = [rng.normal(size=16).astype(np.float32) for _ in sizes]
+    union = np.concatenate(data).astype(np.float64)
+    want_g = (sizes[0] * grads[0].astype(np.float64) + sizes[1] * grads[1]) / sum(sizes)
+    for rank, n_g, v, sums, x, mismatch_raises in res:
+        assert n_g == 2000
+        np.testing.assert_allclose(v, want_g, rtol=1e-6)
+        assert sums[0] == pytest.approx(union.sum(), rel=1e-6) and sums[1] == 2000
+        want_x = (data[rank] - union.mean()) / union.std(ddof=1)
+        np.testing.assert_allclose(x, want_x, rtol=2e-5, atol=2e-6)
+        assert mismatch_raises
+    np.testing.assert_array_equal(res[0][2], res[1][2])      # identical reduced vector on both ranks
