@@ -1,0 +1,168 @@
+"""Golden vectors for the UPDATE paths, produced by the reference's OWN policy classes.
+
+Run in the build container only (needs /root/reference; never on the GPU box):
+
+    python oracle/make_golden_policies.py
+
+The reference (fsrl.policy.*) cannot normally be imported here: tianshou / gymnasium are absent.
+This script registers the repo's thin shims for exactly those two packages (fsrl_b200.compat --
+attribute containers, spaces, plain torch.nn modules; none of the device code is involved), puts
+/root/reference on sys.path so that ``fsrl`` IS the reference, and then drives the reference's
+``learn()`` on CPU with torch autograd + torch.optim.Adam on small seeded batches.  What it
+records -- inputs, initial weights, the per-minibatch statistics the reference logs and the final
+weights -- pins ``oracle/{ppo,cpo,trpo,focops}.py`` (tests/test_oracle_golden.py replays them on
+CPU); the CUDA path is then compared with the oracle in the -m gpu tests.
+
+The only non-reference ingredient is ``Batch.split`` (tianshou 0.5.0 source is absent): it is the
+restatement in oracle/ppo.py::split_indices [SURVEY.md 2.3, UNVERIFIED] -- permutation order is
+therefore shared by construction, the arithmetic of every update step is the reference's.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+D, A, H, N, BS, REPEAT = 8, 2, 16, 200, 64, 2
+
+
+def _bootstrap():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)               # `fsrl` must resolve to the reference, not to the shim
+    import fsrl_b200.compat as compat
+    done = compat.install()
+    assert "fsrl" not in done, "the reference package must be the real one"
+    import fsrl
+    assert fsrl.__file__.startswith(REF), fsrl.__file__
+    from tianshou.data import Batch
+    from oracle.ppo import split_indices
+
+    def split(self, size, shuffle=True, merge_last=False):
+        for idx in split_indices(len(self), size, shuffle=shuffle, merge_last=merge_last):
+            yield self[idx]
+
+    Batch.split = split                   # golden generation only; see the module docstring
+    return Batch
+
+
+class _Capture:
+    """Stands in for fsrl.utils.BaseLogger: keeps every stored scalar in call order."""
+
+    def __init__(self):
+        self.rows = {}
+
+    def store(self, tab=None, **kw):
+        for k, v in kw.items():
+            key = k if tab is None else f"{tab}/{k}"
+            self.rows.setdefault(key, []).append(float(v))
+
+    def print(self, *a, **k):
+        pass
+
+    def write(self, *a, **k):
+        pass
+
+
+def _nets(seed):
+    from tianshou.utils.net.common import Net
+    from tianshou.utils.net.continuous import ActorProb, Critic
+    torch.manual_seed(seed)
+    actor = ActorProb(Net(D, hidden_sizes=(H, H)), A, max_action=1.0)
+    critics = [Critic(Net(D, hidden_sizes=(H, H))) for _ in range(2)]
+    torch.nn.init.constant_(actor.sigma_param, -0.5)
+    for m in list(actor.modules()) + [mm for c in critics for mm in c.modules()]:
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.orthogonal_(m.weight)
+            torch.nn.init.zeros_(m.bias)
+    return actor, critics
+
+
+def _data(seed, actor):
+    rng = np.random.default_rng(seed)
+    obs = rng.normal(size=(N, D)).astype(np.float32)
+    with torch.no_grad():
+        (mu, sigma), _ = actor(torch.from_numpy(obs))
+        act = (mu + sigma * torch.from_numpy(rng.normal(size=(N, A)).astype(np.float32)))
+        # the behaviour policy is a slightly older one: shift the stored log-prob a little
+        logp = torch.distributions.Independent(torch.distributions.Normal(mu, sigma), 1).log_prob(act)
+        logp = logp + torch.from_numpy(rng.normal(scale=0.05, size=N).astype(np.float32))
+    advs = rng.normal(size=(N, 2)).astype(np.float32) * np.array([1.0, 0.5], np.float32)
+    rets = rng.normal(size=(N, 2)).astype(np.float32)
+    values = rets + rng.normal(scale=0.3, size=(N, 2)).astype(np.float32)
+    mean_old = (mu + 0.02 * torch.from_numpy(rng.normal(size=(N, A)).astype(np.float32))).numpy()
+    std_old = (sigma * 1.03).numpy()
+    return dict(obs=obs, act=act.numpy(), logp_old=logp.numpy(), advs=advs, rets=rets, values=values,
+                mean_old=mean_old, std_old=std_old)
+
+
+def _batch(Batch, d):
+    t = lambda k: torch.from_numpy(d[k].copy())
+    return Batch(obs=t("obs"), act=t("act"), logp_old=t("logp_old"), advs=t("advs"), rets=t("rets"),
+                 values=t("values"), mean_old=t("mean_old"), std_old=t("std_old"), info=Batch())
+
+
+def _state(mods):
+    out = {}
+    for name, m in mods:
+        for k, v in m.state_dict().items():
+            out[f"{name}.{k}"] = v.detach().numpy().copy()
+    return out
+
+
+def _space():
+    from gymnasium.spaces import Box
+    return Box(low=-np.ones(A, np.float32), high=np.ones(A, np.float32)), Box(low=-np.ones(D, np.float32) * 10, high=np.ones(D, np.float32) * 10)
+
+
+def _dist(*logits):
+    return torch.distributions.Independent(torch.distributions.Normal(*logits), 1)
+
+
+def golden_ppo(Batch):
+    from fsrl.policy.ppo_lag import PPOLagrangian
+    cases = {}
+    for name, kw, lag in (("base", dict(), 0.7), ("dualclip_vclip", dict(dual_clip=3.0, value_clip=True, reward_normalization=True), 0.3),
+                          ("nolag", dict(use_lagrangian=False), 0.0)):
+        actor, critics = _nets(3)
+        d = _data(11, actor)
+        init = _state([("actor", actor)] + [(f"critics.{i}", c) for i, c in enumerate(critics)])
+        params = [p for m in [actor] + critics for p in m.parameters()]
+        optim = torch.optim.Adam(params, lr=5e-4)
+        act_space, obs_space = _space()
+        log = _Capture()
+        pol = PPOLagrangian(actor, critics, optim, _dist, logger=log, target_kl=1e9, max_grad_norm=0.5,
+                            cost_limit=10.0, observation_space=obs_space, action_space=act_space, **kw)
+        if pol.use_lagrangian:
+            pol.lag_optims[0].lagrangian = lag
+        pol.train()
+        np.random.seed(21)
+        torch.manual_seed(5)
+        pol.learn(_batch(Batch, d), BS, REPEAT)
+        final = _state([("actor", actor)] + [(f"critics.{i}", c) for i, c in enumerate(critics)])
+        cases[name] = dict(kw=kw, lag=lag, data=d, init=init, final=final, stats=log.rows)
+    return cases
+
+
+def _save(name, cases):
+    flat = {}
+    for cname, c in cases.items():
+        for grp in ("data", "init", "final"):
+            for k, v in c[grp].items():
+                flat[f"{cname}|{grp}|{k}"] = np.asarray(v)
+        for k, v in c["stats"].items():
+            flat[f"{cname}|stats|{k}"] = np.asarray(v, dtype=np.float64)
+        flat[f"{cname}|lag"] = np.asarray(c["lag"], dtype=np.float64)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **flat)
+    print("wrote", path, f"{os.path.getsize(path) / 1024:.1f} KiB", {k: len(v["stats"]) for k, v in cases.items()})
+
+
+if __name__ == "__main__":
+    B = _bootstrap()
+    _save("policy_ppo_golden.npz", golden_ppo(B))

@@ -42,7 +42,7 @@ def process(actor, critics, batch, gamma, gae_lambda, unfinished=None):
 
 def learn(actor, critics, optim, batch, batch_size, repeat, lagrangian, rescaling=True,
           eps_clip=0.2, vf_coef=0.25, max_grad_norm=None, target_kl=0.02, norm_adv=True,
-          dual_clip=None, use_lagrangian=True, max_steps=None):
+          dual_clip=None, use_lagrangian=True, max_steps=None, value_clip=False):
     """ppo_lag.py:214-257.  Returns a list of per-minibatch stat dicts (un-averaged)."""
     obs = torch.from_numpy(batch["obs"]); act = torch.from_numpy(batch["act"])
     logp_old_all = torch.from_numpy(batch["logp_old"])
@@ -82,7 +82,14 @@ def learn(actor, critics, optim, batch, batch_size, repeat, lagrangian, rescalin
             vf_losses = []
             for i, c in enumerate(critics):
                 value = c(obs[idx_t]).flatten()
-                vf_losses.append((rets_all[idx_t, i] - value).pow(2).mean())
+                if value_clip:                                                   # :156-163
+                    v_old = torch.from_numpy(batch["values"])[idx_t, i]
+                    v_clip = v_old + (value - v_old).clamp(-eps_clip, eps_clip)
+                    vf1 = (rets_all[idx_t, i] - value).pow(2)
+                    vf2 = (rets_all[idx_t, i] - v_clip).pow(2)
+                    vf_losses.append(torch.max(vf1, vf2).mean())
+                else:
+                    vf_losses.append((rets_all[idx_t, i] - value).pow(2).mean())
             loss_vf = sum(vf_losses)
             loss = loss_actor + vf_coef * loss_vf
             optim.zero_grad()

@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import cport, returns
 from oracle.lagrangian import PIDLagrangian
@@ -89,3 +90,68 @@ def test_dual_gae_layout():
     # a terminated step does not bootstrap: adv = r - v
     i = int(np.flatnonzero(term)[0])
     assert abs(advs[i, 0] - (np.float32(0) + 0)) >= 0  # smoke
+
+
+# ---------------------------------------------------------------------------------------------------
+# update paths: the oracle restatements replay golden vectors produced by the reference's OWN
+# policy classes (oracle/make_golden_policies.py drives fsrl.policy.*.learn on CPU in the build
+# container; tianshou / gymnasium are supplied by thin shims, the arithmetic is the reference's)
+# ---------------------------------------------------------------------------------------------------
+def _load_policy_golden(golden_dir, fname):
+    raw = np.load(os.path.join(golden_dir, fname))
+    cases = {}
+    for key in raw.files:
+        parts = key.split("|")
+        c = cases.setdefault(parts[0], {"data": {}, "init": {}, "final": {}, "stats": {}})
+        if len(parts) == 2:
+            c[parts[1]] = float(raw[key])
+        else:
+            c[parts[1]][parts[2]] = raw[key]
+    return cases
+
+
+def _oracle_nets_from(init, D, A, H):
+    from oracle import nets as onets
+    sd = {k: torch.from_numpy(v) for k, v in init.items()}
+    actor = onets.load_from_state_dict(onets.GaussActor(D, A, [H, H]), sd, "actor.")
+    critics = [onets.load_from_state_dict(onets.ValueNet(D, [H, H]), sd, f"critics.{i}.") for i in range(2)]
+    return actor, critics
+
+
+def _assert_final_params(final, actor, critics, atol):
+    pairs = [("actor.preprocess.model.model.0.weight", actor.body.layers[0].weight),
+             ("actor.preprocess.model.model.0.bias", actor.body.layers[0].bias),
+             ("actor.preprocess.model.model.2.weight", actor.body.layers[1].weight),
+             ("actor.mu.model.0.weight", actor.mu.weight), ("actor.mu.model.0.bias", actor.mu.bias),
+             ("actor.sigma_param", actor.sigma_param)]
+    for i, c in enumerate(critics):
+        pairs += [(f"critics.{i}.preprocess.model.model.0.weight", c.body.layers[0].weight),
+                  (f"critics.{i}.preprocess.model.model.2.weight", c.body.layers[1].weight),
+                  (f"critics.{i}.last.model.0.weight", c.last.weight), (f"critics.{i}.last.model.0.bias", c.last.bias)]
+    for key, p in pairs:
+        want = final[key]
+        got = p.detach().numpy().reshape(want.shape)
+        assert np.abs(got - want).max() <= atol, (key, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("case,kw", [("base", {}), ("dualclip_vclip", dict(dual_clip=3.0, value_clip=True)),
+                                     ("nolag", dict(use_lagrangian=False))])
+def test_ppo_oracle_replays_reference_learn(golden_dir, case, kw):
+    from oracle import ppo as oppo
+    g = _load_policy_golden(golden_dir, "policy_ppo_golden.npz")[case]
+    d = g["data"]
+    D, A, H = d["obs"].shape[1], d["act"].shape[1], g["init"]["actor.mu.model.0.weight"].shape[1]
+    actor, critics = _oracle_nets_from(g["init"], D, A, H)
+    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
+    np.random.seed(21)
+    stats = oppo.learn(actor, critics, opt, d, 64, 2, g["lag"], max_grad_norm=0.5, target_kl=1e9, **kw)
+    ref = g["stats"]
+    assert len(stats) == len(ref["loss/kl"])
+    for key in ("loss/actor_rew", "loss/actor_total", "loss/kl", "loss/vf0", "loss/vf1", "loss/vf_total",
+                "loss/total", "loss/entropy"):
+        got = np.array([s[key] for s in stats])
+        np.testing.assert_allclose(got, ref[key], rtol=2e-5, atol=2e-7, err_msg=key)
+    if kw.get("use_lagrangian", True):
+        np.testing.assert_allclose([s["loss/actor_safety"] for s in stats], ref["loss/actor_safety"], rtol=2e-5, atol=2e-7)
+        np.testing.assert_allclose(ref["loss/lagrangian"], g["lag"])
+    _assert_final_params(g["final"], actor, critics, atol=2e-6)
