@@ -149,6 +149,88 @@ def golden_ppo(Batch):
     return cases
 
 
+def _crit_optim(critics, lr):
+    return torch.optim.Adam([p for c in critics for p in c.parameters()], lr=lr)
+
+
+def _mods(actor, critics):
+    return [("actor", actor)] + [(f"critics.{i}", c) for i, c in enumerate(critics)]
+
+
+def golden_cpo(Batch):
+    """cpo.py:353-370 on one full batch: cost_limit / ave_cost pairs that reach different dual cases."""
+    from fsrl.policy.cpo import CPO
+    cases = {}
+    for name, cost_limit, ave_cost in (("feasible", 1000.0, 12.0), ("infeasible", 0.0, 35.0), ("tight", 10.0, 10.5)):
+        actor, critics = _nets(4)
+        d = _data(12, actor)
+        for i in range(2):                       # process_fn standardises the advantages (:127-131)
+            a = d["advs"][:, i]
+            d["advs"][:, i] = (a - a.mean()) / a.std(ddof=1)
+        init = _state(_mods(actor, critics))
+        act_space, obs_space = _space()
+        log = _Capture()
+        pol = CPO(actor, critics, _crit_optim(critics, 1e-3), _dist, logger=log, target_kl=0.01, max_backtracks=10,
+                  optim_critic_iters=3, l2_reg=0.001, cost_limit=cost_limit, observation_space=obs_space,
+                  action_space=act_space)
+        pol.pre_update_fn(stats_train={"cost": ave_cost})
+        pol.train()
+        np.random.seed(22)
+        torch.manual_seed(6)
+        pol.learn(_batch(Batch, d), 99999, 2)
+        cases[name] = dict(kw=dict(cost_limit=cost_limit, ave_cost=ave_cost), lag=0.0, data=d, init=init,
+                           final=_state(_mods(actor, critics)), stats=log.rows,
+                           extra=dict(cost_limit=cost_limit, ave_cost=ave_cost))
+    return cases
+
+
+def golden_trpo(Batch):
+    from fsrl.policy.trpo_lag import TRPOLagrangian
+    cases = {}
+    for name, lag in (("lag06", 0.6), ("lag0", 0.0)):
+        actor, critics = _nets(5)
+        d = _data(13, actor)
+        for i in range(2):
+            a = d["advs"][:, i]
+            d["advs"][:, i] = (a - a.mean()) / a.std(ddof=1)
+        init = _state(_mods(actor, critics))
+        act_space, obs_space = _space()
+        log = _Capture()
+        pol = TRPOLagrangian(actor, critics, _crit_optim(critics, 5e-4), _dist, logger=log, target_kl=0.001,
+                             optim_critic_iters=3, cost_limit=10.0, observation_space=obs_space,
+                             action_space=act_space)
+        pol.lag_optims[0].lagrangian = lag
+        pol.train()
+        np.random.seed(23)
+        torch.manual_seed(7)
+        pol.learn(_batch(Batch, d), 99999, 2)
+        cases[name] = dict(kw={}, lag=lag, data=d, init=init, final=_state(_mods(actor, critics)), stats=log.rows)
+    return cases
+
+
+def golden_focops(Batch):
+    from fsrl.policy.focops import FOCOPS
+    cases = {}
+    for name, eta, ave_cost in (("eta02", 0.02, 31.5), ("eta_tiny", 1e-4, 4.0)):
+        actor, critics = _nets(6)
+        d = _data(14, actor)
+        init = _state(_mods(actor, critics))
+        act_space, obs_space = _space()
+        log = _Capture()
+        nu = (2.0, 1e-2, torch.zeros(1))
+        pol = FOCOPS(actor, critics, torch.optim.Adam(actor.parameters(), lr=5e-4), _crit_optim(critics, 1e-3), _dist,
+                     logger=log, cost_limit=10.0, nu=nu, l2_reg=1e-3, delta=1e9, eta=eta, tem_lambda=0.95,
+                     max_grad_norm=0.5, observation_space=obs_space, action_space=act_space)
+        pol.pre_update_fn(stats_train={"cost": ave_cost})
+        pol.train()
+        np.random.seed(24)
+        torch.manual_seed(8)
+        pol.learn(_batch(Batch, d), BS, REPEAT)
+        cases[name] = dict(kw={}, lag=0.0, data=d, init=init, final=_state(_mods(actor, critics)), stats=log.rows,
+                           extra=dict(eta=eta, ave_cost=ave_cost))
+    return cases
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -158,6 +240,8 @@ def _save(name, cases):
         for k, v in c["stats"].items():
             flat[f"{cname}|stats|{k}"] = np.asarray(v, dtype=np.float64)
         flat[f"{cname}|lag"] = np.asarray(c["lag"], dtype=np.float64)
+        for k, v in c.get("extra", {}).items():
+            flat[f"{cname}|{k}"] = np.asarray(v, dtype=np.float64)
     path = os.path.join(OUT, name)
     np.savez_compressed(path, **flat)
     print("wrote", path, f"{os.path.getsize(path) / 1024:.1f} KiB", {k: len(v["stats"]) for k, v in cases.items()})
@@ -166,3 +250,6 @@ def _save(name, cases):
 if __name__ == "__main__":
     B = _bootstrap()
     _save("policy_ppo_golden.npz", golden_ppo(B))
+    _save("policy_cpo_golden.npz", golden_cpo(B))
+    _save("policy_trpo_golden.npz", golden_trpo(B))
+    _save("policy_focops_golden.npz", golden_focops(B))

@@ -155,3 +155,68 @@ def test_ppo_oracle_replays_reference_learn(golden_dir, case, kw):
         np.testing.assert_allclose([s["loss/actor_safety"] for s in stats], ref["loss/actor_safety"], rtol=2e-5, atol=2e-7)
         np.testing.assert_allclose(ref["loss/lagrangian"], g["lag"])
     _assert_final_params(g["final"], actor, critics, atol=2e-6)
+
+
+def _cmp_stats(stats, ref, keys, rtol, atol):
+    for key in keys:
+        assert key in ref, (key, sorted(ref))
+        got = np.array([float(s[key]) for s in stats])
+        want = np.asarray(ref[key])
+        assert len(got) == len(want), (key, len(got), len(want))
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=key)
+
+
+@pytest.mark.parametrize("case", ["feasible", "infeasible", "tight"])
+def test_cpo_oracle_replays_reference_learn(golden_dir, case):
+    """cpo.py:147-370 (critic regression, CG, dual case analysis, line search) run by the reference itself."""
+    from oracle import cpo as ocpo
+    g = _load_policy_golden(golden_dir, "policy_cpo_golden.npz")[case]
+    d = g["data"]
+    D, A, H = d["obs"].shape[1], d["act"].shape[1], g["init"]["actor.mu.model.0.weight"].shape[1]
+    actor, critics = _oracle_nets_from(g["init"], D, A, H)
+    opt = torch.optim.Adam([p for c in critics for p in c.parameters()], lr=1e-3)
+    np.random.seed(22)
+    stats = ocpo.learn(actor, critics, opt, d, 99999, 2, g["ave_cost"], g["cost_limit"], optim_critic_iters=3,
+                       l2_reg=0.001, delta=0.01, max_backtracks=10)
+    ref = g["stats"]
+    assert [int(s["loss/optim_case"]) for s in stats] == [int(x) for x in ref["loss/optim_case"]]
+    _cmp_stats(stats, ref, ("loss/kl", "loss/entropy", "loss/rew_loss", "loss/cost_loss", "loss/vf0", "loss/vf1",
+                            "loss/vf_total", "loss/step_size"), rtol=2e-3, atol=2e-6)
+    _cmp_stats(stats, ref, ("loss/optim_Q", "loss/optim_R", "loss/optim_S", "loss/optim_lam", "loss/optim_nu"),
+               rtol=5e-3, atol=1e-5)
+    _assert_final_params(g["final"], actor, critics, atol=5e-5)
+
+
+@pytest.mark.parametrize("case", ["lag06", "lag0"])
+def test_trpo_oracle_replays_reference_learn(golden_dir, case):
+    from oracle import trpo as otrpo
+    g = _load_policy_golden(golden_dir, "policy_trpo_golden.npz")[case]
+    d = g["data"]
+    D, A, H = d["obs"].shape[1], d["act"].shape[1], g["init"]["actor.mu.model.0.weight"].shape[1]
+    actor, critics = _oracle_nets_from(g["init"], D, A, H)
+    opt = torch.optim.Adam([p for c in critics for p in c.parameters()], lr=5e-4)
+    np.random.seed(23)
+    stats = otrpo.learn(actor, critics, opt, d, 99999, 2, g["lag"], optim_critic_iters=3, delta=0.001)
+    ref = g["stats"]
+    _cmp_stats(stats, ref, ("loss/actor_rew", "loss/actor_total", "loss/kl", "loss/step_size", "loss/vf0", "loss/vf1"),
+               rtol=2e-3, atol=2e-6)
+    _assert_final_params(g["final"], actor, critics, atol=5e-5)
+
+
+@pytest.mark.parametrize("case", ["eta02", "eta_tiny"])
+def test_focops_oracle_replays_reference_learn(golden_dir, case):
+    from oracle import focops as ofoc
+    g = _load_policy_golden(golden_dir, "policy_focops_golden.npz")[case]
+    d = g["data"]
+    D, A, H = d["obs"].shape[1], d["act"].shape[1], g["init"]["actor.mu.model.0.weight"].shape[1]
+    actor, critics = _oracle_nets_from(g["init"], D, A, H)
+    aopt = torch.optim.Adam(actor.parameters(), lr=5e-4)
+    copt = torch.optim.Adam([p for c in critics for p in c.parameters()], lr=1e-3)
+    nu, loss_nu = ofoc.nu_step(0.0, 1e-2, 2.0, 10.0, g["ave_cost"])
+    ref = g["stats"]
+    assert ref["loss/nu_value"][0] == pytest.approx(nu, abs=1e-7) and ref["loss/nu_loss"][0] == pytest.approx(loss_nu)
+    np.random.seed(24)
+    stats = ofoc.learn(actor, critics, aopt, copt, d, 64, 2, nu, eta=g["eta"], delta=1e9)
+    _cmp_stats(stats, ref, ("loss/actor_loss", "loss/kl", "loss/entropy", "loss/vf0", "loss/vf1", "loss/vf_total"),
+               rtol=2e-5, atol=2e-7)
+    _assert_final_params(g["final"], actor, critics, atol=2e-6)
