@@ -26,8 +26,10 @@ class MLP(nn.Module):
     """[Linear -> ReLU] x len(hidden) then Linear(out) iff out > 0."""
 
     def __init__(self, input_dim: int, output_dim: int = 0, hidden_sizes: Sequence[int] = (),
-                 device=None):
+                 device=None, linear_layer=nn.Linear, flatten_input: bool = True, **_):
         super().__init__()
+        if linear_layer is not nn.Linear:
+            raise NotImplementedError("only nn.Linear layers map onto the device engine")
         dims = [int(input_dim)] + [int(h) for h in hidden_sizes]
         layers: List[nn.Module] = []
         for i, o in zip(dims[:-1], dims[1:]):

@@ -12,10 +12,19 @@ Parity pinning
   reference's *own* code: ``oracle/make_golden.py`` AST-extracts / imports them from
   ``/root/reference`` (read-only, this container only) and writes the fixtures under
   ``tests/golden/``; ``tests/test_oracle_golden.py`` replays them.
-* Everything that needs ``tianshou`` / ``gymnasium`` / ``pybullet`` (absent, no network)
-  is a restatement that follows the cited reference lines; for those pieces parity is
-  **unpinned** by executable reference code (the reference has no numeric tests,
-  SURVEY.md F7) and is anchored on the reference's call sites only.
+* The update paths -- ``PPOLagrangian / CPO / TRPOLagrangian / FOCOPS / SACLagrangian /
+  DDPGLagrangian.learn`` -- are pinned against the reference's own classes as well:
+  ``oracle/make_golden_policies.py`` (this container only) registers thin ``tianshou`` /
+  ``gymnasium`` shims (attribute containers, spaces, plain ``torch.nn`` modules), imports the REAL
+  ``fsrl.policy.*`` from ``/root/reference`` and drives ``learn()`` on CPU on seeded batches;
+  the logged per-step statistics and final weights are the fixtures
+  ``tests/golden/policy_*_golden.npz`` that ``oracle/{ppo,cpo,trpo,focops,offpolicy}.py`` must
+  reproduce (CPO: dual cases 0-3; PPO: dual clip + value clip; SAC: auto / fixed alpha with the
+  reference's own reparameterisation noise recorded).
+* Still **unpinned** by executable reference code (``tianshou`` 0.5.0 itself is absent, no
+  network): ``Batch.split`` ordering, ``VectorReplayBuffer`` index semantics and the collector /
+  ``compute_*_returns`` glue around the pinned numba kernels -- restated from SURVEY.md 2.3 /
+  Appendix C and anchored on the reference's call sites.
 * The environment dynamics (pybullet / mujoco) cannot be reproduced at all; the device
   env is *our* documented model and ``oracle/envs.py`` is its CPU twin.
 """

@@ -161,7 +161,8 @@ def golden_cpo(Batch):
     """cpo.py:353-370 on one full batch: cost_limit / ave_cost pairs that reach different dual cases."""
     from fsrl.policy.cpo import CPO
     cases = {}
-    for name, cost_limit, ave_cost in (("feasible", 1000.0, 12.0), ("infeasible", 0.0, 35.0), ("tight", 10.0, 10.5)):
+    for name, cost_limit, ave_cost in (("feasible", 1000.0, 12.0), ("infeasible", 0.0, 35.0), ("case2", 10.0, 9.99),
+                                       ("case1_then_2", 10.0, 10.05), ("case0_then_1", 10.0, 10.1)):
         actor, critics = _nets(4)
         d = _data(12, actor)
         for i in range(2):                       # process_fn standardises the advantages (:127-131)
@@ -231,6 +232,117 @@ def golden_focops(Batch):
     return cases
 
 
+class _NoiseTape:
+    """Records every standard-normal draw torch.distributions makes (Normal.rsample), so that the
+    oracle replay injects exactly the reference's reparameterisation noise."""
+
+    def __init__(self):
+        import torch.distributions.normal as tn
+        self._tn, self._orig, self.draws = tn, tn._standard_normal, []
+
+    def __enter__(self):
+        def tapped(shape, dtype, device):
+            e = self._orig(shape, dtype=dtype, device=device)
+            self.draws.append(e.detach().numpy().copy())
+            return e
+        self._tn._standard_normal = tapped
+        return self
+
+    def __exit__(self, *a):
+        self._tn._standard_normal = self._orig
+
+
+def _q_nets(seed, double):
+    from tianshou.utils.net.common import Net
+    from tianshou.utils.net.continuous import Actor, ActorProb, Critic
+    from fsrl.utils.net.continuous import DoubleCritic
+    torch.manual_seed(seed)
+    if double:
+        actor = ActorProb(Net(D, hidden_sizes=(H, H)), A, max_action=1.0, unbounded=True, conditioned_sigma=True)
+        critics = [DoubleCritic(Net(D, A, hidden_sizes=(H, H), concat=True), Net(D, A, hidden_sizes=(H, H), concat=True))
+                   for _ in range(2)]
+    else:
+        actor = Actor(Net(D, hidden_sizes=(H, H)), A, max_action=1.0)
+        critics = [Critic(Net(D, A, hidden_sizes=(H, H), concat=True)) for _ in range(2)]
+    for m in list(actor.modules()) + [mm for c in critics for mm in c.modules()]:
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.orthogonal_(m.weight)
+            torch.nn.init.zeros_(m.bias)
+    return actor, critics
+
+
+def _off_data(seed):
+    rng = np.random.default_rng(seed)
+    return dict(obs=rng.normal(size=(BS, D)).astype(np.float32),
+                act=np.tanh(rng.normal(size=(BS, A))).astype(np.float32),
+                rets=rng.normal(size=(BS, 2)).astype(np.float32) * np.array([2.0, 1.0], np.float32))
+
+
+def golden_sac(Batch):
+    """sac_lag.py:185-269: three consecutive learn() calls on given n-step targets (`rets`)."""
+    from fsrl.policy.sac_lag import SACLagrangian
+    cases = {}
+    for name, auto_alpha, lag in (("auto_alpha", True, 0.8), ("fixed_alpha", False, 0.0)):
+        actor, critics = _q_nets(7, True)
+        init = _state(_mods(actor, critics))
+        if auto_alpha:
+            log_alpha = torch.zeros(1, requires_grad=True)
+            alpha = (-float(A), log_alpha, torch.optim.Adam([log_alpha], lr=3e-4))
+        else:
+            alpha = 0.2
+        act_space, obs_space = _space()
+        log = _Capture()
+        pol = SACLagrangian(actor, critics, torch.optim.Adam(actor.parameters(), lr=5e-4),
+                            torch.optim.Adam(torch.nn.ModuleList(critics).parameters(), lr=1e-3), logger=log,
+                            alpha=alpha, tau=0.05, gamma=0.97, n_step=2, cost_limit=10.0,
+                            observation_space=obs_space, action_space=act_space)
+        pol.lag_optims[0].lagrangian = lag
+        pol.train()
+        torch.manual_seed(9)
+        data, eps = {}, []
+        for k in range(3):
+            d = _off_data(30 + k)
+            with _NoiseTape() as tape:
+                pol.learn(Batch(obs=torch.from_numpy(d["obs"]), act=torch.from_numpy(d["act"]),
+                                rets=torch.from_numpy(d["rets"]), info=Batch()))
+            assert len(tape.draws) == 1
+            for kk, v in d.items():
+                data[f"{kk}{k}"] = v
+            data[f"eps{k}"] = tape.draws[0]
+        final = _state(_mods(actor, critics) + [(f"critics_old.{i}", c) for i, c in enumerate(pol.critics_old)])
+        cases[name] = dict(kw={}, lag=lag, data=data, init=init, final=final, stats=log.rows,
+                           extra=dict(auto_alpha=float(auto_alpha)))
+    return cases
+
+
+def golden_ddpg(Batch):
+    """ddpg_lag.py:165-223: three consecutive learn() calls on given n-step targets."""
+    from fsrl.policy.ddpg_lag import DDPGLagrangian
+    cases = {}
+    for name, lag in (("lag05", 0.5), ("lag0", 0.0)):
+        actor, critics = _q_nets(8, False)
+        init = _state(_mods(actor, critics))
+        act_space, obs_space = _space()
+        log = _Capture()
+        pol = DDPGLagrangian(actor, critics, torch.optim.Adam(actor.parameters(), lr=5e-4),
+                             torch.optim.Adam(torch.nn.ModuleList(critics).parameters(), lr=1e-3), logger=log,
+                             tau=0.05, gamma=0.97, n_step=2, cost_limit=10.0, observation_space=obs_space,
+                             action_space=act_space)
+        pol.lag_optims[0].lagrangian = lag
+        pol.train()
+        data = {}
+        for k in range(3):
+            d = _off_data(40 + k)
+            pol.learn(Batch(obs=torch.from_numpy(d["obs"]), act=torch.from_numpy(d["act"]),
+                            rets=torch.from_numpy(d["rets"]), info=Batch()))
+            for kk, v in d.items():
+                data[f"{kk}{k}"] = v
+        final = _state(_mods(actor, critics) + [("actor_old", pol.actor_old)] +
+                       [(f"critics_old.{i}", c) for i, c in enumerate(pol.critics_old)])
+        cases[name] = dict(kw={}, lag=lag, data=data, init=init, final=final, stats=log.rows)
+    return cases
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -253,3 +365,5 @@ if __name__ == "__main__":
     _save("policy_cpo_golden.npz", golden_cpo(B))
     _save("policy_trpo_golden.npz", golden_trpo(B))
     _save("policy_focops_golden.npz", golden_focops(B))
+    _save("policy_sac_golden.npz", golden_sac(B))
+    _save("policy_ddpg_golden.npz", golden_ddpg(B))

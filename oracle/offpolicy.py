@@ -64,24 +64,12 @@ def sac_forward(actor, obs, eps, deterministic=False):
     return sq, log_prob
 
 
-def sac_step(actor, critics, critics_old, actor_opt, critic_opt, buf, idx, eps_next, eps_cur, *, alpha,
-             gamma, n_step, tau, lagrangian, rescaling=True, use_lagrangian=True, auto_alpha=None):
-    """One SACLagrangian.update: critics = list of (q1, q2) module pairs per return stream."""
+def sac_update(actor, critics, critics_old, actor_opt, critic_opt, obs, act, rets, eps_cur, *, alpha, tau,
+               lagrangian, rescaling=True, use_lagrangian=True, auto_alpha=None):
+    """SACLagrangian.learn (sac_lag.py:260-269) on a batch whose n-step targets `rets` [B, C] are given:
+    critics_loss (:185-210), policy_loss (:212-258, reparameterisation noise eps_cur), sync_weight (:132-134)."""
     C = len(critics)
-    with torch.no_grad():
-        # process_fn -> _target_q at the n-step terminal indices (:136-145)
-        _, terminal = nstep_targets(buf, idx, [np.zeros(len(idx))] * C, gamma, n_step)
-        obs_next = torch.from_numpy(buf.obs_next[terminal])
-        a_next, lp_next = sac_forward(actor, obs_next, eps_next)
-        tq = []
-        for i in range(C):
-            q = torch.min(critics_old[i][0](obs_next, a_next), critics_old[i][1](obs_next, a_next))
-            tq.append((q - alpha * lp_next).numpy())
-    rets, _ = nstep_targets(buf, idx, tq, gamma, n_step)
-    rets = torch.from_numpy(rets)
-    obs = torch.from_numpy(buf.obs[idx]); act = torch.from_numpy(buf.act[idx])
     stats = {}
-    # critics_loss (:185-210)
     loss_c = 0
     for i in range(C):
         li = 0
@@ -92,7 +80,6 @@ def sac_step(actor, critics, critics_old, actor_opt, critic_opt, buf, idx, eps_n
         stats[f"loss/q{i}"] = float(li)
     critic_opt.zero_grad(); loss_c.backward(); critic_opt.step()
     stats["loss/q_total"] = float(loss_c)
-    # policy_loss (:212-258)
     a, lp = sac_forward(actor, obs, eps_cur)
     q = torch.min(critics[0][0](obs, a), critics[0][1](obs, a)).flatten()
     loss_rew = (alpha * lp.flatten() - q).mean()
@@ -113,7 +100,6 @@ def sac_step(actor, critics, critics_old, actor_opt, critic_opt, buf, idx, eps_n
         alpha_opt.zero_grad(); alpha_loss.backward(); alpha_opt.step()
         new_alpha = float(log_alpha.detach().exp())
         stats["loss/alpha_loss"] = float(alpha_loss); stats["loss/alpha_value"] = new_alpha
-    # sync_weight (:132-134)
     with torch.no_grad():
         for i in range(C):
             for j in range(2):
@@ -122,17 +108,31 @@ def sac_step(actor, critics, critics_old, actor_opt, critic_opt, buf, idx, eps_n
     return stats, new_alpha
 
 
-def ddpg_step(actor, actor_old, critics, critics_old, actor_opt, critic_opt, buf, idx, *, gamma, n_step,
-              tau, lagrangian, rescaling=True, use_lagrangian=True):
+def sac_step(actor, critics, critics_old, actor_opt, critic_opt, buf, idx, eps_next, eps_cur, *, alpha,
+             gamma, n_step, tau, lagrangian, rescaling=True, use_lagrangian=True, auto_alpha=None):
+    """One SACLagrangian.update: critics = list of (q1, q2) module pairs per return stream."""
     C = len(critics)
     with torch.no_grad():
+        # process_fn -> _target_q at the n-step terminal indices (:136-145)
         _, terminal = nstep_targets(buf, idx, [np.zeros(len(idx))] * C, gamma, n_step)
         obs_next = torch.from_numpy(buf.obs_next[terminal])
-        a_next = actor_old(obs_next)
-        tq = [critics_old[i](obs_next, a_next).numpy() for i in range(C)]
+        a_next, lp_next = sac_forward(actor, obs_next, eps_next)
+        tq = []
+        for i in range(C):
+            q = torch.min(critics_old[i][0](obs_next, a_next), critics_old[i][1](obs_next, a_next))
+            tq.append((q - alpha * lp_next).numpy())
     rets, _ = nstep_targets(buf, idx, tq, gamma, n_step)
     rets = torch.from_numpy(rets)
     obs = torch.from_numpy(buf.obs[idx]); act = torch.from_numpy(buf.act[idx])
+    return sac_update(actor, critics, critics_old, actor_opt, critic_opt, obs, act, rets, eps_cur, alpha=alpha, tau=tau,
+                      lagrangian=lagrangian, rescaling=rescaling, use_lagrangian=use_lagrangian, auto_alpha=auto_alpha)
+
+
+def ddpg_update(actor, actor_old, critics, critics_old, actor_opt, critic_opt, obs, act, rets, *, tau, lagrangian,
+                rescaling=True, use_lagrangian=True):
+    """DDPGLagrangian.learn (ddpg_lag.py:215-223) on a batch with given n-step targets `rets` [B, C]:
+    critics_loss (:165-189), policy_loss (:191-213), sync_weight (:120-123)."""
+    C = len(critics)
     stats = {}
     loss_c = 0
     for i in range(C):
@@ -141,6 +141,7 @@ def ddpg_step(actor, actor_old, critics, critics_old, actor_opt, critic_opt, buf
         loss_c = loss_c + li
         stats[f"loss/q{i}"] = float(li)
     critic_opt.zero_grad(); loss_c.backward(); critic_opt.step()
+    stats["loss/q_total"] = float(loss_c)
     a = actor(obs)
     loss_rew = -critics[0](obs, a).mean()
     loss_saf = torch.zeros(())
@@ -158,3 +159,18 @@ def ddpg_step(actor, actor_old, critics, critics_old, actor_opt, critic_opt, buf
             for tp, sp in zip(critics_old[i].parameters(), critics[i].parameters()):
                 tp.copy_(tau * sp + (1 - tau) * tp)
     return stats
+
+
+def ddpg_step(actor, actor_old, critics, critics_old, actor_opt, critic_opt, buf, idx, *, gamma, n_step,
+              tau, lagrangian, rescaling=True, use_lagrangian=True):
+    C = len(critics)
+    with torch.no_grad():
+        _, terminal = nstep_targets(buf, idx, [np.zeros(len(idx))] * C, gamma, n_step)
+        obs_next = torch.from_numpy(buf.obs_next[terminal])
+        a_next = actor_old(obs_next)
+        tq = [critics_old[i](obs_next, a_next).numpy() for i in range(C)]
+    rets, _ = nstep_targets(buf, idx, tq, gamma, n_step)
+    rets = torch.from_numpy(rets)
+    obs = torch.from_numpy(buf.obs[idx]); act = torch.from_numpy(buf.act[idx])
+    return ddpg_update(actor, actor_old, critics, critics_old, actor_opt, critic_opt, obs, act, rets, tau=tau,
+                       lagrangian=lagrangian, rescaling=rescaling, use_lagrangian=use_lagrangian)

@@ -150,3 +150,58 @@ def test_running_mean_std_matches_batch_statistics():
     full = np.concatenate(xs)
     assert rms.count == len(full)
     assert rms.mean == pytest.approx(full.mean(), rel=1e-12) and rms.var == pytest.approx(full.var(), rel=1e-10)
+
+
+def test_oracle_offpolicy_step_equals_targets_plus_update():
+    """oracle glue check (CPU): sac_step / ddpg_step == n-step targets from the buffer followed by
+    sac_update / ddpg_update (the halves pinned separately: nstep_return by the reference's numba
+    function, the updates by the reference's own learn())."""
+    import copy
+    from oracle import nets as onets, offpolicy as ooff
+    from oracle.collector import OracleBuffer
+    rng = np.random.default_rng(2)
+    D, A, H, E, T = 5, 2, 8, 3, 12
+    buf = OracleBuffer(E * T, E, D, A)
+    for t in range(T):
+        ids = np.arange(E)
+        buf.add(ids, rng.normal(size=(E, D)).astype(np.float32), np.tanh(rng.normal(size=(E, A))).astype(np.float32),
+                rng.normal(size=E).astype(np.float32), (rng.random(E) < 0.2).astype(np.float32), np.zeros(E, np.float32),
+                rng.random(E) < 0.1, np.full(E, t == T - 1), rng.normal(size=(E, D)).astype(np.float32))
+    idx = rng.integers(0, E * T, size=16).astype(np.int64)
+    torch.manual_seed(0)
+    actor = onets.GaussActor(D, A, [H, H], unbounded=True, conditioned_sigma=True)
+    crit = [[onets.ValueNet(D + A, [H, H]) for _ in range(2)] for _ in range(2)]
+    crit_old = copy.deepcopy(crit)
+    eps_n, eps_c = torch.randn(16, A), torch.randn(16, A)
+
+    def run(step_fn):
+        a, c, co = copy.deepcopy(actor), copy.deepcopy(crit), copy.deepcopy(crit_old)
+        ao = torch.optim.Adam(a.parameters(), lr=1e-3)
+        cop = torch.optim.Adam([p for pair in c for q in pair for p in q.parameters()], lr=1e-3)
+        return step_fn(a, c, co, ao, cop), a
+
+    (st1, _), a1 = run(lambda a, c, co, ao, cop: ooff.sac_step(a, c, co, ao, cop, buf, idx, eps_n, eps_c, alpha=0.2, gamma=0.97,
+                                                                n_step=2, tau=0.05, lagrangian=0.4))
+
+    def manual(a, c, co, ao, cop):
+        with torch.no_grad():
+            _, terminal = ooff.nstep_targets(buf, idx, [np.zeros(16)] * 2, 0.97, 2)
+            on = torch.from_numpy(buf.obs_next[terminal])
+            an, lpn = ooff.sac_forward(a, on, eps_n)
+            tq = [(torch.min(co[i][0](on, an), co[i][1](on, an)) - 0.2 * lpn).numpy() for i in range(2)]
+        rets, _ = ooff.nstep_targets(buf, idx, tq, 0.97, 2)
+        return ooff.sac_update(a, c, co, ao, cop, torch.from_numpy(buf.obs[idx]), torch.from_numpy(buf.act[idx]),
+                               torch.from_numpy(rets), eps_c, alpha=0.2, tau=0.05, lagrangian=0.4)
+
+    (st2, _), a2 = run(manual)
+    assert st1 == st2
+    for p, q in zip(a1.parameters(), a2.parameters()):
+        assert torch.equal(p, q)
+    # DDPG
+    dact = onets.DetActor(D, A, [H, H])
+    dcrit = [onets.ValueNet(D + A, [H, H]) for _ in range(2)]
+    a, ao_, c, co = copy.deepcopy(dact), copy.deepcopy(dact), copy.deepcopy(dcrit), copy.deepcopy(dcrit)
+    st = ooff.ddpg_step(a, ao_, c, co, torch.optim.Adam(a.parameters(), lr=1e-3),
+                        torch.optim.Adam([p for q in c for p in q.parameters()], lr=1e-3), buf, idx, gamma=0.97, n_step=2,
+                        tau=0.05, lagrangian=0.4)
+    assert np.isfinite(list(st.values())).all() and {"loss/q0", "loss/q1", "loss/actor_total"} <= set(st)

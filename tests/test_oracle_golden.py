@@ -166,8 +166,9 @@ def _cmp_stats(stats, ref, keys, rtol, atol):
         np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=key)
 
 
-@pytest.mark.parametrize("case", ["feasible", "infeasible", "tight"])
-def test_cpo_oracle_replays_reference_learn(golden_dir, case):
+@pytest.mark.parametrize("case,dual_cases", [("feasible", [3, 3]), ("infeasible", [0, 0]), ("case2", [2, 2]),
+                                            ("case1_then_2", [1, 2]), ("case0_then_1", [0, 1])])
+def test_cpo_oracle_replays_reference_learn(golden_dir, case, dual_cases):
     """cpo.py:147-370 (critic regression, CG, dual case analysis, line search) run by the reference itself."""
     from oracle import cpo as ocpo
     g = _load_policy_golden(golden_dir, "policy_cpo_golden.npz")[case]
@@ -179,7 +180,7 @@ def test_cpo_oracle_replays_reference_learn(golden_dir, case):
     stats = ocpo.learn(actor, critics, opt, d, 99999, 2, g["ave_cost"], g["cost_limit"], optim_critic_iters=3,
                        l2_reg=0.001, delta=0.01, max_backtracks=10)
     ref = g["stats"]
-    assert [int(s["loss/optim_case"]) for s in stats] == [int(x) for x in ref["loss/optim_case"]]
+    assert [int(s["loss/optim_case"]) for s in stats] == [int(x) for x in ref["loss/optim_case"]] == dual_cases
     _cmp_stats(stats, ref, ("loss/kl", "loss/entropy", "loss/rew_loss", "loss/cost_loss", "loss/vf0", "loss/vf1",
                             "loss/vf_total", "loss/step_size"), rtol=2e-3, atol=2e-6)
     _cmp_stats(stats, ref, ("loss/optim_Q", "loss/optim_R", "loss/optim_S", "loss/optim_lam", "loss/optim_nu"),
@@ -220,3 +221,102 @@ def test_focops_oracle_replays_reference_learn(golden_dir, case):
     _cmp_stats(stats, ref, ("loss/actor_loss", "loss/kl", "loss/entropy", "loss/vf0", "loss/vf1", "loss/vf_total"),
                rtol=2e-5, atol=2e-7)
     _assert_final_params(g["final"], actor, critics, atol=2e-6)
+
+
+def _load_q(net, sd, prefix, k=None):
+    from oracle import nets as onets
+    pre = "preprocess" if k is None else f"preprocess{k}"
+    last = "last" if k is None else f"last{k}"
+    g = lambda key: sd[prefix + key]
+    onets.load_linear(net.body.layers[0], g(pre + ".model.model.0.weight"), g(pre + ".model.model.0.bias"))
+    onets.load_linear(net.body.layers[1], g(pre + ".model.model.2.weight"), g(pre + ".model.model.2.bias"))
+    onets.load_linear(net.last, g(last + ".model.0.weight"), g(last + ".model.0.bias"))
+    return net
+
+
+def _assert_q(final, prefix, net, k, atol):
+    pre = "preprocess" if k is None else f"preprocess{k}"
+    last = "last" if k is None else f"last{k}"
+    for key, p in ((pre + ".model.model.0.weight", net.body.layers[0].weight),
+                   (pre + ".model.model.2.weight", net.body.layers[1].weight),
+                   (pre + ".model.model.2.bias", net.body.layers[1].bias),
+                   (last + ".model.0.weight", net.last.weight), (last + ".model.0.bias", net.last.bias)):
+        want = final[prefix + key]
+        assert np.abs(p.detach().numpy().reshape(want.shape) - want).max() <= atol, (prefix + key)
+
+
+@pytest.mark.parametrize("case", ["auto_alpha", "fixed_alpha"])
+def test_sac_oracle_replays_reference_learn(golden_dir, case):
+    """sac_lag.py:185-269 (twin-Q critics, tanh-squashed actor loss, alpha step, Polyak) run by the reference
+    itself; the reparameterisation noise it drew is replayed from the golden file."""
+    from oracle import nets as onets, offpolicy as ooff
+    g = _load_policy_golden(golden_dir, "policy_sac_golden.npz")[case]
+    d, init = g["data"], {k: torch.from_numpy(v) for k, v in g["init"].items()}
+    D, A = d["obs0"].shape[1], d["act0"].shape[1]
+    H = g["init"]["actor.mu.model.0.weight"].shape[1]
+    actor = onets.load_from_state_dict(onets.GaussActor(D, A, [H, H], unbounded=True, conditioned_sigma=True), init, "actor.")
+    crit = [[_load_q(onets.ValueNet(D + A, [H, H]), init, f"critics.{i}.", k) for k in (1, 2)] for i in range(2)]
+    crit_old = [[_load_q(onets.ValueNet(D + A, [H, H]), init, f"critics.{i}.", k) for k in (1, 2)] for i in range(2)]
+    a_opt = torch.optim.Adam(actor.parameters(), lr=5e-4)
+    c_opt = torch.optim.Adam([p for pair in crit for q in pair for p in q.parameters()], lr=1e-3)
+    auto, alpha = None, 0.2
+    if g["auto_alpha"]:
+        log_alpha = torch.zeros(1, requires_grad=True)
+        auto = (-float(A), log_alpha, torch.optim.Adam([log_alpha], lr=3e-4))
+        alpha = 1.0
+    stats = []
+    for k in range(3):
+        t = lambda name: torch.from_numpy(d[f"{name}{k}"])
+        st, alpha = ooff.sac_update(actor, crit, crit_old, a_opt, c_opt, t("obs"), t("act"), t("rets"), t("eps"),
+                                    alpha=alpha, tau=0.05, lagrangian=g["lag"], auto_alpha=auto)
+        stats.append(st)
+    ref = g["stats"]
+    keys = ["loss/q0", "loss/q1", "loss/q_total", "loss/actor_rew", "loss/actor_safety", "loss/actor_total"]
+    if g["auto_alpha"]:
+        keys += ["loss/alpha_loss", "loss/alpha_value"]
+    _cmp_stats(stats, ref, keys, rtol=2e-5, atol=2e-7)
+    final = g["final"]
+    for key, p in (("actor.mu.model.0.weight", actor.mu.weight), ("actor.sigma.model.0.weight", actor.sigma.weight),
+                   ("actor.preprocess.model.model.0.weight", actor.body.layers[0].weight)):
+        assert np.abs(p.detach().numpy() - final[key]).max() <= 2e-6, key
+    for i in range(2):
+        for k in (1, 2):
+            _assert_q(final, f"critics.{i}.", crit[i][k - 1], k, 2e-6)
+            _assert_q(final, f"critics_old.{i}.", crit_old[i][k - 1], k, 2e-6)      # Polyak-averaged targets
+
+
+@pytest.mark.parametrize("case", ["lag05", "lag0"])
+def test_ddpg_oracle_replays_reference_learn(golden_dir, case):
+    from oracle import nets as onets, offpolicy as ooff
+    g = _load_policy_golden(golden_dir, "policy_ddpg_golden.npz")[case]
+    d, init = g["data"], {k: torch.from_numpy(v) for k, v in g["init"].items()}
+    D, A = d["obs0"].shape[1], d["act0"].shape[1]
+    H = g["init"]["actor.last.model.0.weight"].shape[1]
+
+    def det_actor():
+        a = onets.DetActor(D, A, [H, H])
+        onets.load_linear(a.body.layers[0], init["actor.preprocess.model.model.0.weight"], init["actor.preprocess.model.model.0.bias"])
+        onets.load_linear(a.body.layers[1], init["actor.preprocess.model.model.2.weight"], init["actor.preprocess.model.model.2.bias"])
+        onets.load_linear(a.last, init["actor.last.model.0.weight"], init["actor.last.model.0.bias"])
+        return a
+
+    actor, actor_old = det_actor(), det_actor()
+    crit = [_load_q(onets.ValueNet(D + A, [H, H]), init, f"critics.{i}.") for i in range(2)]
+    crit_old = [_load_q(onets.ValueNet(D + A, [H, H]), init, f"critics.{i}.") for i in range(2)]
+    a_opt = torch.optim.Adam(actor.parameters(), lr=5e-4)
+    c_opt = torch.optim.Adam([p for q in crit for p in q.parameters()], lr=1e-3)
+    stats = []
+    for k in range(3):
+        t = lambda name: torch.from_numpy(d[f"{name}{k}"])
+        stats.append(ooff.ddpg_update(actor, actor_old, crit, crit_old, a_opt, c_opt, t("obs"), t("act"), t("rets"),
+                                      tau=0.05, lagrangian=g["lag"]))
+    _cmp_stats(stats, g["stats"], ["loss/q0", "loss/q1", "loss/q_total", "loss/actor_rew", "loss/actor_safety",
+                                   "loss/actor_total"], rtol=2e-5, atol=2e-7)
+    final = g["final"]
+    for prefix, a in (("actor.", actor), ("actor_old.", actor_old)):
+        for key, p in (("preprocess.model.model.0.weight", a.body.layers[0].weight), ("last.model.0.weight", a.last.weight),
+                       ("last.model.0.bias", a.last.bias)):
+            assert np.abs(p.detach().numpy() - final[prefix + key]).max() <= 2e-6, prefix + key
+    for i in range(2):
+        _assert_q(final, f"critics.{i}.", crit[i], None, 2e-6)
+        _assert_q(final, f"critics_old.{i}.", crit_old[i], None, 2e-6)
