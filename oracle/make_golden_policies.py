@@ -343,6 +343,85 @@ def golden_ddpg(Batch):
     return cases
 
 
+class _RingView:
+    """What BasePolicy.compute_*_returns asks of a tianshou buffer, served from an OracleBuffer: the
+    ring semantics (next / unfinished_index) are OUR restatement [tianshou absent]; everything the
+    reference then does with them (masks, end flags, dtype flow, the numba kernels) is its own code."""
+
+    def __init__(self, buf, Batch):
+        from oracle import offpolicy as ooff
+        self._b, self._next = buf, ooff.buffer_next
+        self.terminated, self.truncated = buf.terminated, buf.truncated
+        self.done = buf.terminated | buf.truncated
+        self.rew = buf.rew.astype(np.float64)                 # tianshou stores rew as float64
+        self.info = Batch(cost=buf.cost.astype(np.float64))
+
+    def next(self, idx):
+        return self._next(self._b, idx)
+
+    def unfinished_index(self):
+        return self._b.unfinished_index()
+
+
+def _ring(seed, E=3, T=40, p_term=0.08):
+    from oracle.collector import OracleBuffer
+    rng = np.random.default_rng(seed)
+    buf = OracleBuffer(E * T, E, D, A)
+    lens = [T, T - 7, T - 15]                                # ragged: two envs stop mid-episode (unfinished)
+    for t in range(T):
+        ids = np.array([e for e in range(E) if t < lens[e]])
+        n = len(ids)
+        trunc = np.array([(t + 1) % 13 == 0 for _ in ids])
+        buf.add(ids, rng.normal(size=(n, D)).astype(np.float32), np.tanh(rng.normal(size=(n, A))).astype(np.float32),
+                rng.normal(0.5, 1.0, size=n).astype(np.float32), (rng.random(n) < 0.1).astype(np.float32),
+                np.zeros(n, np.float32), rng.random(n) < p_term, trunc, rng.normal(size=(n, D)).astype(np.float32))
+    return buf
+
+
+def golden_returns_glue(Batch):
+    """base_policy.py:384-451 (compute_gae_returns, with and without reward normalisation) and :453-512
+    (compute_nstep_returns) executed by the reference on a ragged 3-env ring."""
+    from fsrl.policy.ppo_lag import PPOLagrangian
+    cases = {}
+    buf = _ring(50)
+    view = _RingView(buf, Batch)
+    idx = buf.sample_all()
+    ring = dict(obs=buf.obs, obs_next=buf.obs_next, act=buf.act, rew=buf.rew, cost=buf.cost,
+                terminated=buf.terminated, truncated=buf.truncated, ptr=buf.ptr, len=buf.len, idx=idx)
+    for name, rew_norm in (("gae", False), ("gae_rew_norm", True)):
+        actor, critics = _nets(9)
+        init = _state(_mods(actor, critics))
+        act_space, obs_space = _space()
+        pol = PPOLagrangian(actor, critics, torch.optim.Adam(actor.parameters()), _dist, logger=_Capture(),
+                            reward_normalization=rew_norm, gamma=0.99, observation_space=obs_space,
+                            action_space=act_space)
+        out = {}
+        for call in range(2):                                 # the second call sees the updated running std
+            batch = Batch(obs=torch.from_numpy(buf.obs[idx]), obs_next=torch.from_numpy(buf.obs_next[idx]),
+                          rew=view.rew[idx], terminated=buf.terminated[idx], truncated=buf.truncated[idx],
+                          info=Batch(cost=buf.cost[idx].astype(np.float64)))
+            batch = pol.compute_gae_returns(batch, view, idx, 0.95)
+            out[f"values{call}"] = batch.values.numpy(); out[f"rets{call}"] = batch.rets.numpy()
+            out[f"advs{call}"] = batch.advs.numpy()
+            out[f"rms_var{call}"] = np.array([float(r.var) for r in pol.ret_rms])
+        cases[name] = dict(kw={}, lag=0.0, data=ring, init=init, final=out, stats={})
+    # n-step targets with a fixed target-Q function
+    rng = np.random.default_rng(51)
+    actor, critics = _nets(9)
+    act_space, obs_space = _space()
+    pol = PPOLagrangian(actor, critics, torch.optim.Adam(actor.parameters()), _dist, logger=_Capture(), gamma=0.97,
+                        observation_space=obs_space, action_space=act_space)
+    sel = rng.choice(idx, size=48).astype(np.int64)
+    out = {"sel": sel}
+    for n_step in (1, 2, 3, 5):
+        tq = [rng.normal(size=(48, 1)).astype(np.float32) for _ in range(2)]
+        b = pol.compute_nstep_returns(Batch(), view, sel, lambda _buf, _term: [torch.from_numpy(t) for t in tq], n_step)
+        out[f"tq{n_step}"] = np.stack([t[:, 0] for t in tq])
+        out[f"rets{n_step}"] = b.rets.numpy()
+    cases["nstep"] = dict(kw={}, lag=0.0, data=ring, init={}, final=out, stats={})
+    return cases
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -367,3 +446,4 @@ if __name__ == "__main__":
     _save("policy_focops_golden.npz", golden_focops(B))
     _save("policy_sac_golden.npz", golden_sac(B))
     _save("policy_ddpg_golden.npz", golden_ddpg(B))
+    _save("policy_returns_glue_golden.npz", golden_returns_glue(B))

@@ -320,3 +320,63 @@ def test_ddpg_oracle_replays_reference_learn(golden_dir, case):
     for i in range(2):
         _assert_q(final, f"critics.{i}.", crit[i], None, 2e-6)
         _assert_q(final, f"critics_old.{i}.", crit_old[i], None, 2e-6)
+
+
+def _ring_from(d):
+    from oracle.collector import OracleBuffer
+    E = len(d["ptr"])
+    cap = d["obs"].shape[0] // E
+    buf = OracleBuffer(cap * E, E, d["obs"].shape[1], d["act"].shape[1])
+    for k in ("obs", "obs_next", "act", "rew", "cost"):
+        setattr(buf, k, d[k])
+    buf.terminated, buf.truncated = d["terminated"].astype(bool), d["truncated"].astype(bool)
+    buf.ptr, buf.len = d["ptr"].astype(np.int64), d["len"].astype(np.int64)
+    return buf
+
+
+@pytest.mark.parametrize("case", ["gae", "gae_rew_norm"])
+def test_gae_glue_replays_reference_compute_gae_returns(golden_dir, case):
+    """base_policy.py:384-451 executed by the reference on a ragged ring (unfinished episodes, terminations,
+    truncations): value mask, end flags, dtype flow, optional running-std normalisation."""
+    from fsrl_b200.utils.optim_util import RunningMeanStd
+    g = _load_policy_golden(golden_dir, "policy_returns_glue_golden.npz")[case]
+    d, out = g["data"], g["final"]
+    buf = _ring_from(d)
+    idx = d["idx"].astype(np.int64)
+    D, A, H = d["obs"].shape[1], d["act"].shape[1], g["init"]["actor.mu.model.0.weight"].shape[1]
+    _, critics = _oracle_nets_from(g["init"], D, A, H)
+    with torch.no_grad():
+        v = np.stack([c(torch.from_numpy(buf.obs[idx])).flatten().numpy() for c in critics])
+        vn = np.stack([c(torch.from_numpy(buf.obs_next[idx])).flatten().numpy() for c in critics])
+    unfinished = np.isin(idx, buf.unfinished_index())
+    assert unfinished.sum() == 2                       # two of the three envs stop mid-episode
+    rms = [RunningMeanStd(), RunningMeanStd()]
+    for call in range(2):
+        if case == "gae":
+            vals, rets, advs = returns.dual_gae(v, vn, buf.rew[idx], buf.cost[idx], buf.terminated[idx], buf.truncated[idx],
+                                                unfinished, 0.99, 0.95)
+        else:
+            vals, rets, advs, moments = returns.dual_gae_rew_norm(
+                v, vn, buf.rew[idx], buf.cost[idx], buf.terminated[idx], buf.truncated[idx], unfinished, 0.99, 0.95,
+                [r.var for r in rms])
+            for r, (m, var, cnt) in zip(rms, moments):
+                r.update_moments(m, var, cnt)
+            np.testing.assert_allclose([r.var for r in rms], out[f"rms_var{call}"], rtol=1e-6)
+        np.testing.assert_allclose(vals, out[f"values{call}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(advs, out[f"advs{call}"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(rets, out[f"rets{call}"], rtol=2e-6, atol=2e-6)
+
+
+def test_nstep_glue_replays_reference_compute_nstep_returns(golden_dir):
+    """base_policy.py:453-512 executed by the reference (n = 1, 2, 3, 5) with a fixed target-Q function."""
+    from oracle import offpolicy as ooff
+    g = _load_policy_golden(golden_dir, "policy_returns_glue_golden.npz")["nstep"]
+    buf = _ring_from(g["data"])
+    out = g["final"]
+    sel = out["sel"].astype(np.int64)
+    for n_step in (1, 2, 3, 5):
+        tq = [out[f"tq{n_step}"][i] for i in range(2)]
+        rets, _ = ooff.nstep_targets(buf, sel, tq, 0.97, n_step)
+        want = out[f"rets{n_step}"]                      # the reference keeps target_q's (bsz, 1) shape: (bsz, 1, C)
+        assert want.shape == (len(sel), 1, 2)
+        np.testing.assert_allclose(rets, want[:, 0, :], rtol=1e-6, atol=1e-6, err_msg=f"n_step={n_step}")
