@@ -314,7 +314,67 @@ def run_ours(args):
 # -------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle restatement of the reference path on the host cores
 # -------------------------------------------------------------------------------------------------
+def _reference_dir():
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
+    return d if os.path.isdir(os.path.join(d, "fsrl")) else None
+
+
 def cpu_reference(sample_envs=32, cycles=1, threads=None):
+    """CPU arm.  When `baseline/_ref` holds the reference (pip --no-deps --target install, built by
+    __graft_entry__.build()), its OWN classes do the work that dominates the CPU time -- process_fn =
+    BasePolicy.compute_gae_returns (numba gae_return) and PPOLagrangian.learn (eager torch autograd +
+    Adam) run unmodified on the host cores; the third-party packages it imports but that are absent
+    here (tianshou, gymnasium) are thin shims (oracle/refrun.py), and rollout collection -- which in
+    the reference lives in tianshou's vector env / buffer and in pybullet -- is the oracle's in-process
+    numpy env twin (no IPC: a lower bound on the reference's collect cost).  Without `baseline/_ref`
+    the whole path is the oracle port."""
+    ref_dir = _reference_dir()
+    if ref_dir is not None:
+        try:
+            return cpu_reference_real(ref_dir, sample_envs, cycles, threads)
+        except Exception as e:              # never lose the baseline: fall back to the port and say why
+            print(f"[bench] reference classes unavailable ({type(e).__name__}: {e}); timing the oracle port",
+                  file=sys.stderr)
+    return cpu_reference_port(sample_envs, cycles, threads)
+
+
+def cpu_reference_real(ref_dir, sample_envs, cycles, threads):
+    import oracle.collector as ocol
+    from oracle import refrun
+    from oracle.envs import OracleVecEnv
+    Batch = refrun.bootstrap(ref_dir)
+    threads = threads or best_thread_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(SEED); np.random.seed(SEED)
+    D, A, T = 8, 2, 300
+    pol, actor, critics = refrun.ppo_lag_policy(D, A, HIDDEN, lr=5e-4, target_kl=float("inf"), max_grad_norm=0.5,
+                                                cost_limit=10.0, gamma=0.99)      # ppol_cfg.py values
+    act_fn = lambda obs: actor(obs)[0]                                           # (mu, sigma)
+    env = OracleVecEnv(0, sample_envs, SEED); env.reset()
+    buf = ocol.OracleBuffer(sample_envs * T, sample_envs, D, A)
+    ctr = np.zeros(sample_envs, np.uint32)
+    t0 = time.time()
+    n = 0
+    for _ in range(cycles):
+        buf.reset()
+        st = ocol.collect(env, act_fn, sample_envs, SEED, ctr, buf)
+        pol.pre_update_fn(stats_train=st)                                        # PID step on the collect's cost
+        idx = buf.sample_all()
+        view = refrun.RingView(buf, Batch)
+        batch = Batch(obs=torch.from_numpy(buf.obs[idx]), obs_next=torch.from_numpy(buf.obs_next[idx]),
+                      act=torch.from_numpy(buf.act[idx]), rew=view.rew[idx], terminated=buf.terminated[idx],
+                      truncated=buf.truncated[idx], info=Batch(cost=buf.cost[idx].astype(np.float64)))
+        batch = pol.process_fn(batch, view, idx)                                 # ppo_lag.py:134-150
+        pol.learn(batch, BATCH, REPEAT)                                          # ppo_lag.py:214-257
+        n += st["n/st"]
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "env-steps/s", "cores": threads, "kind": "reference",
+            "sample": f"{sample_envs} envs x {T} steps x {cycles} cycle(s) of c2 (2x256 MLP, batch 256, repeat 4): "
+                      f"unmodified fsrl.policy.PPOLagrangian (process_fn + learn) from baseline/_ref with "
+                      f"tianshou/gymnasium shims; collect = in-process numpy env twin (oracle), {dt:.1f} s"}
+
+
+def cpu_reference_port(sample_envs=32, cycles=1, threads=None):
     """The reference's CPU path (FastCollector over per-env worker processes + numba GAE +
     eager-torch PPO update) cannot be installed here (tianshou/gymnasium/pybullet absent,
     no network): this times its restatement in oracle/ -- numpy env twin stepped in-process
@@ -406,8 +466,9 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "c2 shapes (2x256 MLP, batch 256, repeat 4) on a bounded sample of "
-                               f"{args.cpu_envs} envs x 300 steps per step; CPU restatement of the "
-                               "reference path (oracle/), the reference itself is not installable"},
+                               f"{args.cpu_envs} envs x 300 steps per step on the host cores; see "
+                               "cpu_baseline.kind / sample for what ran (reference classes from baseline/_ref, "
+                               "or the oracle port)"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -34,39 +34,13 @@ D, A, H, N, BS, REPEAT = 8, 2, 16, 200, 64, 2
 
 def _bootstrap():
     sys.path.insert(0, ROOT)
-    sys.path.insert(0, REF)               # `fsrl` must resolve to the reference, not to the shim
-    import fsrl_b200.compat as compat
-    done = compat.install()
-    assert "fsrl" not in done, "the reference package must be the real one"
-    import fsrl
-    assert fsrl.__file__.startswith(REF), fsrl.__file__
-    from tianshou.data import Batch
-    from oracle.ppo import split_indices
-
-    def split(self, size, shuffle=True, merge_last=False):
-        for idx in split_indices(len(self), size, shuffle=shuffle, merge_last=merge_last):
-            yield self[idx]
-
-    Batch.split = split                   # golden generation only; see the module docstring
-    return Batch
+    from oracle import refrun
+    return refrun.bootstrap(REF)
 
 
-class _Capture:
-    """Stands in for fsrl.utils.BaseLogger: keeps every stored scalar in call order."""
-
-    def __init__(self):
-        self.rows = {}
-
-    def store(self, tab=None, **kw):
-        for k, v in kw.items():
-            key = k if tab is None else f"{tab}/{k}"
-            self.rows.setdefault(key, []).append(float(v))
-
-    def print(self, *a, **k):
-        pass
-
-    def write(self, *a, **k):
-        pass
+def _Capture():
+    from oracle import refrun
+    return refrun.Capture()
 
 
 def _nets(seed):
@@ -343,24 +317,9 @@ def golden_ddpg(Batch):
     return cases
 
 
-class _RingView:
-    """What BasePolicy.compute_*_returns asks of a tianshou buffer, served from an OracleBuffer: the
-    ring semantics (next / unfinished_index) are OUR restatement [tianshou absent]; everything the
-    reference then does with them (masks, end flags, dtype flow, the numba kernels) is its own code."""
-
-    def __init__(self, buf, Batch):
-        from oracle import offpolicy as ooff
-        self._b, self._next = buf, ooff.buffer_next
-        self.terminated, self.truncated = buf.terminated, buf.truncated
-        self.done = buf.terminated | buf.truncated
-        self.rew = buf.rew.astype(np.float64)                 # tianshou stores rew as float64
-        self.info = Batch(cost=buf.cost.astype(np.float64))
-
-    def next(self, idx):
-        return self._next(self._b, idx)
-
-    def unfinished_index(self):
-        return self._b.unfinished_index()
+def _RingView(buf, Batch):
+    from oracle import refrun
+    return refrun.RingView(buf, Batch)
 
 
 def _ring(seed, E=3, T=40, p_term=0.08):
