@@ -397,7 +397,30 @@ def _save(name, cases):
     print("wrote", path, f"{os.path.getsize(path) / 1024:.1f} KiB", {k: len(v["stats"]) for k, v in cases.items()})
 
 
+def check(ref_dir, rtol=2e-5):
+    """Re-run the PPO cases with the reference found in `ref_dir` (e.g. the baseline/_ref install) and
+    compare with the committed fixture: the installed copy must behave like the source tree."""
+    global REF
+    REF = ref_dir
+    B = _bootstrap()
+    fresh = golden_ppo(B)
+    raw = np.load(os.path.join(OUT, "policy_ppo_golden.npz"))
+    worst = 0.0
+    for cname, c in fresh.items():
+        for k, v in c["stats"].items():
+            want = raw[f"{cname}|stats|{k}"]
+            got = np.asarray(v, dtype=np.float64)
+            assert got.shape == want.shape, (cname, k)
+            err = np.abs(got - want).max() / (np.abs(want).max() + 1e-12)
+            worst = max(worst, err)
+            assert err <= rtol, (cname, k, err)
+    print(f"reference in {ref_dir} reproduces tests/golden/policy_ppo_golden.npz (max rel err {worst:.2e})")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--check":
+        check(os.path.abspath(sys.argv[2]))
+        sys.exit(0)
     B = _bootstrap()
     _save("policy_ppo_golden.npz", golden_ppo(B))
     _save("policy_cpo_golden.npz", golden_cpo(B))
