@@ -381,6 +381,19 @@ def golden_returns_glue(Batch):
     return cases
 
 
+def golden_trainers():
+    """fsrl/trainer/{base_trainer,onpolicy,offpolicy}.py + fsrl.utils.BaseLogger driven by scripted fakes."""
+    import json
+    from fsrl.trainer import OffpolicyTrainer, OnpolicyTrainer
+    from fsrl.utils import BaseLogger
+    from oracle import trainer_scenario
+    rec = trainer_scenario.run(OnpolicyTrainer, OffpolicyTrainer, BaseLogger)
+    path = os.path.join(OUT, "trainer_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", path, {k: (len(v["trace"]), len(v["epochs"])) for k, v in rec.items()})
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -429,3 +442,4 @@ if __name__ == "__main__":
     _save("policy_sac_golden.npz", golden_sac(B))
     _save("policy_ddpg_golden.npz", golden_ddpg(B))
     _save("policy_returns_glue_golden.npz", golden_returns_glue(B))
+    golden_trainers()

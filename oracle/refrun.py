@@ -40,6 +40,17 @@ def bootstrap(ref_dir: str):
     done = compat.install()
     if "fsrl" in done:
         raise RuntimeError("the compat layer shadowed the reference package")
+    import importlib.util
+    import types
+    for absent in ("h5py",):              # imported at module top by fsrl.data.traj_buf (offline-dataset export); unused here
+        if absent not in sys.modules and importlib.util.find_spec(absent) is None:
+            sys.modules[absent] = types.ModuleType(absent)
+    if "tianshou.data.utils.converter" not in sys.modules:            # same module: HDF5 export helper, unused here
+        def to_hdf5(*a, **k):
+            raise NotImplementedError("HDF5 export needs h5py and tianshou, both absent")
+        conv = types.ModuleType("tianshou.data.utils.converter"); conv.to_hdf5 = to_hdf5
+        utils = types.ModuleType("tianshou.data.utils"); utils.converter = conv
+        sys.modules["tianshou.data.utils"], sys.modules["tianshou.data.utils.converter"] = utils, conv
     import fsrl
     if not os.path.abspath(fsrl.__file__).startswith(ref_dir):
         raise RuntimeError(f"fsrl resolved to {fsrl.__file__}, expected {ref_dir}")

@@ -1,0 +1,108 @@
+"""Deterministic fake collector / policy used to compare trainer implementations (test infrastructure).
+
+``run(OnTrainer, OffTrainer, LoggerCls)`` drives an on-policy and an off-policy trainer for a few
+epochs with scripted collect statistics and records (a) every call the trainer makes on the policy and
+the collectors, in order, with its arguments, and (b) what it returns / logs, minus wall-clock values.
+oracle/make_golden_policies.py runs it with the REFERENCE's trainers and logger
+(fsrl.trainer.*, fsrl.utils.BaseLogger) and stores the record as tests/golden/trainer_golden.json;
+tests/test_oracle_golden.py runs it with fsrl_b200's and compares.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TIME_KEYS = ("duration", "train_collector_time", "train_model_time", "train_speed", "test_time", "test_speed")
+
+
+class FakeCollector:
+    def __init__(self, name, trace, seed):
+        self.name, self.trace = name, trace
+        self.rng = np.random.default_rng(seed)
+        self.buffer = "buffer:" + name
+        self.collect_step = self.collect_episode = 0
+        self.collect_time = 0.0
+
+    def reset_stat(self):
+        self.trace.append([self.name, "reset_stat"])
+        self.collect_step = self.collect_episode = 0
+        self.collect_time = 0.0
+
+    def reset_env(self, *a, **k):
+        self.trace.append([self.name, "reset_env"])
+
+    def reset_buffer(self, keep_statistics=False):
+        self.trace.append([self.name, "reset_buffer", bool(keep_statistics)])
+
+    def collect(self, n_episode=None, **kw):
+        self.trace.append([self.name, "collect", n_episode, sorted(kw)])
+        lens = self.rng.integers(20, 60, size=n_episode)
+        n_st = int(lens.sum())
+        cost = float(np.round(self.rng.uniform(0, 30), 3))
+        rew = float(np.round(self.rng.uniform(-5, 40), 3))
+        self.collect_step += n_st
+        self.collect_episode += n_episode
+        self.collect_time += 0.01
+        return {"n/ep": n_episode, "n/st": n_st, "rew": rew, "len": float(lens.mean()), "total_cost": cost * n_episode,
+                "cost": cost, "truncated": 1.0, "terminated": 0.0}
+
+
+class FakePolicy:
+    def __init__(self, trace):
+        self.trace = trace
+
+    def train(self, mode=True):
+        self.trace.append(["policy", "train"])
+        return self
+
+    def eval(self):
+        self.trace.append(["policy", "eval"])
+        return self
+
+    def pre_update_fn(self, **kw):
+        self.trace.append(["policy", "pre_update_fn", {k: (v if isinstance(v, (int, float, str)) else "<obj>")
+                                                       for k, v in sorted(kw.items()) if k != "stats_train"},
+                           kw["stats_train"]["n/st"]])
+
+    def update(self, sample_size, buffer, **kw):
+        self.trace.append(["policy", "update", sample_size, buffer, {k: v for k, v in sorted(kw.items())}])
+
+    def post_update_fn(self, **kw):
+        self.trace.append(["policy", "post_update_fn", sorted(kw)])
+
+
+def _clean(d):
+    out = {}
+    for k, v in d.items():
+        if any(k.endswith(t) for t in TIME_KEYS):
+            continue
+        out[k] = float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v
+    return out
+
+
+def run(OnTrainer, OffTrainer, LoggerCls):
+    record = {}
+    for kind in ("onpolicy", "offpolicy"):
+        trace = []
+        policy = FakePolicy(trace)
+        train_c, test_c = FakeCollector("train", trace, 1), FakeCollector("test", trace, 2)
+        logger = LoggerCls()
+        stops = []
+
+        def stop_fn(best_rew, best_cost):
+            stops.append([float(best_rew), float(best_cost)])
+            return len(stops) >= 3                         # ends the run after the third epoch
+
+        common = dict(max_epoch=5, batch_size=64, cost_limit=12.0, step_per_epoch=400, episode_per_collect=4,
+                      episode_per_test=2, save_model_interval=2, stop_fn=stop_fn, logger=logger, verbose=False,
+                      show_progress=False)
+        if kind == "onpolicy":
+            trainer = OnTrainer(policy, train_c, test_c, repeat_per_collect=3, **common)
+        else:
+            trainer = OffTrainer(policy, train_c, test_c, update_per_step=0.05, **common)
+        epochs = []
+        for epoch, stats, info in trainer:
+            epochs.append({"epoch": int(epoch), "stats": _clean(stats), "info": _clean(info)})
+        record[kind] = {"trace": trace, "epochs": epochs, "stops": stops,
+                        "env_step": int(trainer.env_step), "cum_episode": int(trainer.cum_episode),
+                        "cum_cost": float(trainer.cum_cost)}
+    return record

@@ -396,3 +396,29 @@ def test_installed_reference_reproduces_golden():
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "reproduces" in out.stdout
+
+
+def test_trainers_and_logger_match_reference_trace(golden_dir):
+    """a15 (drivers + the train_speed bookkeeping): fsrl_b200's On/OffpolicyTrainer + BaseLogger, driven by
+    the scripted fakes of oracle/trainer_scenario.py, make the same calls in the same order and return /
+    log the same values as the reference's trainers did (tests/golden/trainer_golden.json)."""
+    from fsrl_b200.trainer import OffpolicyTrainer, OnpolicyTrainer
+    from fsrl_b200.utils.logger import BaseLogger
+    from oracle import trainer_scenario
+    want = json.load(open(os.path.join(golden_dir, "trainer_golden.json")))
+    got = json.loads(json.dumps(trainer_scenario.run(OnpolicyTrainer, OffpolicyTrainer, BaseLogger)))
+    for kind in ("onpolicy", "offpolicy"):
+        w, g = want[kind], got[kind]
+        assert g["trace"] == w["trace"], next((i, a, b) for i, (a, b) in enumerate(zip(g["trace"], w["trace"])) if a != b)
+        np.testing.assert_allclose(np.array(g["stops"]), np.array(w["stops"]), rtol=1e-9)
+        assert (g["env_step"], g["cum_episode"]) == (w["env_step"], w["cum_episode"])
+        assert g["cum_cost"] == pytest.approx(w["cum_cost"])
+        assert len(g["epochs"]) == len(w["epochs"]) == 3
+        for ge, we in zip(g["epochs"], w["epochs"]):
+            assert ge["epoch"] == we["epoch"]
+            assert set(ge["stats"]) == set(we["stats"]), set(ge["stats"]) ^ set(we["stats"])
+            for k in we["stats"]:
+                assert ge["stats"][k] == pytest.approx(we["stats"][k], rel=1e-9), k
+            assert set(ge["info"]) == set(we["info"]), set(ge["info"]) ^ set(we["info"])
+            for k in we["info"]:
+                assert ge["info"][k] == pytest.approx(we["info"][k], rel=1e-9), k
