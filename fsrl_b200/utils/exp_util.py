@@ -39,10 +39,12 @@ def load_config_and_model(path: str, best: bool = False) -> Tuple[dict, dict]:
 
 
 def to_string(values):
+    """Flatten a config value into a run-name fragment the way the reference does (exp_util.py:90-108):
+    sequences and dict values (in sorted-key order) are joined with "_", scalars use ``str()``."""
+    if isinstance(values, dict):
+        return "_".join(to_string(values[k]) for k in sorted(values))
     if isinstance(values, (list, tuple)):
-        return "-".join(to_string(v) for v in values)
-    if isinstance(values, float):
-        return f"{values:g}"
+        return "_".join(to_string(v) for v in values)
     return str(values)
 
 
@@ -56,14 +58,17 @@ DEFAULT_KEY_ABBRE = {"cost_limit": "cost", "mstep_iter_num": "mnum", "estep_iter
 
 def auto_name(default_cfg: dict, current_cfg: dict, prefix: str = "", suffix: str = "",
               skip_keys: Sequence[str] = DEFAULT_SKIP_KEY, key_abbre: Dict = DEFAULT_KEY_ABBRE) -> str:
-    """Run name = the keys that differ from the default config (exp_util.py:131-169)."""
-    parts = [prefix] if prefix else []
-    for k in sorted(default_cfg.keys()):
-        if k in skip_keys or k not in current_cfg:
+    """Run name built like the reference's (exp_util.py:131-169): ``prefix``, then one
+    ``<key or its abbreviation><value>`` fragment per config key (sorted) whose value differs from the
+    default and is not in ``skip_keys``, then ``suffix`` -- all joined with "_" -- or "default" when
+    nothing differs; a "-xxxx" tag of four random hex digits keeps repeated runs apart."""
+    import uuid
+    fragments = [prefix] if prefix else []
+    for key in sorted(default_cfg.keys()):
+        if key in skip_keys or default_cfg[key] == current_cfg[key]:
             continue
-        if default_cfg[k] != current_cfg[k]:
-            parts.append(f"{key_abbre.get(k, k)}_{to_string(current_cfg[k])}")
+        fragments.append(key_abbre.get(key, key) + to_string(current_cfg[key]))
     if suffix:
-        parts.append(suffix)
-    name = "-".join(parts) if parts else "default"
-    return f"{name}-{str(hash(name))[-4:]}" if False else name
+        fragments.append(suffix)
+    name = "_".join(fragments) if fragments else "default"
+    return f"{name}-{str(uuid.uuid4())[:4]}"

@@ -394,6 +394,38 @@ def golden_trainers():
     print("wrote", path, {k: (len(v["trace"]), len(v["epochs"])) for k, v in rec.items()})
 
 
+def golden_configs_and_names():
+    """fsrl/config/*_cfg.py defaults (every TrainCfg / Bullet* / Mujoco* dataclass) and
+    fsrl.utils.exp_util.{to_string, auto_name} on a handful of inputs."""
+    import importlib
+    import json
+    from dataclasses import asdict
+    from fsrl.utils.exp_util import auto_name, to_string
+    rec = {"configs": {}, "to_string": [], "auto_name": []}
+    for key in ("ppol", "cpo", "sacl", "ddpgl", "trpol", "focosp"):
+        mod = importlib.import_module(f"fsrl.config.{key}_cfg")
+        for cls in ("TrainCfg", "Bullet1MCfg", "Bullet5MCfg", "Bullet10MCfg", "MujocoBaseCfg", "Mujoco2MCfg",
+                    "Mujoco10MCfg", "Mujoco20MCfg"):
+            d = asdict(getattr(mod, cls)())
+            rec["configs"][f"{key}.{cls}"] = {k: (list(v) if isinstance(v, tuple) else v) for k, v in d.items()}
+    for v in (3, 2.5, 1e-4, 0.00037, 123456.789, True, None, "abc", [1, 2.5, "x"], (64, 64), {"a": 1, "b": [2, 3]}, 1e9, 10):
+        rec["to_string"].append([repr(v), to_string(v)])
+    base = asdict(importlib.import_module("fsrl.config.ppol_cfg").TrainCfg())
+    for changes, prefix, suffix, skip in (({}, "ppol", "", []), ({"lr": 1e-3, "seed": 5}, "ppol", "", []),
+                                          ({"hidden_sizes": (256, 256), "cost_limit": 25, "task": "SafetyAntCircle-v0"}, "x", "s1", []),
+                                          ({"gamma": 0.995, "unbounded": True}, "", "end", ["gamma"])):
+        cur = dict(base); cur.update(changes)
+        rec["auto_name"].append({"changes": {k: (list(v) if isinstance(v, tuple) else v) for k, v in changes.items()},
+                                 "prefix": prefix, "suffix": suffix, "skip": skip,
+                                 # the last 5 characters are a random "-uuid4[:4]" tag
+                                 "name": (auto_name(base, cur, prefix, suffix, skip_keys=skip) if skip
+                                          else auto_name(base, cur, prefix, suffix))[:-5]})
+    path = os.path.join(OUT, "config_names_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", path, len(rec["configs"]), "config classes")
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -443,3 +475,4 @@ if __name__ == "__main__":
     _save("policy_ddpg_golden.npz", golden_ddpg(B))
     _save("policy_returns_glue_golden.npz", golden_returns_glue(B))
     golden_trainers()
+    golden_configs_and_names()

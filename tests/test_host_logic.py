@@ -89,7 +89,8 @@ def test_compat_shims_resolve_reference_imports():
     env = gym.make("SafetyCarCircle-v0")
     assert env.observation_space.shape == (8,) and env.action_space.shape == (2,)
     assert env.spec.max_episode_steps == 300
-    assert auto_name({"a": 1, "b": 2}, {"a": 1, "b": 3}, "ppol") == "ppol-b_3"
+    name = auto_name({"a": 1, "b": 2}, {"a": 1, "b": 3}, "ppol")       # reference format: prefix_<key><value>-<tag>
+    assert name[:-5] == "ppol_b3" and name[-5] == "-" and len(name) == len("ppol_b3") + 5
     with pytest.raises(KeyError):
         gym.make("NoSuchTask-v0")
 

@@ -422,3 +422,30 @@ def test_trainers_and_logger_match_reference_trace(golden_dir):
             assert set(ge["info"]) == set(we["info"]), set(ge["info"]) ^ set(we["info"])
             for k in we["info"]:
                 assert ge["info"][k] == pytest.approx(we["info"][k], rel=1e-9), k
+
+
+def test_config_defaults_and_run_names_match_reference(golden_dir):
+    """Every config dataclass of the reference (fsrl/config/*_cfg.py: TrainCfg, Bullet*, Mujoco*) has the same
+    fields and defaults in fsrl_b200.config, and exp_util.to_string / auto_name produce the same run names."""
+    import dataclasses
+    from fsrl_b200 import config as cfg
+    from fsrl_b200.utils.exp_util import auto_name, to_string
+    want = json.load(open(os.path.join(golden_dir, "config_names_golden.json")))
+    norm = lambda d: {k: (list(v) if isinstance(v, tuple) else v) for k, v in d.items()}
+    assert len(want["configs"]) == 48
+    for name, fields in want["configs"].items():
+        key, cls = name.split(".")
+        got = norm(dataclasses.asdict(getattr(getattr(cfg, key + "_cfg"), cls)()))
+        assert list(got) == list(fields) or set(got) == set(fields), (name, set(got) ^ set(fields))
+        for k, v in fields.items():
+            assert got[k] == v, (name, k, got[k], v)
+    samples = (3, 2.5, 1e-4, 0.00037, 123456.789, True, None, "abc", [1, 2.5, "x"], (64, 64), {"a": 1, "b": [2, 3]}, 1e9, 10)
+    for v, (rep, s) in zip(samples, want["to_string"]):
+        assert repr(v) == rep and to_string(v) == s, (v, to_string(v), s)
+    base = dataclasses.asdict(cfg.ppol_cfg.TrainCfg())
+    for case in want["auto_name"]:
+        cur = dict(base)
+        cur.update({k: (tuple(v) if isinstance(v, list) else v) for k, v in case["changes"].items()})
+        got = (auto_name(base, cur, case["prefix"], case["suffix"], skip_keys=case["skip"]) if case["skip"]
+               else auto_name(base, cur, case["prefix"], case["suffix"]))
+        assert got[:-5] == case["name"] and got[-5] == "-", (got, case["name"])
