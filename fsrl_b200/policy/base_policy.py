@@ -235,31 +235,37 @@ class BasePolicy(ABC, nn.Module):
             tp.data.copy_(tau * sp.data + (1 - tau) * tp.data)
 
     def map_action(self, act):
-        if isinstance(self.action_space, Box) and isinstance(act, np.ndarray):
-            if self.action_bound_method == "clip":
-                act = np.clip(act, -1.0, 1.0)
-            elif self.action_bound_method == "tanh":
-                act = np.tanh(act)
-            if self.action_scaling:
-                assert np.min(act) >= -1.0 and np.max(act) <= 1.0, \
-                    "action scaling only accepts raw action range = [-1, 1]"
-                low, high = self.action_space.low, self.action_space.high
-                act = low + (high - low) * (act + 1.0) / 2.0
-        return act
+        """Policy output -> what the env receives (base_policy.py:226-256): bound to [-1, 1] by clipping or
+        tanh, then stretch affinely onto [low, high].  Host twin of the epilogue fused into the rollout
+        kernel (csrc/rollout.cu); only ndarray actions of Box spaces are touched."""
+        if not (isinstance(self.action_space, Box) and isinstance(act, np.ndarray)):
+            return act
+        bound = {"clip": lambda a: np.clip(a, -1.0, 1.0), "tanh": np.tanh}.get(self.action_bound_method)
+        unit = bound(act) if bound is not None else act
+        if not self.action_scaling:
+            return unit
+        assert np.min(unit) >= -1.0 and np.max(unit) <= 1.0, "action scaling only accepts raw action range = [-1, 1]"
+        lo, hi = self.action_space.low, self.action_space.high
+        return lo + (hi - lo) * (unit + 1.0) / 2.0
 
     def map_action_inverse(self, act):
-        if isinstance(self.action_space, Box):
-            act = to_numpy(act)
-            if isinstance(act, np.ndarray):
-                if self.action_scaling:
-                    low, high = self.action_space.low, self.action_space.high
-                    scale = high - low
-                    eps = np.finfo(np.float32).eps.item()
-                    scale[scale < eps] += eps
-                    act = (act - low) * 2.0 / scale - 1.0
-                if self.action_bound_method == "tanh":
-                    act = (np.log(1.0 + act) - np.log(1.0 - act)) / 2.0
-        return act
+        """Env-range action (e.g. ``action_space.sample()`` during random warm-up) -> the policy's own range
+        (base_policy.py:258-283): undo the affine stretch (degenerate dimensions get an epsilon width), then
+        undo tanh bounding with atanh."""
+        if not isinstance(self.action_space, Box):
+            return act
+        raw = to_numpy(act)
+        if not isinstance(raw, np.ndarray):
+            return raw
+        if self.action_scaling:
+            lo = self.action_space.low
+            width = self.action_space.high - lo
+            tiny = np.finfo(np.float32).eps.item()
+            width[width < tiny] += tiny
+            raw = (raw - lo) * 2.0 / width - 1.0
+        if self.action_bound_method == "tanh":
+            raw = (np.log(1.0 + raw) - np.log(1.0 - raw)) / 2.0
+        return raw
 
     def process_fn(self, batch, buffer, indices):
         return batch

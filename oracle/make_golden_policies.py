@@ -426,6 +426,34 @@ def golden_configs_and_names():
     print("wrote", path, len(rec["configs"]), "config classes")
 
 
+def golden_action_maps():
+    """BasePolicy.map_action / map_action_inverse (base_policy.py:226-283) of the reference on sample actions."""
+    import json
+    from fsrl.policy.ppo_lag import PPOLagrangian
+    from gymnasium.spaces import Box
+    rng = np.random.default_rng(60)
+    acts = (rng.normal(scale=1.5, size=(6, 3))).astype(np.float32)
+    lows, highs = np.array([-2.0, 0.0, -1.0], np.float32), np.array([2.0, 0.0, 3.0], np.float32)   # one degenerate dim
+    rec = {"act": acts.tolist(), "low": lows.tolist(), "high": highs.tolist(), "cases": []}
+    for method in ("clip", "tanh", ""):
+        for scaling in (True, False):
+            actor, critics = _nets(2)
+            pol = PPOLagrangian(actor, critics, torch.optim.Adam(actor.parameters()), _dist, logger=_Capture(),
+                                action_scaling=scaling, action_bound_method=method,
+                                observation_space=_space()[1], action_space=Box(low=lows.copy(), high=highs.copy()))
+            src = np.clip(acts, -1, 1) if (method == "" and scaling) else acts
+            fwd = pol.map_action(src.copy())
+            env_acts = (lows + (highs - lows) * rng.random(size=(6, 3))).astype(np.float32)
+            inv = pol.map_action_inverse(env_acts.copy())
+            rec["cases"].append({"method": method, "scaling": scaling, "src": src.tolist(),
+                                 "mapped": np.asarray(fwd, np.float64).tolist(), "env_acts": env_acts.tolist(),
+                                 "inverse": np.nan_to_num(np.asarray(inv, np.float64), nan=1e30, posinf=1e30, neginf=-1e30).tolist()})
+    path = os.path.join(OUT, "action_map_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f)
+    print("wrote", path, len(rec["cases"]), "cases")
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -476,3 +504,4 @@ if __name__ == "__main__":
     _save("policy_returns_glue_golden.npz", golden_returns_glue(B))
     golden_trainers()
     golden_configs_and_names()
+    golden_action_maps()

@@ -449,3 +449,25 @@ def test_config_defaults_and_run_names_match_reference(golden_dir):
         got = (auto_name(base, cur, case["prefix"], case["suffix"], skip_keys=case["skip"]) if case["skip"]
                else auto_name(base, cur, case["prefix"], case["suffix"]))
         assert got[:-5] == case["name"] and got[-5] == "-", (got, case["name"])
+
+
+def test_action_maps_match_reference(golden_dir):
+    """BasePolicy.map_action / map_action_inverse (a4) against the reference's own methods: clip / tanh / no
+    bounding, with and without scaling, including a degenerate (low == high) action dimension."""
+    import types
+    import warnings
+    from fsrl_b200.policy.base_policy import BasePolicy
+    from fsrl_b200.spaces import Box
+    g = json.load(open(os.path.join(golden_dir, "action_map_golden.json")))
+    low, high = np.array(g["low"], np.float32), np.array(g["high"], np.float32)
+    assert len(g["cases"]) == 6
+    for c in g["cases"]:
+        stub = types.SimpleNamespace(action_space=Box(low=low.copy(), high=high.copy()), action_scaling=c["scaling"],
+                                     action_bound_method=c["method"])
+        mapped = BasePolicy.map_action(stub, np.array(c["src"], np.float32))
+        np.testing.assert_allclose(np.asarray(mapped, np.float64), np.array(c["mapped"]), rtol=0, atol=0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")           # atanh of values outside (-1, 1): nan / inf like the reference
+            inv = BasePolicy.map_action_inverse(stub, np.array(c["env_acts"], np.float32))
+        inv = np.nan_to_num(np.asarray(inv, np.float64), nan=1e30, posinf=1e30, neginf=-1e30)
+        np.testing.assert_allclose(inv, np.array(c["inverse"]), rtol=0, atol=0)
