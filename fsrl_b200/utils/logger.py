@@ -117,14 +117,21 @@ class BaseLogger:
             torch.save(self.checkpoint_fn(), os.path.join(d, "model" + tag + ".pt"))
 
     def save_config(self, config: dict, verbose=True) -> None:
+        """``<log_dir>/config.yaml`` in the reference's wire format (base_logger.py:128-163): the run name is
+        written INTO the caller's dict, and the dict is dumped as is (block style, insertion order, tuples as
+        ``!!python/tuple``) so that either side's ``load_config_and_model`` reads the other's runs."""
         if self.name is not None:
-            config = dict(config, name=self.name)
+            config["name"] = self.name
         if verbose:
             print("Saving config:", {k: v for k, v in config.items()})
         if self.log_dir:
             import yaml
             with open(os.path.join(self.log_dir, "config.yaml"), "w") as f:
-                yaml.dump(_plain(config), f, default_flow_style=False, indent=4, sort_keys=False)
+                try:
+                    yaml.dump(config, f, default_flow_style=False, indent=4, sort_keys=False)
+                except yaml.representer.RepresenterError:      # an object PyYAML cannot tag: fall back to plain types
+                    f.seek(0); f.truncate()
+                    yaml.dump(_plain(config), f, default_flow_style=False, indent=4, sort_keys=False)
 
     def restore_data(self) -> None:
         pass

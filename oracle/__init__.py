@@ -21,6 +21,11 @@ Parity pinning
   ``tests/golden/policy_*_golden.npz`` that ``oracle/{ppo,cpo,trpo,focops,offpolicy}.py`` must
   reproduce (CPO: dual cases 0-3; PPO: dual clip + value clip; SAC: auto / fixed alpha with the
   reference's own reparameterisation noise recorded).
+* The same generator pins host-side pieces of the drop-in surface against the reference's own code:
+  the ``compute_gae_returns`` / ``compute_nstep_returns`` glue (value mask, end flags, reward
+  normalisation), the trainers + ``BaseLogger`` (call traces, returned statistics, file bytes;
+  scenario in ``oracle/trainer_scenario.py``), every config dataclass, run naming, and
+  ``map_action`` / ``map_action_inverse``.
 * Still **unpinned** by executable reference code (``tianshou`` 0.5.0 itself is absent, no
   network): ``Batch.split`` ordering, ``VectorReplayBuffer`` index semantics and the collector /
   ``compute_*_returns`` glue around the pinned numba kernels -- restated from SURVEY.md 2.3 /

@@ -388,10 +388,22 @@ def golden_trainers():
     from fsrl.utils import BaseLogger
     from oracle import trainer_scenario
     rec = trainer_scenario.run(OnpolicyTrainer, OffpolicyTrainer, BaseLogger)
+    import tempfile
+    from fsrl.utils.exp_util import load_config_and_model
+    with tempfile.TemporaryDirectory() as tmp:
+        rec["logger_files"] = trainer_scenario.logger_files(BaseLogger, tmp)
+    # cross-read: a run directory written by fsrl_b200's logger must load with the REFERENCE's loader
+    from fsrl_b200.utils.logger import BaseLogger as OurLogger
+    with tempfile.TemporaryDirectory() as tmp:
+        trainer_scenario.logger_files(OurLogger, tmp)
+        cfg, model = load_config_and_model(os.path.join(tmp, "run"))
+        assert cfg["task"] == "SafetyCarCircle-v0" and tuple(cfg["hidden_sizes"]) == (128, 128) and "model" in model
+        cfg_b, model_b = load_config_and_model(os.path.join(tmp, "run"), best=True)
+        assert torch.equal(model_b["model"]["w"], torch.arange(3.0))
     path = os.path.join(OUT, "trainer_golden.json")
     with open(path, "w") as f:
         json.dump(rec, f, indent=1, sort_keys=True)
-    print("wrote", path, {k: (len(v["trace"]), len(v["epochs"])) for k, v in rec.items()})
+    print("wrote", path, {k: (len(v["trace"]), len(v["epochs"])) for k, v in rec.items() if "trace" in v})
 
 
 def golden_configs_and_names():

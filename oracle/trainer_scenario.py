@@ -106,3 +106,31 @@ def run(OnTrainer, OffTrainer, LoggerCls):
                         "env_step": int(trainer.env_step), "cum_episode": int(trainer.cum_episode),
                         "cum_cost": float(trainer.cum_cost)}
     return record
+
+
+def logger_files(LoggerCls, log_dir):
+    """Drive a file-backed logger through config saving, two writes and a checkpoint; return the text of
+    the files it produced (config.yaml, progress.txt) and the checkpoint file names."""
+    import os
+    import torch
+    lg = LoggerCls(log_dir, log_txt=True, name="run")
+    cfg = {"task": "SafetyCarCircle-v0", "hidden_sizes": (128, 128), "lr": 5e-4, "lagrangian_pid": (0.05, 0.0005, 0.1),
+           "cost_limit": 10, "unbounded": False, "group": None}
+    lg.save_config(cfg, verbose=False)
+    lg.setup_checkpoint_fn(lambda: {"model": {"w": torch.arange(3.0)}})
+    for step, vals in ((1000, [(1.0, 12.0), (3.0, 8.0)]), (2000, [(5.0, 4.0)])):
+        for rew, cost in vals:
+            lg.store(tab="train", reward=rew, cost=cost)
+        lg.store(tab="update", gradient_steps=step // 10)
+        lg.store(total=0.25 * step, tab="loss")
+        lg.write(step, display=False)
+    lg.save_checkpoint()
+    lg.save_checkpoint(suffix=7)
+    lg.save_checkpoint(suffix="best")
+    if getattr(lg, "output_file", None) is not None:
+        lg.output_file.flush()
+    run = os.path.join(log_dir, "run")
+    return {"cfg_after": {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()},
+            "config.yaml": open(os.path.join(run, "config.yaml")).read(),
+            "progress.txt": open(os.path.join(run, "progress.txt")).read(),
+            "checkpoints": sorted(os.listdir(os.path.join(run, "checkpoint")))}

@@ -471,3 +471,25 @@ def test_action_maps_match_reference(golden_dir):
             inv = BasePolicy.map_action_inverse(stub, np.array(c["env_acts"], np.float32))
         inv = np.nan_to_num(np.asarray(inv, np.float64), nan=1e30, posinf=1e30, neginf=-1e30)
         np.testing.assert_allclose(inv, np.array(c["inverse"]), rtol=0, atol=0)
+
+
+def test_logger_files_match_reference_byte_for_byte(golden_dir, tmp_path):
+    """f3: config.yaml, progress.txt and the checkpoint file names written by fsrl_b200's BaseLogger equal what
+    the reference's BaseLogger wrote for the same calls; our loader reads the reference's files."""
+    from fsrl_b200.utils.exp_util import load_config_and_model
+    from fsrl_b200.utils.logger import BaseLogger
+    from oracle import trainer_scenario
+    want = json.load(open(os.path.join(golden_dir, "trainer_golden.json")))["logger_files"]
+    got = trainer_scenario.logger_files(BaseLogger, str(tmp_path / "ours"))
+    assert got["progress.txt"] == want["progress.txt"]
+    assert got["config.yaml"] == want["config.yaml"]
+    assert got["checkpoints"] == want["checkpoints"] == ["model.pt", "model_7.pt", "model_best.pt"]
+    assert got["cfg_after"] == want["cfg_after"]                      # the reference writes `name` into the caller's dict
+    # a run directory as the REFERENCE wrote it (texts from the golden file) loads with our loader
+    ref_run = tmp_path / "theirs" / "run"
+    (ref_run / "checkpoint").mkdir(parents=True)
+    (ref_run / "config.yaml").write_text(want["config.yaml"])
+    torch.save({"model": {"w": torch.arange(3.0)}}, ref_run / "checkpoint" / "model.pt")
+    cfg, model = load_config_and_model(str(ref_run))
+    assert cfg["hidden_sizes"] == (128, 128) and cfg["lagrangian_pid"] == (0.05, 0.0005, 0.1) and cfg["name"] == "run"
+    assert torch.equal(model["model"]["w"], torch.arange(3.0))
