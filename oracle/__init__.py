@@ -25,10 +25,10 @@ Parity pinning
   the ``compute_gae_returns`` / ``compute_nstep_returns`` glue (value mask, end flags, reward
   normalisation), the trainers + ``BaseLogger`` (call traces, returned statistics, file bytes;
   scenario in ``oracle/trainer_scenario.py``), every config dataclass, run naming, and
-  ``map_action`` / ``map_action_inverse``.
+  ``map_action`` / ``map_action_inverse``, and ``FastCollector.collect`` itself (episode counting,
+  surplus-env rule, reset order: nine scenarios over the numpy env twin, incl. scripted terminations).
 * Still **unpinned** by executable reference code (``tianshou`` 0.5.0 itself is absent, no
-  network): ``Batch.split`` ordering, ``VectorReplayBuffer`` index semantics and the collector /
-  ``compute_*_returns`` glue around the pinned numba kernels -- restated from SURVEY.md 2.3 /
+  network): ``Batch.split`` ordering and ``VectorReplayBuffer`` ring-index semantics -- restated from SURVEY.md 2.3 /
   Appendix C and anchored on the reference's call sites.
 * The environment dynamics (pybullet / mujoco) cannot be reproduced at all; the device
   env is *our* documented model and ``oracle/envs.py`` is its CPU twin.

@@ -466,6 +466,90 @@ def golden_action_maps():
     print("wrote", path, len(rec["cases"]), "cases")
 
 
+def golden_collector():
+    """fsrl/data/fast_collector.py:192-408 executed by the reference: its FastCollector drives a numpy twin of
+    our env model through a minimal vector-env facade and a recording buffer (deterministic eval-mode
+    policy), for several (env count, n_episode) pairs that exercise the surplus-env rule.  The recorded
+    buffers / statistics are what oracle/collector.py::collect must reproduce."""
+    from fsrl.data import FastCollector
+    from fsrl.policy.ppo_lag import PPOLagrangian
+    from gymnasium.spaces import Box
+    from tianshou.data import ReplayBufferManager
+    from oracle.collector import OracleBuffer
+    from oracle.envs import OracleVecEnv
+    KIND, SEED_ENV = "ball_run", 77                      # T = 100, terminates when the ball leaves the track
+
+    from oracle.trainer_scenario import TerminatingEnv
+
+    class VecEnv:
+        def __init__(self, n, period=0):
+            self.e = TerminatingEnv(KIND, n, SEED_ENV, period) if period else OracleVecEnv(KIND, n, SEED_ENV)
+            self.action_space = [Box(low=-np.ones(self.e.A, np.float32), high=np.ones(self.e.A, np.float32))] * n
+
+        def __len__(self):
+            return self.e.E
+
+        def reset(self, ids=None, **kw):
+            obs = self.e.reset(ids)
+            return obs, {"cost": np.zeros(len(obs))}
+
+        def step(self, action, id=None):
+            ids = np.arange(self.e.E) if id is None else np.asarray(id)
+            obs_next, rew, cost, term, trunc = self.e.step(np.asarray(action, np.float32), ids)
+            trunc = trunc & ~term
+            return obs_next, rew.astype(np.float64), term, trunc, {"cost": cost.astype(np.float64)}
+
+    class RecBuffer(ReplayBufferManager):
+        def __init__(self, total, n, D, A):                 # deliberately NOT calling the device buffer's __init__
+            self.b = OracleBuffer(total, n, D, A)
+            self.buffer_num, self.maxsize = n, total
+            self.run_rew, self.run_len = np.zeros(n), np.zeros(n, np.int64)
+
+        def reset(self, keep_statistics=False):
+            self.b.reset()
+
+        def add(self, batch, buffer_ids=None):
+            ids = np.asarray(buffer_ids)
+            ptr = ids * self.b.cap + self.b.ptr[ids]
+            self.b.add(ids, batch.obs, batch.act, batch.rew.astype(np.float32), np.asarray(batch.cost, np.float32),
+                       np.zeros(len(ids), np.float32), batch.terminated, batch.truncated, batch.obs_next)
+            self.run_rew[ids] += batch.rew; self.run_len[ids] += 1
+            done = np.asarray(batch.done, bool)
+            ep_rew = np.where(done, self.run_rew[ids], 0.0); ep_len = np.where(done, self.run_len[ids], 0)
+            fin = ids[done]
+            self.run_rew[fin] = 0; self.run_len[fin] = 0
+            return ptr, ep_rew, ep_len, ptr
+
+    cases = {}
+    for E, n_ep, period in ((4, 4, 0), (4, 9, 0), (3, 7, 0), (5, 2, 0), (2, 1, 0),
+                            (4, 11, 41), (5, 13, 29), (3, 5, 41), (6, 4, 17)):
+        torch.manual_seed(15)
+        env = VecEnv(E, period)
+        D, A = env.e.D, env.e.A
+        from tianshou.utils.net.common import Net
+        from tianshou.utils.net.continuous import ActorProb, Critic
+        actor = ActorProb(Net(D, hidden_sizes=(H, H)), A, max_action=1.0)
+        critics = [Critic(Net(D, hidden_sizes=(H, H))) for _ in range(2)]
+        torch.nn.init.constant_(actor.sigma_param, -0.5)
+        pol = PPOLagrangian(actor, critics, torch.optim.Adam(actor.parameters()), _dist, logger=_Capture(),
+                            observation_space=Box(low=-np.ones(D, np.float32) * 10, high=np.ones(D, np.float32) * 10),
+                            action_space=env.action_space[0])
+        pol.eval()
+        buf = RecBuffer(E * 100 * 4, E, D, A)
+        col = FastCollector(pol, env, buf, exploration_noise=False)
+        st = col.collect(n_episode=n_ep)
+        b = buf.b
+        cases[f"E{E}_n{n_ep}" + (f"_term{period}" if period else "")] = dict(
+            kw={}, lag=0.0, init=_state([("actor", actor)]), stats={},
+            data=dict(E=np.array(E), n_episode=np.array(n_ep), period=np.array(period)),
+            final=dict(obs=b.obs, obs_next=b.obs_next, act=b.act, rew=b.rew, cost=b.cost, terminated=b.terminated,
+                       truncated=b.truncated, ptr=b.ptr, len=b.len,
+                       stats=np.array([st[k] for k in ("n/ep", "n/st", "rew", "len", "total_cost", "cost", "truncated", "terminated")],
+                                      dtype=np.float64),
+                       collect_step=np.array(col.collect_step), collect_episode=np.array(col.collect_episode)))
+    return cases
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -514,6 +598,7 @@ if __name__ == "__main__":
     _save("policy_sac_golden.npz", golden_sac(B))
     _save("policy_ddpg_golden.npz", golden_ddpg(B))
     _save("policy_returns_glue_golden.npz", golden_returns_glue(B))
+    _save("collector_golden.npz", golden_collector())
     golden_trainers()
     golden_configs_and_names()
     golden_action_maps()

@@ -134,3 +134,29 @@ def logger_files(LoggerCls, log_dir):
             "config.yaml": open(os.path.join(run, "config.yaml")).read(),
             "progress.txt": open(os.path.join(run, "progress.txt")).read(),
             "checkpoints": sorted(os.listdir(os.path.join(run, "checkpoint")))}
+
+
+class TerminatingEnv:
+    """The numpy env twin plus a scripted termination rule (our env models only ever truncate at T): env e
+    terminates at step t of its k-th episode when (7 e + 13 t + 5 k) % period == 0, so that episodes end at
+    different times in different envs -- what the collector's surplus-env bookkeeping has to cope with."""
+
+    def __init__(self, kind, n_env, seed, period=41):
+        from oracle.envs import OracleVecEnv
+        self.inner = OracleVecEnv(kind, n_env, seed)
+        self.period = period
+        self.E, self.D, self.A = self.inner.E, self.inner.D, self.inner.A
+
+    def reset(self, ids=None):
+        return self.inner.reset(ids)
+
+    def observe(self, ids=None):
+        return self.inner.observe(ids)
+
+    def step(self, act, ids):
+        ids = np.asarray(ids)
+        k = self.inner.ep_idx[ids].astype(np.int64)
+        obs_next, rew, cost, term, trunc = self.inner.step(act, ids)
+        t = self.inner.t[ids].astype(np.int64)
+        term = term | ((7 * ids.astype(np.int64) + 13 * t + 5 * k) % self.period == 0)
+        return obs_next, rew, cost, term, trunc

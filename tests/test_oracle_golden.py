@@ -493,3 +493,33 @@ def test_logger_files_match_reference_byte_for_byte(golden_dir, tmp_path):
     cfg, model = load_config_and_model(str(ref_run))
     assert cfg["hidden_sizes"] == (128, 128) and cfg["lagrangian_pid"] == (0.05, 0.0005, 0.1) and cfg["name"] == "run"
     assert torch.equal(model["model"]["w"], torch.arange(3.0))
+
+
+@pytest.mark.parametrize("case", ["E4_n4", "E4_n9", "E3_n7", "E5_n2", "E2_n1", "E4_n11_term41", "E5_n13_term29",
+                                  "E3_n5_term41", "E6_n4_term17"])
+def test_collector_oracle_replays_reference_fast_collector(golden_dir, case):
+    """a1: fsrl/data/fast_collector.py:192-408 was executed by the reference's own FastCollector on the numpy env
+    twin (deterministic eval-mode policy); oracle/collector.py::collect must fill the same buffer slots with the
+    same transitions and return the same statistics -- episode counting, the surplus-env rule, reset order."""
+    from oracle import collector as ocol, nets as onets
+    from oracle.envs import OracleVecEnv
+    g = _load_policy_golden(golden_dir, "collector_golden.npz")[case]
+    E, n_ep = int(g["data"]["E"]), int(g["data"]["n_episode"])
+    want = g["final"]
+    period = int(g["data"]["period"])          # > 0: scripted terminations, episodes end at different times per env
+    from oracle.trainer_scenario import TerminatingEnv
+    env = TerminatingEnv("ball_run", E, 77, period) if period else OracleVecEnv("ball_run", E, 77)
+    env.reset()
+    D, A = env.D, env.A
+    H = g["init"]["actor.mu.model.0.weight"].shape[1]
+    actor = onets.load_from_state_dict(onets.GaussActor(D, A, [H, H]), {k: torch.from_numpy(v) for k, v in g["init"].items()}, "actor.")
+    buf = ocol.OracleBuffer(E * 100 * 4, E, D, A)
+    st = ocol.collect(env, actor, n_ep, 0, np.zeros(E, np.uint32), buf, mode="eval")
+    got_stats = np.array([st[k] for k in ("n/ep", "n/st", "rew", "len", "total_cost", "cost", "truncated", "terminated")])
+    np.testing.assert_allclose(got_stats, want["stats"], rtol=1e-6, atol=1e-9)
+    assert int(want["collect_episode"]) == n_ep == st["n/ep"] and int(want["collect_step"]) == st["n/st"]
+    np.testing.assert_array_equal(buf.ptr, want["ptr"]); np.testing.assert_array_equal(buf.len, want["len"])
+    for k in ("terminated", "truncated"):
+        np.testing.assert_array_equal(getattr(buf, k), want[k].astype(bool), err_msg=k)
+    for k in ("obs", "obs_next", "act", "rew", "cost"):
+        np.testing.assert_allclose(getattr(buf, k), want[k], rtol=1e-6, atol=1e-6, err_msg=k)
