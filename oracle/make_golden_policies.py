@@ -550,6 +550,58 @@ def golden_collector():
     return cases
 
 
+def golden_state_dicts():
+    """Checkpoint surface of every learner: state_dict keys / shapes (incl. the PID `_extra_state`,
+    lagrangian_base.py:122-143) and the PID state after a scripted cost sequence."""
+    import json
+    from copy import deepcopy
+    from fsrl.policy import CPO, FOCOPS, DDPGLagrangian, PPOLagrangian, SACLagrangian, TRPOLagrangian
+    act_space, obs_space = _space()
+    common = dict(observation_space=obs_space, action_space=act_space)
+    rec = {}
+
+    def describe(pol):
+        sd = pol.state_dict()
+        out = {"keys": {k: (list(v.shape) if torch.is_tensor(v) else "object") for k, v in sd.items()}}
+        if hasattr(pol, "lag_optims"):
+            for cost in (25.0, 14.0, 3.0, 40.0):
+                pol.pre_update_fn(stats_train={"cost": cost})
+            ex = pol.get_extra_state()
+            out["extra_state"] = [{k: (list(v) if isinstance(v, (tuple, list)) else float(v)) for k, v in e.items()} for e in ex]
+            out["lagrangian"] = [float(o.get_lag()) for o in pol.lag_optims]
+            clone = deepcopy(pol)
+            for o in clone.lag_optims:
+                o.lagrangian = 0.0
+            clone.load_state_dict(pol.state_dict())
+            out["restored"] = [float(o.get_lag()) for o in clone.lag_optims]
+        return out
+
+    actor, critics = _nets(1)
+    rec["ppol"] = describe(PPOLagrangian(actor, critics, torch.optim.Adam(actor.parameters()), _dist, logger=_Capture(),
+                                         cost_limit=10.0, **common))
+    actor, critics = _nets(1)
+    rec["trpol"] = describe(TRPOLagrangian(actor, critics, _crit_optim(critics, 1e-3), _dist, logger=_Capture(),
+                                           cost_limit=10.0, **common))
+    actor, critics = _nets(1)
+    rec["cpo"] = describe(CPO(actor, critics, _crit_optim(critics, 1e-3), _dist, logger=_Capture(), cost_limit=10.0, **common))
+    actor, critics = _nets(1)
+    rec["focops"] = describe(FOCOPS(actor, critics, torch.optim.Adam(actor.parameters()), _crit_optim(critics, 1e-3), _dist,
+                                    logger=_Capture(), cost_limit=10.0, nu=(2.0, 1e-2, torch.zeros(1)), **common))
+    actor, critics = _q_nets(1, True)
+    log_alpha = torch.zeros(1, requires_grad=True)
+    rec["sacl"] = describe(SACLagrangian(actor, critics, torch.optim.Adam(actor.parameters()),
+                                         torch.optim.Adam(torch.nn.ModuleList(critics).parameters()), logger=_Capture(),
+                                         alpha=(-2.0, log_alpha, torch.optim.Adam([log_alpha])), cost_limit=10.0, **common))
+    actor, critics = _q_nets(1, False)
+    rec["ddpgl"] = describe(DDPGLagrangian(actor, critics, torch.optim.Adam(actor.parameters()),
+                                           torch.optim.Adam(torch.nn.ModuleList(critics).parameters()), logger=_Capture(),
+                                           cost_limit=10.0, **common))
+    path = os.path.join(OUT, "state_dict_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", path, {k: len(v["keys"]) for k, v in rec.items()})
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -602,3 +654,4 @@ if __name__ == "__main__":
     golden_trainers()
     golden_configs_and_names()
     golden_action_maps()
+    golden_state_dicts()

@@ -523,3 +523,77 @@ def test_collector_oracle_replays_reference_fast_collector(golden_dir, case):
         np.testing.assert_array_equal(getattr(buf, k), want[k].astype(bool), err_msg=k)
     for k in ("obs", "obs_next", "act", "rew", "cost"):
         np.testing.assert_allclose(getattr(buf, k), want[k], rtol=1e-6, atol=1e-6, err_msg=k)
+
+
+def _our_policy(kind):
+    """fsrl_b200 learners built on the CPU (the device arena is created lazily, so the host-side surface --
+    state_dict, PID bookkeeping -- can be inspected without a GPU)."""
+    from torch.distributions import Independent, Normal
+    from fsrl_b200 import nets
+    from fsrl_b200.optim import FusedAdam
+    from fsrl_b200.policy import CPO, FOCOPS, DDPGLagrangian, PPOLagrangian, SACLagrangian, TRPOLagrangian
+    from fsrl_b200.spaces import Box
+    D, A, H = 8, 2, 16
+    sp = dict(observation_space=Box(low=-np.ones(D, np.float32) * 10, high=np.ones(D, np.float32) * 10),
+              action_space=Box(low=-np.ones(A, np.float32), high=np.ones(A, np.float32)))
+    dist = lambda *l: Independent(Normal(*l), 1)
+    if kind in ("ppol", "trpol", "cpo", "focops"):
+        actor = nets.ActorProb(nets.Net(D, hidden_sizes=(H, H)), A, max_action=1.0)
+        critics = [nets.Critic(nets.Net(D, hidden_sizes=(H, H))) for _ in range(2)]
+        if kind == "ppol":
+            return PPOLagrangian(actor, critics, FusedAdam(lr=5e-4), dist, cost_limit=10.0, **sp)
+        if kind == "trpol":
+            return TRPOLagrangian(actor, critics, FusedAdam(lr=1e-3), dist, cost_limit=10.0, **sp)
+        if kind == "cpo":
+            return CPO(actor, critics, FusedAdam(lr=1e-3), dist, cost_limit=10.0, **sp)
+        return FOCOPS(actor, critics, FusedAdam(lr=5e-4), FusedAdam(lr=1e-3), dist, cost_limit=10.0, nu=(2.0, 1e-2, 0.0), **sp)
+    if kind == "sacl":
+        actor = nets.ActorProb(nets.Net(D, hidden_sizes=(H, H)), A, max_action=1.0, unbounded=True, conditioned_sigma=True)
+        critics = [nets.DoubleCritic(nets.Net(D, A, hidden_sizes=(H, H), concat=True), nets.Net(D, A, hidden_sizes=(H, H), concat=True))
+                   for _ in range(2)]
+        log_alpha = torch.zeros(1, requires_grad=True)
+        return SACLagrangian(actor, critics, FusedAdam(lr=5e-4), FusedAdam(lr=1e-3),
+                             alpha=(-2.0, log_alpha, torch.optim.Adam([log_alpha])), cost_limit=10.0, **sp)
+    actor = nets.Actor(nets.Net(D, hidden_sizes=(H, H)), A, max_action=1.0)
+    critics = [nets.Critic(nets.Net(D, A, hidden_sizes=(H, H), concat=True)) for _ in range(2)]
+    return DDPGLagrangian(actor, critics, FusedAdam(lr=5e-4), FusedAdam(lr=1e-3), cost_limit=10.0, **sp)
+
+
+@pytest.mark.parametrize("kind", ["ppol", "trpol", "cpo", "focops", "sacl", "ddpgl"])
+def test_checkpoint_surface_matches_reference(golden_dir, kind):
+    """f3: `{"model": policy.state_dict()}` is the checkpoint both sides exchange -- same keys, same shapes (incl.
+    the PID `_extra_state`), and the PID multiplier after a scripted cost sequence and a state_dict round trip."""
+    want = json.load(open(os.path.join(golden_dir, "state_dict_golden.json")))[kind]
+    pol = _our_policy(kind)
+    sd = pol.state_dict()
+    got_keys = {k: (list(v.shape) if torch.is_tensor(v) else "object") for k, v in sd.items()}
+    assert set(got_keys) == set(want["keys"]), sorted(set(got_keys) ^ set(want["keys"]))
+    for k, shape in want["keys"].items():
+        assert got_keys[k] == shape, (k, got_keys[k], shape)
+    if "extra_state" in want:
+        for cost in (25.0, 14.0, 3.0, 40.0):
+            pol.pre_update_fn(stats_train={"cost": cost})
+        ex = pol.get_extra_state()
+        assert len(ex) == len(want["extra_state"])
+        for e, w in zip(ex, want["extra_state"]):
+            assert set(e) == set(w)
+            for k in w:
+                np.testing.assert_allclose(np.asarray(e[k], np.float64), np.asarray(w[k], np.float64), rtol=1e-12)
+        np.testing.assert_allclose(pol.lagrangians(), want["lagrangian"], rtol=1e-12)
+        # restoring: the reference goes through load_state_dict -> set_extra_state; ours would first build the
+        # device arena in load_state_dict, so the CPU test exercises the same hook directly
+        clone = _our_policy(kind)
+        assert clone.lagrangians() != pol.lagrangians()
+        clone.set_extra_state(pol.state_dict()["_extra_state"])
+        # Reference quirk, pinned here: its set_extra_state looks for an "_extra_state" KEY inside what torch
+        # hands it -- which is the list itself -- so load_state_dict leaves the PID at zero
+        # (lagrangian_base.py:139-143; the golden records 0.0).  fsrl_b200 restores the state (the evident
+        # intent; resume continues the dual variable) and still accepts the wrapped form.
+        assert want["restored"] == [0.0] * len(want["restored"])
+        np.testing.assert_allclose(clone.lagrangians(), want["lagrangian"], rtol=1e-12)
+        wrapped = _our_policy(kind)
+        wrapped.set_extra_state({"_extra_state": pol.state_dict()["_extra_state"]})
+        np.testing.assert_allclose(wrapped.lagrangians(), want["lagrangian"], rtol=1e-12)
+        for cost in (5.0, 30.0):                      # and the restored PID continues identically
+            clone.pre_update_fn(stats_train={"cost": cost}); pol.pre_update_fn(stats_train={"cost": cost})
+        np.testing.assert_allclose(clone.lagrangians(), pol.lagrangians(), rtol=1e-12)
