@@ -51,3 +51,27 @@ def test_ops_refuse_cpu_tensors():
     x = torch.zeros(2, 8)
     with pytest.raises(TypeError, match="CUDA tensor"):
         ops.gae_dual(x, x, x[0], x[0], torch.zeros(8, dtype=torch.uint8), None, 0.99, 0.95)
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/fsrl_b200.h must compile as C99 (no C++, no torch types) and the
+    struct sizes a C compiler sees must be the ones the CUDA build reports (what a cgo / JNI / ctypes binding
+    relies on)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "fsrl_b200.h"\n'
+                   'int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fsrl_mlp3_t), '
+                   'sizeof(fsrl_collect_stats_t), sizeof(fsrl_rollout_t), sizeof(fsrl_ppo_update_t), sizeof(fsrl_netref_t), '
+                   'sizeof(fsrl_netlist_t), sizeof(fsrl_engine_t), sizeof(fsrl_eng_input_t), sizeof(fsrl_offpolicy_t), '
+                   'sizeof(fsrl_cpo_t)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           "-o", str(exe), str(src)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    from fsrl_b200 import _lib
+    assert sizes == [int(_lib.lib.fsrl_abi_sizeof(i)) for i in range(10)]
