@@ -199,3 +199,41 @@ def test_reward_normalization_matches_oracle():
             assert policy.ret_rms[i].var == pytest.approx(rms[i].var, rel=1e-4)
             assert policy.ret_rms[i].mean == pytest.approx(rms[i].mean, rel=1e-4, abs=1e-6)
     assert rms[0].var != 1.0
+
+
+def test_ppo_value_clip_and_dual_clip_match_oracle():
+    """The value-clip (ppo_lag.py:156-163) and dual-clip (:188-191) branches of the device loss head against the
+    oracle (which reproduces the reference's own learn() for exactly these options, tests/test_oracle_golden.py)."""
+    from oracle import ppo as oppo
+    hidden, lag = (64, 64), 0.5
+    policy, venv, buf, col = build_ppo("SafetyCarCircle-v0", hidden=hidden, n_env=4, max_grad_norm=0.5,
+                                       value_clip=True, dual_clip=1.05, reward_normalization=True)
+    col.collect(n_episode=4)
+    policy.lag_optims[0].lagrangian = lag
+    actor, critics = oracle_nets(policy, hidden)
+    idx = buf.sample_indices(0)
+    batch = policy.process_fn(None, buf, idx)
+    b = buffer_to_numpy(buf)
+    sel = idx.cpu().numpy()
+    ob = {k: b[k][sel] for k in ("obs", "obs_next", "act", "rew", "cost", "terminated", "truncated")}
+    # make both clips bite from the first step on: move the stored old values away from the critics' outputs
+    # (|v - v_old| > eps_clip for many rows) and spread the probability ratios around 1 (ratio > dual_clip = 1.05
+    # for a good part of the negative-advantage rows)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    batch.v.mul_(0.5).add_(0.3)
+    batch.logp_old.add_(0.1 * torch.randn(batch.logp_old.shape, device="cuda", generator=gen))
+    ob["advs"] = batch.advs.cpu().numpy().copy(); ob["rets"] = batch.rets.cpu().numpy().copy()
+    ob["values"] = batch.values.cpu().numpy().copy(); ob["logp_old"] = batch.logp_old.cpu().numpy().copy()
+    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
+    np.random.seed(321)
+    ostats = oppo.learn(actor, critics, opt, ob, 64, 1, lag, max_grad_norm=0.5, target_kl=1e9, dual_clip=1.05,
+                        value_clip=True)
+    np.random.seed(321)
+    policy._target_kl = 1e9
+    policy.learn(batch, batch_size=64, repeat=1)
+    st = policy.last_stats
+    K = 6
+    for key in ("loss/actor_rew", "loss/actor_safety", "loss/vf0", "loss/vf1", "loss/kl", "loss/total", "loss/grad_norm"):
+        want = np.array([s[key] for s in ostats]); got = np.asarray(st[key])
+        np.testing.assert_allclose(got[:K], want[:K], rtol=3e-4, atol=3e-6, err_msg=key)
+        np.testing.assert_allclose(got, want, rtol=5e-2, atol=5e-4, err_msg=key)
