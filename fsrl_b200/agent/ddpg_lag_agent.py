@@ -22,7 +22,7 @@ class DDPGLagAgent(OffpolicyAgent):
                  device: str = "cuda", thread: int = 4, seed: int = 10, actor_lr: float = 1e-4,
                  critic_lr: float = 1e-3, hidden_sizes: Tuple[int, ...] = (128, 128), tau: float = 0.005,
                  exploration_noise: float = 0.1, n_step: int = 3, use_lagrangian: bool = True,
-                 lagrangian_pid: Tuple = (0.05, 0.0005, 0.1), rescaling: bool = True, gamma: float = 0.99,
+                 lagrangian_pid: Tuple = (0.5, 0.001, 0.1), rescaling: bool = True, gamma: float = 0.99,
                  deterministic_eval: bool = True, action_scaling: bool = True,
                  action_bound_method: str = "clip", lr_scheduler=None) -> None:
         super().__init__()

@@ -21,11 +21,11 @@ class SACLagAgent(OffpolicyAgent):
     def __init__(self, env, logger: BaseLogger = DummyLogger(), cost_limit: float = 10,
                  device: str = "cuda", thread: int = 4, seed: int = 10, actor_lr: float = 5e-4,
                  critic_lr: float = 1e-3, hidden_sizes: Tuple[int, ...] = (128, 128),
-                 auto_alpha: bool = True, alpha_lr: float = 3e-4, alpha: float = 0.005, tau: float = 0.05,
+                 auto_alpha: bool = True, alpha_lr: float = 3e-4, alpha: float = 0.002, tau: float = 0.05,
                  n_step: int = 2, use_lagrangian: bool = True,
                  lagrangian_pid: Tuple = (0.05, 0.0005, 0.1), rescaling: bool = True, gamma: float = 0.99,
                  conditioned_sigma: bool = True, unbounded: bool = True, last_layer_scale: bool = False,
-                 deterministic_eval: bool = True, action_scaling: bool = True,
+                 deterministic_eval: bool = False, action_scaling: bool = True,
                  action_bound_method: str = "clip", lr_scheduler=None) -> None:
         super().__init__()
         self.logger, self.cost_limit = logger, cost_limit

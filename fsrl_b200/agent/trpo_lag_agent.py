@@ -55,3 +55,14 @@ class TRPOLagAgent(OnpolicyAgent):
             action_space=env.action_space, lr_scheduler=lr_scheduler)
         self.policy.arena
         self.policy.set_action_seed(seed)
+
+    def learn(self, train_envs, test_envs=None, epoch: int = 300, episode_per_collect: int = 20,
+              step_per_epoch: int = 10000, repeat_per_collect: int = 4, buffer_size: int = 100000,
+              testing_num: int = 2, batch_size: int = 99999, reward_threshold: float = 450,
+              save_interval: int = 4, resume: bool = False, save_ckpt: bool = True,
+              verbose: bool = True, show_progress: bool = True):
+        """Same protocol as OnpolicyAgent.learn; the trust-region step wants the whole collect as ONE batch, hence
+        the reference's default batch_size = 99999 (trpo_lag_agent.py:190-213)."""
+        return super().learn(train_envs, test_envs, epoch, episode_per_collect, step_per_epoch, repeat_per_collect,
+                             buffer_size, testing_num, batch_size, reward_threshold, save_interval, resume, save_ckpt,
+                             verbose, show_progress)

@@ -37,7 +37,7 @@ def _fused(optim) -> FusedAdam:
 
 class FOCOPS(TrustRegionMixin, BasePolicy):
     def __init__(self, actor, critics, actor_optim, critic_optim, dist_fn=None,
-                 logger: BaseLogger = DummyLogger(), cost_limit: float = np.inf,
+                 logger: BaseLogger = DummyLogger(), cost_limit: float = 10,
                  nu: Union[float, Tuple[float, float, Any]] = 0.01, l2_reg: float = 1e-3, delta: float = 0.02,
                  eta: float = 0.02, tem_lambda: float = 0.95, gae_lambda: float = 0.95,
                  max_grad_norm: Optional[float] = 0.5, advantage_normalization: bool = True,

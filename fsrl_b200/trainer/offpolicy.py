@@ -7,7 +7,7 @@ from .base_trainer import BaseTrainer
 
 
 class OffpolicyTrainer(BaseTrainer):
-    def __init__(self, policy, train_collector, test_collector=None, max_epoch: int = 100,
+    def __init__(self, policy, train_collector, test_collector=None, max_epoch: int = 1000,
                  batch_size: int = 512, cost_limit: float = float("inf"),
                  step_per_epoch: int = 10000, update_per_step: float = 0.1,
                  episode_per_collect: int = 1, save_model_interval: int = 1,

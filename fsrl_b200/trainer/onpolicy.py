@@ -7,7 +7,7 @@ from .base_trainer import BaseTrainer
 
 
 class OnpolicyTrainer(BaseTrainer):
-    def __init__(self, policy, train_collector, test_collector=None, max_epoch: int = 100,
+    def __init__(self, policy, train_collector, test_collector=None, max_epoch: int = 10000,
                  batch_size: int = 512, cost_limit: float = float("inf"),
                  step_per_epoch: int = 10000, repeat_per_collect: int = 4,
                  episode_per_collect: int = 10, save_model_interval: int = 1,

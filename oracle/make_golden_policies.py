@@ -602,6 +602,53 @@ def golden_state_dicts():
     print("wrote", path, {k: len(v["keys"]) for k, v in rec.items()})
 
 
+def golden_signatures():
+    """Public call signatures of the drop-in surface: parameter names, order and defaults of the
+    reference's agents, policies, collector, trainers and loggers."""
+    import inspect
+    import json
+    import fsrl.agent as A_
+    import fsrl.data as D_
+    import fsrl.policy as P_
+    import fsrl.trainer as T_
+    import fsrl.utils as U_
+
+    def sig(fn):
+        out = []
+        for name, p in inspect.signature(fn).parameters.items():
+            if name == "self":
+                continue
+            d = p.default
+            if d is inspect.Parameter.empty:
+                rep = "<required>"
+            elif isinstance(d, (int, float, str, bool, tuple, list, type(None))):
+                rep = repr(d)
+            else:
+                rep = "<object:%s>" % type(d).__name__
+            out.append([name, str(p.kind), rep])
+        return out
+
+    rec = {}
+    for mod, names, methods in (
+            (A_, ["PPOLagAgent", "CPOAgent", "SACLagAgent", "DDPGLagAgent", "TRPOLagAgent", "FOCOPSAgent"],
+             ["__init__", "learn", "evaluate"]),
+            (P_, ["PPOLagrangian", "CPO", "SACLagrangian", "DDPGLagrangian", "TRPOLagrangian", "FOCOPS"],
+             ["__init__", "learn", "process_fn", "pre_update_fn", "update", "forward", "map_action", "map_action_inverse"]),
+            (D_, ["FastCollector"], ["__init__", "collect", "reset_env", "reset_buffer", "reset_stat"]),
+            (T_, ["OnpolicyTrainer", "OffpolicyTrainer"], ["__init__", "policy_update_fn", "train_step", "test_step", "run"]),
+            (U_, ["BaseLogger", "TensorboardLogger", "WandbLogger", "DummyLogger"],
+             ["__init__", "store", "write", "save_checkpoint", "save_config", "get_mean", "print"])):
+        for cn in names:
+            cls = getattr(mod, cn)
+            for m in methods:
+                if hasattr(cls, m):
+                    rec[f"{cn}.{m}"] = sig(getattr(cls, m))
+    path = os.path.join(OUT, "signatures_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", path, len(rec), "signatures")
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -655,3 +702,4 @@ if __name__ == "__main__":
     golden_configs_and_names()
     golden_action_maps()
     golden_state_dicts()
+    golden_signatures()

@@ -597,3 +597,57 @@ def test_checkpoint_surface_matches_reference(golden_dir, kind):
         for cost in (5.0, 30.0):                      # and the restored PID continues identically
             clone.pre_update_fn(stats_train={"cost": cost}); pol.pre_update_fn(stats_train={"cost": cost})
         np.testing.assert_allclose(clone.lagrangians(), pol.lagrangians(), rtol=1e-12)
+
+
+def test_public_signatures_match_reference(golden_dir):
+    """(b) drop-in boundary: every parameter of the reference's agents / policies / collector / trainers / loggers
+    (names, order, defaults; tests/golden/signatures_golden.json, extracted with inspect from the reference) exists
+    on the fsrl_b200 class with the same default.  Deliberate deviations are listed here, nothing else may differ."""
+    import inspect
+    import fsrl_b200.agent as A_
+    import fsrl_b200.data as D_
+    import fsrl_b200.policy as P_
+    import fsrl_b200.trainer as T_
+    from fsrl_b200.utils import logger as U_
+    want = json.load(open(os.path.join(golden_dir, "signatures_golden.json")))
+    allowed = {
+        # the engine only runs on CUDA devices ("cpu" is accepted and mapped to "cuda")
+        **{(f"{a}.__init__", "device"): "'cuda'" for a in ("PPOLagAgent", "CPOAgent", "SACLagAgent", "DDPGLagAgent",
+                                                           "TRPOLagAgent", "FOCOPSAgent")},
+        # dist_fn is optional: the device kernels implement Independent(Normal) directly
+        **{(f"{p}.__init__", "dist_fn"): "None" for p in ("PPOLagrangian", "CPO", "TRPOLagrangian", "FOCOPS")},
+    }
+    home = {**{n: A_ for n in ("PPOLagAgent", "CPOAgent", "SACLagAgent", "DDPGLagAgent", "TRPOLagAgent", "FOCOPSAgent")},
+            **{n: P_ for n in ("PPOLagrangian", "CPO", "SACLagrangian", "DDPGLagrangian", "TRPOLagrangian", "FOCOPS")},
+            "FastCollector": D_, "OnpolicyTrainer": T_, "OffpolicyTrainer": T_,
+            **{n: U_ for n in ("BaseLogger", "TensorboardLogger", "WandbLogger", "DummyLogger")}}
+
+    def rep(d):
+        if d is inspect.Parameter.empty:
+            return "<required>"
+        return repr(d) if isinstance(d, (int, float, str, bool, tuple, list, type(None))) else "<object:%s>" % type(d).__name__
+
+    assert len(want) == 109
+    problems = []
+    for key, ref_params in sorted(want.items()):
+        cn, m = key.split(".")
+        cls = getattr(home[cn], cn)
+        assert hasattr(cls, m), key
+        ours = inspect.signature(getattr(cls, m)).parameters
+        has_kwargs = any(p.kind is inspect.Parameter.VAR_KEYWORD for p in ours.values())
+        for name, kind, default in ref_params:
+            if kind in ("VAR_KEYWORD", "VAR_POSITIONAL"):
+                continue
+            if name not in ours:
+                if not has_kwargs:
+                    problems.append(f"{key}: parameter {name} missing")
+                continue
+            got = rep(ours[name].default)
+            if got != default and not (default.startswith("<object") or got.startswith("<object")):
+                if allowed.get((key, name)) != got:
+                    problems.append(f"{key}: {name} default {got} != reference {default}")
+        ref_order = [n for n, k, _ in ref_params if k == "POSITIONAL_OR_KEYWORD"]
+        our_order = [n for n, p in ours.items() if p.kind is inspect.Parameter.POSITIONAL_OR_KEYWORD and n != "self"]
+        if [n for n in our_order if n in ref_order] != [n for n in ref_order if n in our_order]:
+            problems.append(f"{key}: positional order differs {our_order} vs {ref_order}")
+    assert not problems, "\n".join(problems)
