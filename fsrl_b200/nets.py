@@ -11,6 +11,8 @@ them as an independent fp32 cross-check); the hot path never calls them.
 """
 from __future__ import annotations
 
+from copy import deepcopy
+
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -252,8 +254,9 @@ class DoubleCritic(nn.Module):
         self.preprocess1, self.preprocess2 = preprocess_net1, preprocess_net2
         self.output_dim = 1
         self.last1 = MLP(preprocess_net1.output_dim, 1, ())
-        self.last2 = MLP(preprocess_net2.output_dim, 1, ())
-        self.last2.load_state_dict(self.last1.state_dict())        # reference: deepcopy(last1)
+        # a COPY of last1, not a fresh MLP: constructing one would draw from the torch RNG and every later
+        # initialisation (the agents' orthogonal re-init) would leave the reference's seed-for-seed stream
+        self.last2 = deepcopy(self.last1)
 
     def forward(self, obs, act=None, info={}):
         dev = next(self.parameters()).device

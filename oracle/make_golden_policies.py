@@ -649,6 +649,26 @@ def golden_signatures():
     print("wrote", path, len(rec), "signatures")
 
 
+def golden_agent_inits():
+    """Initial weights the reference's agent presets produce for a given seed (seed_all -> net construction ->
+    orthogonal init -> optional last-layer scaling; e.g. ppo_lag_agent.py:128-162): the torch RNG is consumed in a
+    fixed order, so a drop-in must build the same nets in the same order to start from the same point."""
+    import types
+    from fsrl.agent import CPOAgent, DDPGLagAgent, FOCOPSAgent, PPOLagAgent, SACLagAgent, TRPOLagAgent
+    from fsrl.utils import BaseLogger
+    act_space, obs_space = _space()
+    env = types.SimpleNamespace(observation_space=obs_space, action_space=act_space)
+    cases = {}
+    for name, cls, kw in (("ppol", PPOLagAgent, {}), ("ppol_scaled", PPOLagAgent, dict(last_layer_scale=True)),
+                          ("cpo", CPOAgent, {}), ("trpol", TRPOLagAgent, {}), ("focops", FOCOPSAgent, {}),
+                          ("sacl", SACLagAgent, {}), ("sacl_fixed_sigma", SACLagAgent, dict(conditioned_sigma=False)),
+                          ("ddpgl", DDPGLagAgent, {})):
+        agent = cls(env, logger=BaseLogger(), device="cpu", seed=7, hidden_sizes=(H, H), **kw)
+        sd = {k: v.detach().numpy().copy() for k, v in agent.policy.state_dict().items() if torch.is_tensor(v)}
+        cases[name] = dict(kw=kw, lag=0.0, data={}, init=sd, final={}, stats={})
+    return cases
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -703,3 +723,4 @@ if __name__ == "__main__":
     golden_action_maps()
     golden_state_dicts()
     golden_signatures()
+    _save("agent_init_golden.npz", golden_agent_inits())

@@ -651,3 +651,27 @@ def test_public_signatures_match_reference(golden_dir):
         if [n for n in our_order if n in ref_order] != [n for n in ref_order if n in our_order]:
             problems.append(f"{key}: positional order differs {our_order} vs {ref_order}")
     assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("case,agent,kw", [("ppol", "PPOLagAgent", {}), ("ppol_scaled", "PPOLagAgent", dict(last_layer_scale=True)),
+                                           ("cpo", "CPOAgent", {}), ("trpol", "TRPOLagAgent", {}), ("focops", "FOCOPSAgent", {}),
+                                           ("sacl", "SACLagAgent", {}), ("ddpgl", "DDPGLagAgent", {})])
+def test_agent_presets_start_from_the_reference_weights(golden_dir, monkeypatch, case, agent, kw):
+    """Same seed -> same initial parameters as the reference's agent presets (bit for bit): seed_all, the order in
+    which the nets are built (default torch init consumes the RNG), orthogonal re-initialisation order, sigma_param
+    constant, last-layer scaling, deep-copied target nets.  The device arena is patched out: only the host recipe
+    is under test, so this runs without a GPU."""
+    import types
+    import fsrl_b200.agent as A_
+    from fsrl_b200.policy.base_policy import BasePolicy
+    from fsrl_b200.spaces import Box
+    monkeypatch.setattr(BasePolicy, "_build_arena",
+                        lambda self, device=None: setattr(self, "_arena", types.SimpleNamespace(device="cpu")) or self._arena)
+    want = _load_policy_golden(golden_dir, "agent_init_golden.npz")[case]["init"]
+    env = types.SimpleNamespace(observation_space=Box(low=-np.ones(8, np.float32) * 10, high=np.ones(8, np.float32) * 10),
+                                action_space=Box(low=-np.ones(2, np.float32), high=np.ones(2, np.float32)))
+    a = getattr(A_, agent)(env, seed=7, hidden_sizes=(16, 16), **kw)
+    got = {k: v.detach().cpu().numpy() for k, v in a.policy.state_dict().items() if torch.is_tensor(v)}
+    assert set(got) == set(want), sorted(set(got) ^ set(want))
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
