@@ -669,6 +669,18 @@ def golden_agent_inits():
     return cases
 
 
+def golden_exports():
+    """The reference packages' ``__all__`` lists."""
+    import importlib
+    import json
+    rec = {m: sorted(getattr(importlib.import_module(f"fsrl.{m}"), "__all__", []))
+           for m in ("agent", "policy", "data", "trainer", "utils")}
+    path = os.path.join(OUT, "exports_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", path, {k: len(v) for k, v in rec.items()})
+
+
 def _save(name, cases):
     flat = {}
     for cname, c in cases.items():
@@ -723,4 +735,5 @@ if __name__ == "__main__":
     golden_action_maps()
     golden_state_dicts()
     golden_signatures()
+    golden_exports()
     _save("agent_init_golden.npz", golden_agent_inits())
