@@ -294,6 +294,21 @@ class BasePolicy(ABC, nn.Module):
     def value_mask(buffer, indices):
         return buffer.terminated[indices] == 0
 
+    @staticmethod
+    def get_metrics(batch):
+        """[reward, cost] streams of a batch (base_policy.py:377-382).  The reference re-reads the cost from
+        ``batch.info["cost"]`` because tianshou's buffer drops the collector's ``cost`` key; the device buffer
+        stores it as a first-class array, and a host ``Batch`` with an ``info`` entry is accepted as well."""
+        cost = getattr(batch, "cost", None)
+        if cost is None:
+            info = getattr(batch, "info", None)
+            cost = info.get("cost", None) if info is not None and hasattr(info, "get") else None
+        if cost is None:
+            cost = np.zeros(np.shape(batch.rew))
+        if isinstance(cost, np.ndarray):
+            cost = cost.astype(np.asarray(batch.rew).dtype)
+        return [batch.rew, cost]
+
     # ---- GAE ---------------------------------------------------------------------------------------------
     def gather_batch(self, buffer, indices: torch.Tensor) -> DeviceBatch:
         """buffer[indices] as SoA device arrays; zero-copy when the valid transitions are the

@@ -61,6 +61,24 @@ class LagrangianPolicy(BasePolicy):
             for i, sd in enumerate(state):
                 self.lag_optims[i].load_state_dict(sd)
 
+    def safety_loss(self, values: List) -> Tuple["torch.Tensor", dict]:
+        """Host-side twin of the term the fused update kernels apply (lagrangian_base.py:145-166): the
+        lambda-weighted means of the constrained quantities ``values`` (one tensor per cost stream), plus
+        the statistics the reference logs -- the rescaling factor 1 / (sum(lambda) + 1) (Stooke et al.,
+        Alg. 1) and, per stream, the multiplier and its loss term (suffix "_i" for i >= 1)."""
+        import torch
+        lams = [opt.get_lag() for opt in self.lag_optims]
+        assert len(values) == len(lams), "lags and values length must be equal"
+        stats = {"loss/rescaling": 1. / (np.sum(lams) + 1) if self.rescaling else 1}
+        total = 0.
+        for i, (value, lam) in enumerate(zip(values, lams)):
+            term = torch.mean(value * lam)
+            total = total + term
+            tag = "" if i == 0 else f"_{i}"
+            stats["loss/lagrangian" + tag] = lam
+            stats["loss/actor_safety" + tag] = term.item()
+        return total, stats
+
     def lagrangians(self) -> List[float]:
         return [float(o.get_lag()) for o in self.lag_optims]
 

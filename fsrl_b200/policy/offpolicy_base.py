@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..data.batch import Batch
 from ..engine import EngineCtx
 from ..nets import SIGMA_MAX, SIGMA_MIN
 from .lagrangian_base import LagrangianPolicy
@@ -138,6 +139,33 @@ class OffPolicyLagrangian(LagrangianPolicy):
         start = np.where(lens == buffer.cap, ptr, 0)
         flat = env * buffer.cap + (start[env] + k) % buffer.cap
         return torch.as_tensor(flat.astype(np.int32), device=self.device)
+
+    def compute_nstep_returns(self, batch, buffer, indice, target_q_fn, n_step: int = 1):
+        """API twin of BasePolicy.compute_nstep_returns (base_policy.py:453-512) for callers that drive the
+        pieces themselves (the built-in update path fuses this into ``fsrl_offpolicy_steps``): the n-step walk,
+        the discounted reward / cost sums, gamma^k and the value mask come from ``fsrl_nstep_prepare``;
+        ``target_q_fn(buffer, terminal_indices)`` returns one tensor per critic stream, and
+        ``batch.rets[b, i] = partial_i[b] + gamma^k[b] * ~terminated[terminal[b]] * target_q_i[b]``."""
+        idx = torch.as_tensor(indice, device=self.device).to(torch.int32).contiguous()
+        B = int(idx.numel())
+        self._ensure_engine(max(B, 256))
+        d = self._descriptor(buffer)
+        d.n_step = int(n_step)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.fsrl_nstep_prepare(ctypes.byref(d), idx.data_ptr(), B, self._stream()))
+        w = self._w
+        terminal = w["term_idx"][:B]
+        with torch.no_grad():
+            target_q_list = target_q_fn(buffer, terminal)
+        partial = w["partial"][:2 * B].view(2, B)
+        rets = []
+        for i in range(self.critics_num):
+            tq = torch.as_tensor(target_q_list[i], device=self.device).reshape(B, -1).float() * w["vmask"][:B, None]
+            rets.append((tq.double() * w["gpow"][:B, None] + partial[i][:, None]).float())
+        if batch is None:
+            batch = Batch()
+        batch.rets = torch.stack(rets, dim=-1)
+        return batch
 
     def update_many(self, n_updates: int, batch_size: int, buffer, chunk: int = 4096) -> None:
         """`n_updates` x policy.update(batch_size, buffer) without returning to Python per step."""

@@ -52,6 +52,10 @@ class SACLagrangian(OffPolicyLagrangian):
         self._noise = exploration_noise
         self._alpha_dev = None
 
+    def set_exp_noise(self, noise) -> None:
+        """sac_lag.py:125-127 (the reference's SAC agents pass None: the stochastic actor explores by itself)."""
+        self._noise = noise
+
     def _net_list(self):
         return [self.actor] + list(self.critics) + list(self.critics_old)
 

@@ -669,6 +669,55 @@ def golden_agent_inits():
     return cases
 
 
+def golden_public_attrs_and_safety_loss():
+    """Public (non-nn.Module) attribute names of each learner instance, and LagrangianPolicy.safety_loss /
+    BasePolicy.get_metrics on sample inputs."""
+    import json
+    from fsrl.policy import CPO, FOCOPS, DDPGLagrangian, PPOLagrangian, SACLagrangian, TRPOLagrangian
+    base = set(dir(torch.nn.Module()))
+    act_space, obs_space = _space()
+    sp = dict(observation_space=obs_space, action_space=act_space)
+
+    def pub(o):
+        return sorted(n for n in dir(o) if not n.startswith("_") and n not in base)
+
+    rec = {"attrs": {}}
+    actor, critics = _nets(1)
+    ppo = PPOLagrangian(actor, critics, torch.optim.Adam(actor.parameters()), _dist, logger=_Capture(), cost_limit=10.0, **sp)
+    rec["attrs"]["PPOLagrangian"] = pub(ppo)
+    actor, critics = _nets(1)
+    rec["attrs"]["CPO"] = pub(CPO(actor, critics, _crit_optim(critics, 1e-3), _dist, logger=_Capture(), cost_limit=10.0, **sp))
+    actor, critics = _nets(1)
+    rec["attrs"]["TRPOLagrangian"] = pub(TRPOLagrangian(actor, critics, _crit_optim(critics, 1e-3), _dist, logger=_Capture(),
+                                                         cost_limit=10.0, **sp))
+    actor, critics = _nets(1)
+    rec["attrs"]["FOCOPS"] = pub(FOCOPS(actor, critics, torch.optim.Adam(actor.parameters()), _crit_optim(critics, 1e-3), _dist,
+                                         logger=_Capture(), cost_limit=10.0, nu=(2.0, 1e-2, torch.zeros(1)), **sp))
+    actor, critics = _q_nets(1, True)
+    la = torch.zeros(1, requires_grad=True)
+    rec["attrs"]["SACLagrangian"] = pub(SACLagrangian(actor, critics, torch.optim.Adam(actor.parameters()),
+                                                       torch.optim.Adam(torch.nn.ModuleList(critics).parameters()),
+                                                       logger=_Capture(), alpha=(-2.0, la, torch.optim.Adam([la])), cost_limit=10.0, **sp))
+    actor, critics = _q_nets(1, False)
+    rec["attrs"]["DDPGLagrangian"] = pub(DDPGLagrangian(actor, critics, torch.optim.Adam(actor.parameters()),
+                                                         torch.optim.Adam(torch.nn.ModuleList(critics).parameters()),
+                                                         logger=_Capture(), cost_limit=10.0, **sp))
+    # safety_loss (lagrangian_base.py:145-166) with and without rescaling
+    rng = np.random.default_rng(70)
+    vals = rng.normal(size=50).astype(np.float32)
+    cases = []
+    for lag, resc in ((0.0, True), (0.7, True), (2.5, False)):
+        ppo.lag_optims[0].lagrangian = lag
+        ppo.rescaling = resc
+        loss, st = ppo.safety_loss([torch.from_numpy(vals)])
+        cases.append({"lag": lag, "rescaling": resc, "loss": float(loss), "stats": {k: float(v) for k, v in st.items()}})
+    rec["safety_loss"] = {"values": vals.tolist(), "cases": cases}
+    path = os.path.join(OUT, "public_attrs_golden.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("wrote", path, {k: len(v) for k, v in rec["attrs"].items()})
+
+
 def golden_exports():
     """The reference packages' ``__all__`` lists."""
     import importlib
@@ -736,4 +785,5 @@ if __name__ == "__main__":
     golden_state_dicts()
     golden_signatures()
     golden_exports()
+    golden_public_attrs_and_safety_loss()
     _save("agent_init_golden.npz", golden_agent_inits())

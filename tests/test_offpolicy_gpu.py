@@ -204,3 +204,30 @@ def test_offpolicy_rollout_heads_match_oracle(algo, head):
     np.testing.assert_allclose(b["act"][first], obuf.act[first], rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(b["act"], obuf.act, rtol=0, atol=5e-3)
     np.testing.assert_allclose(b["rew"], obuf.rew, rtol=0, atol=5e-3)
+
+
+@pytest.mark.xfail(strict=False, reason="API wrapper added after the round's GPU budget was spent: not yet run on a B200 "
+                                        "(the kernel underneath is covered by test_nstep_prepare_matches_oracle)")
+def test_compute_nstep_returns_api_matches_oracle():
+    """BasePolicy.compute_nstep_returns (base_policy.py:453-512) as a public call: user-supplied target_q_fn,
+    batch.rets of shape (B, 1, C) like the reference's (target_q keeps its trailing axis)."""
+    from oracle import offpolicy as ooff
+    policy, venv, buf, col = _build("ddpg", n_env=3)
+    col.collect(n_episode=5)
+    ob = _oracle_buffer(buf)
+    rng = np.random.default_rng(1)
+    idx = rng.choice(ob.sample_all(), 200).astype(np.int64)
+    for n_step in (1, 2, 4):
+        tq = [rng.standard_normal(200).astype(np.float32) for _ in range(2)]
+        seen = {}
+
+        def target_q_fn(buffer, terminal):
+            seen["terminal"] = terminal.cpu().numpy().copy()
+            return [torch.from_numpy(t).cuda().reshape(-1, 1) for t in tq]
+
+        batch = policy.compute_nstep_returns(None, buf, idx, target_q_fn, n_step)
+        rets, terminal = ooff.nstep_targets(ob, idx, tq, policy._gamma, n_step)
+        assert np.array_equal(seen["terminal"], terminal.astype(np.int32))
+        got = batch.rets.cpu().numpy()
+        assert got.shape == (200, 1, 2)
+        np.testing.assert_allclose(got[:, 0, :], rets, rtol=1e-6, atol=1e-6)

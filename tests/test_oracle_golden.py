@@ -688,3 +688,29 @@ def test_package_exports_cover_the_reference(golden_dir):
         mod = importlib.import_module(f"fsrl_b200.{pkg}")
         missing = [n for n in names if not hasattr(mod, n) and n not in out_of_scope]
         assert not missing, (pkg, missing)
+
+
+def test_public_attributes_and_safety_loss_match_reference(golden_dir):
+    """Every public attribute / method name a reference learner instance exposes exists on the fsrl_b200 learner
+    (the per-piece loss methods are the documented exception: they are fused into the device update), and
+    LagrangianPolicy.safety_loss returns the reference's value and statistics."""
+    g = json.load(open(os.path.join(golden_dir, "public_attrs_golden.json")))
+    fused = {"critics_loss", "policy_loss"}          # no per-piece host methods: one fused kernel chain does both
+    kinds = {"PPOLagrangian": "ppol", "CPO": "cpo", "TRPOLagrangian": "trpol", "FOCOPS": "focops",
+             "SACLagrangian": "sacl", "DDPGLagrangian": "ddpgl"}
+    for cls, kind in kinds.items():
+        pol = _our_policy(kind)
+        missing = [n for n in g["attrs"][cls] if not hasattr(pol, n) and n not in fused]
+        # compute_nstep_returns lives on the off-policy learners (it needs their replay descriptor)
+        missing = [n for n in missing if not (n == "compute_nstep_returns" and kind in ("ppol", "cpo", "trpol", "focops"))]
+        assert not missing, (cls, missing)
+    pol = _our_policy("ppol")
+    vals = torch.tensor(g["safety_loss"]["values"], dtype=torch.float32)
+    for c in g["safety_loss"]["cases"]:
+        pol.lag_optims[0].lagrangian = c["lag"]
+        pol.rescaling = c["rescaling"]
+        loss, st = pol.safety_loss([vals])
+        assert float(loss) == pytest.approx(c["loss"], rel=1e-6, abs=1e-9)
+        assert set(st) == set(c["stats"])
+        for k, v in c["stats"].items():
+            assert float(st[k]) == pytest.approx(v, rel=1e-6, abs=1e-9), k
