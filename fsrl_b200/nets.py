@@ -122,8 +122,12 @@ class Actor(nn.Module):
 class Critic(nn.Module):
     """V(s) or Q(s, a) (when ``act`` is given the input is cat([obs, act]))."""
 
-    def __init__(self, preprocess_net: Net, hidden_sizes=(), device=None, **_):
+    def __init__(self, preprocess_net: Net, hidden_sizes=(), device=None, preprocess_net_output_dim=None,
+                 linear_layer=nn.Linear, flatten_input: bool = True, **_):
+        # tianshou's positional order (subclasses such as the reference's SingleCritic pass all six positionally)
         super().__init__()
+        if linear_layer is not nn.Linear:
+            raise NotImplementedError("only nn.Linear layers map onto the device engine")
         self.preprocess = preprocess_net
         self.output_dim = 1
         self.last = MLP(preprocess_net.output_dim, 1, ())

@@ -718,6 +718,66 @@ def golden_public_attrs_and_safety_loss():
     print("wrote", path, {k: len(v) for k, v in rec["attrs"].items()})
 
 
+def golden_cvpo(Batch):
+    """cvpo.py:248-430: three consecutive CVPO.learn() calls (SingleCritic and DoubleCritic variants) on given
+    n-step targets; the K action particles each call draws from the old policy are recorded."""
+    import torch.distributions as td
+    from fsrl.policy.cvpo import CVPO
+    from fsrl.utils.net.continuous import DoubleCritic, SingleCritic
+    from tianshou.utils.net.common import Net
+    from tianshou.utils.net.continuous import ActorProb
+    cases = {}
+    for name, double in (("single", False), ("double", True)):
+        torch.manual_seed(11)
+        actor = ActorProb(Net(D, hidden_sizes=(H, H)), A, max_action=1.0, conditioned_sigma=True)
+        critics = []
+        for _ in range(2):
+            if double:
+                critics.append(DoubleCritic(Net(D, A, hidden_sizes=(H, H), concat=True), Net(D, A, hidden_sizes=(H, H), concat=True)))
+            else:
+                critics.append(SingleCritic(Net(D, A, hidden_sizes=(H, H), concat=True)))
+        for m in list(actor.modules()) + [mm for c in critics for mm in c.modules()]:
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.orthogonal_(m.weight)
+                torch.nn.init.zeros_(m.bias)
+        init = _state(_mods(actor, critics))
+        act_space, obs_space = _space()
+        log = _Capture()
+        pol = CVPO(actor, critics, torch.optim.Adam(actor.parameters(), lr=5e-4),
+                   torch.optim.Adam(torch.nn.ModuleList(critics).parameters(), lr=1e-3), act_space, _dist, 300, logger=log,
+                   cost_limit=10.0, tau=0.05, gamma=0.98, n_step=2, sample_act_num=8)
+        pol.train()
+        pol.pre_update_fn()
+        torch.manual_seed(12)
+        data = {}
+        orig_sample = td.Independent.sample
+        for k in range(3):
+            d = _off_data(80 + k)
+            drawn = []
+
+            def tapped(self, sample_shape=torch.Size()):
+                out = orig_sample(self, sample_shape)
+                if len(sample_shape):
+                    drawn.append(out.detach().numpy().copy())
+                return out
+
+            td.Independent.sample = tapped
+            try:
+                pol.learn(Batch(obs=torch.from_numpy(d["obs"]), act=torch.from_numpy(d["act"]),
+                                rets=torch.from_numpy(d["rets"]), info=Batch()))
+            finally:
+                td.Independent.sample = orig_sample
+            assert len(drawn) == 1 and drawn[0].shape == (8, BS, A)
+            for kk, v in d.items():
+                data[f"{kk}{k}"] = v
+            data[f"particles{k}"] = drawn[0]
+        final = _state(_mods(actor, critics) + [(f"critics_old.{i}", c) for i, c in enumerate(pol.critics_old)])
+        final["estep_dual"] = pol.estep_dual.detach().numpy().copy()
+        cases[name] = dict(kw={}, lag=0.0, data=data, init=init, final=final, stats=log.rows,
+                           extra=dict(double=float(double), qc_thres=pol.qc_thres[0]))
+    return cases
+
+
 def golden_exports():
     """The reference packages' ``__all__`` lists."""
     import importlib
@@ -777,6 +837,7 @@ if __name__ == "__main__":
     _save("policy_focops_golden.npz", golden_focops(B))
     _save("policy_sac_golden.npz", golden_sac(B))
     _save("policy_ddpg_golden.npz", golden_ddpg(B))
+    _save("policy_cvpo_golden.npz", golden_cvpo(B))
     _save("policy_returns_glue_golden.npz", golden_returns_glue(B))
     _save("collector_golden.npz", golden_collector())
     golden_trainers()

@@ -714,3 +714,58 @@ def test_public_attributes_and_safety_loss_match_reference(golden_dir):
         assert set(st) == set(c["stats"])
         for k, v in c["stats"].items():
             assert float(st[k]) == pytest.approx(v, rel=1e-6, abs=1e-9), k
+
+
+@pytest.mark.parametrize("case", ["single", "double"])
+def test_cvpo_oracle_replays_reference_learn(golden_dir, case):
+    """Groundwork for SURVEY 8(f4): oracle/cvpo.py reproduces three consecutive CVPO.learn() calls of the reference
+    (critic regression, E-step dual Adam + softmax weights over the recorded action particles, M-step with the
+    decoupled KL multipliers, Polyak targets) -- SingleCritic and DoubleCritic variants."""
+    from oracle import cvpo as ocvpo, nets as onets
+    g = _load_policy_golden(golden_dir, "policy_cvpo_golden.npz")[case]
+    d, init = g["data"], {k: torch.from_numpy(v) for k, v in g["init"].items()}
+    D, A = d["obs0"].shape[1], d["act0"].shape[1]
+    H = g["init"]["actor.mu.model.0.weight"].shape[1]
+    double = bool(g["double"])
+
+    def build():
+        actor = onets.load_from_state_dict(onets.GaussActor(D, A, [H, H], conditioned_sigma=True), init, "actor.")
+        if double:
+            crit = [[_load_q(onets.ValueNet(D + A, [H, H]), init, f"critics.{i}.", k) for k in (1, 2)] for i in range(2)]
+        else:
+            crit = [_load_q(onets.ValueNet(D + A, [H, H]), init, f"critics.{i}.") for i in range(2)]
+        return actor, crit
+
+    actor, crit = build()
+    actor_old, crit_old = build()
+    flat = lambda cs: [p for c in cs for q in (c if isinstance(c, list) else [c]) for p in q.parameters()]
+    a_opt = torch.optim.Adam(actor.parameters(), lr=5e-4)
+    c_opt = torch.optim.Adam(flat(crit), lr=1e-3)
+    estep_dual = torch.tensor([1.0, 0.0], requires_grad=True, dtype=torch.float32)
+    e_opt = torch.optim.Adam([estep_dual], lr=0.02)
+    mduals = (torch.zeros(1, requires_grad=True), torch.zeros(1, requires_grad=True))      # pre_update_fn (:172-181)
+    m_opt = torch.optim.Adam(list(mduals), lr=0.1)
+    stats = []
+    for k in range(3):
+        t = lambda name: torch.from_numpy(d[f"{name}{k}"])
+        stats.append(ocvpo.cvpo_update(actor, actor_old, crit, crit_old, a_opt, c_opt, estep_dual, e_opt, mduals, m_opt,
+                                       t("obs"), t("act"), t("rets"), t("particles"), qc_thres=[g["qc_thres"]], tau=0.05))
+    assert g["qc_thres"] == pytest.approx(ocvpo.qc_thresholds(10.0, 0.98, 300)[0], rel=1e-12)
+    ref = g["stats"]
+    keys = ["loss/loss_q0", "loss/loss_q1", "loss/q_total", "loss/estep_loss", "estep/dual0", "estep/dual1",
+            "estep/val_q0", "estep/val_q1", "mstep/mstep_kl_mu", "mstep/mstep_kl_std", "mstep/mstep_loss_mle",
+            "mstep/mstep_loss_kl", "mstep/mstep_loss_total", "mstep/mstep_dual_mu", "mstep/mstep_dual_std", "mstep/entropy"]
+    _cmp_stats(stats, ref, keys, rtol=5e-5, atol=1e-6)
+    final = g["final"]
+    np.testing.assert_allclose(estep_dual.detach().numpy(), final["estep_dual"], rtol=1e-5, atol=1e-7)
+    for key, p in (("actor.mu.model.0.weight", actor.mu.weight), ("actor.sigma.model.0.weight", actor.sigma.weight),
+                   ("actor.preprocess.model.model.2.weight", actor.body.layers[1].weight)):
+        assert np.abs(p.detach().numpy() - final[key]).max() <= 5e-6, key
+    for i in range(2):
+        if double:
+            for k in (1, 2):
+                _assert_q(final, f"critics.{i}.", crit[i][k - 1], k, 5e-6)
+                _assert_q(final, f"critics_old.{i}.", crit_old[i][k - 1], k, 5e-6)
+        else:
+            _assert_q(final, f"critics.{i}.", crit[i], None, 5e-6)
+            _assert_q(final, f"critics_old.{i}.", crit_old[i], None, 5e-6)
