@@ -24,6 +24,8 @@
 //   out-major mirror (needed by the backward GEMM) are written coalesced.
 #include "mlp.cuh"
 #include "fsrl_b200.h"
+#include "ppo_persist.cuh"
+#include <cstdlib>
 
 namespace fsrl {
 
@@ -1227,6 +1229,13 @@ extern "C" size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax) {
     return (size_t)n_nets * (size_t)bmax * (4 * (size_t)H + DOUT_LD);
 }
 
+extern "C" size_t fsrl_ppo_persist_ws_floats(int n_nets, int D, int H) { return ppo_persist_ws_floats(n_nets, D, H); }
+
+extern "C" int fsrl_ppo_persist_active(const fsrl_ppo_update_t* u, long long n_total, int batch_size) {
+    if (!u || u->persist_off || getenv("FSRL_PPO_NO_PERSIST")) return 0;
+    return ppo_persist_supported(*u, n_total, batch_size) ? 1 : 0;
+}
+
 extern "C" int fsrl_ppo_sync_mirror(const fsrl_ppo_update_t* u, void* stream) {
     int rc = check_update(u);
     if (rc) return rc;
@@ -1286,6 +1295,17 @@ extern "C" int fsrl_ppo_lag_epoch(const fsrl_ppo_update_t* u, long long n_total,
         FSRL_REQUIRE(u->mb_stats != nullptr, "ppo: mb_stats buffer missing");
         ppo_adv_stats_kernel<<<n_mb, 256, 0, s>>>(*u, n_total, n_mb);
         FSRL_LAUNCH_CHECK();
+    }
+    if (!u->persist_off && !getenv("FSRL_PPO_NO_PERSIST") && ppo_persist_supported(*u, n_total, batch_size)) {
+        // one persistent launch runs every minibatch of the repeat (csrc/ppo_persist.cu); the out-major
+        // mirror of W2 that the three-launch chain reads is refreshed afterwards
+        const int n_mb = (int)(n_total / batch_size);
+        int rcp = ppo_persist_run(*u, n_mb, stats_slot0, adam_t0, s);
+        if (rcp) return rcp;
+        mirror_w2_kernel<<<u->n_nets * (u->H / 32) * (u->H / 32), 256, 0, s>>>(*u);
+        FSRL_LAUNCH_CHECK();
+        if (n_minibatches) *n_minibatches = n_mb;
+        return FSRL_OK;
     }
     for (long long off = 0; off < n_total; off += batch_size) {
         long long B = batch_size;

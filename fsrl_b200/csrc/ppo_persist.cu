@@ -1,0 +1,737 @@
+// Persistent PPO-Lagrangian update: ONE launch per repeat runs every minibatch step of
+// /root/reference/fsrl/policy/ppo_lag.py:223-247 (forward, clipped-surrogate + lambda * cost-advantage
+// loss and value losses :152-212, lagrangian_base.py:145-166, backward, clip_grad_norm_, Adam) on a
+// co-resident grid of 32 CTAs per network.  Blackwell-native data path: the three 256^3 GEMMs of a
+// network and step run on tcgen05 tensor cores (kind::tf32, fp32-faithful 3-term split, accumulators
+// in tensor memory), operands arrive as bulk asynchronous copies (TMA unit) of pre-split "plane
+// layout" images that the producing CTAs write straight from their epilogues, and the CTAs of a
+// step are chained by device-scope release/acquire counters instead of kernel launches.
+//
+// Work decomposition of one network (H = 256, minibatch = 256 rows = 4 row blocks of 64):
+//   CTA c = 8 a + b           a = row block (4), b = 32-wide column block (8)
+//   S   h1 tile   [64 r x 32 k]   FFMA (K = D)            -> images H1A (MN = r, K = k), H1T (MN = k, K = r)
+//   G1  h2 tile   [64 r x 32 o] = h1[r, :] W2t[:, o]      A = H1A block a, B = W2A block b      (tcgen05)
+//       head partial over the tile's 32 columns -> 8 partials per row block -> loss gradient dOut
+//       dz2 tile = (dOut W3^T) * relu'(h2)                -> images DZA (MN = r, K = o), DZT (MN = o, K = r)
+//   G2  (CTAs 0-15: ka = c / 4, rb = c % 4)  dh1^T tile [64 k x 64 r] = W2t[k, :] dz2[r, :]^T
+//       A = W2B block ka, B = DZA block rb;  * relu'(h1) -> partial dW1 / db1 over the 64 rows
+//   G3  (CTAs 16-31: ka, ob = c % 4)         dW2^T tile [64 o x 64 k] = dz2[:, o]^T h1[:, k]
+//       A = DZT block ob, B = H1T block ka;  the CTA owns this tile of W2: Adam state (p, m, v) lives in
+//       tensor memory for the whole launch, the updated tile is re-published as images W2A / W2B
+//   small parameters (W1, b1, b2, W3, b3, log sigma): every CTA keeps the slices it consumes (+ their
+//       Adam moments) in shared memory and applies the identical update to them (deterministic
+//       replicas); gradients are fixed-order sums of per-row-block partials.
+//   global-norm clip: per-CTA sums of squares -> one device-wide counter hop -> every CTA adds the
+//       96 partials in the same order.
+// All operand images are K-major SWIZZLE_NONE plane images (umma.cuh); transposed copies are written
+// by the producer (MN-major tf32 operands would need the 128B_BASE32B swizzle).
+#include "ppo_persist.cuh"
+#include "umma.cuh"
+
+namespace fsrl {
+namespace pp {
+
+using namespace umma;
+
+constexpr int TPB = 192;                 // warp 0: copy producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int NEPI = 128;
+constexpr int RB = 64;                   // rows per row block
+constexpr int MB = 256;                  // rows per minibatch
+constexpr int SLOT_BYTES = 65536, NSLOT = 3;
+constexpr int OUTP = 8;                  // padded head width
+constexpr int H_ = 256;
+constexpr int IMG = 65536;               // floats per image (256 x 256)
+enum { I_H1A_HI, I_H1A_LO, I_H1T_HI, I_H1T_LO, I_DZA_HI, I_DZA_LO, I_DZT_HI, I_DZT_LO, I_W2A_HI, I_W2A_LO, I_W2B_HI, I_W2B_LO, N_IMG };
+// per-network partial buffers (floats)
+constexpr int HEADP_OFF = N_IMG * IMG;                          // [4 a][8 b][64 r][OUTP]
+constexpr int DB2P_OFF = HEADP_OFF + 4 * 8 * 64 * OUTP;         // [4 a][H]
+constexpr int DW3P_OFF = DB2P_OFF + 4 * H_;                     // [4 a][H][OUTP]
+constexpr int DB3P_OFF = DW3P_OFF + 4 * H_ * OUTP;              // [4 a][16]
+constexpr int DW1P_OFF = DB3P_OFF + 4 * 16;                     // [4 rb][MAXD + 1][H]
+constexpr int MAXD = 40;
+constexpr int NET_WS = DW1P_OFF + 4 * (MAXD + 1) * H_;
+constexpr int SUMSQ_FLOATS = 128;                               // global tail: per-CTA sums of squares
+// flag lines (32 unsigned each): per net A, C, D1, B[4]; global D2
+constexpr int FLAG_LINE = 32;
+constexpr int F_A = 0, F_C = 1, F_D1 = 2, F_B = 3, F_PER_NET = 7;
+constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,32) accumulators, Adam state
+constexpr long long WAIT_CYCLES = 6000000000LL;                  // ~3 s: a lost partner must not hang the GPU
+
+constexpr int ST_ACTOR_REW = 0, ST_ACTOR_SAFETY = 1, ST_KL = 2, ST_VF0 = 3, ST_ENTROPY = 5, ST_GRADNORM = 6;
+constexpr float LOG_SQRT_2PI = 0.9189385332046727f;
+
+struct Args {
+    fsrl_ppo_update_t u;     // batch pointers already gathered (contiguous rows, u.perm == nullptr)
+    int n_mb, slot0;
+    long long adam_t0;
+    float* ws;
+    unsigned* flags;
+    int* err;
+};
+
+struct AdamS { float w1, b2, w2, bc2s, eps, neg_step; };
+__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamS& a) {
+    m = m + a.w1 * (g - m);                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * a.b2 + (a.w2 * g) * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / a.bc2s + a.eps;
+    return p + (a.neg_step * m) / denom;    // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__device__ __forceinline__ void fail(int* err, int code) {
+    *reinterpret_cast<volatile int*>(err) = code;
+    __threadfence_system();
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// sum over the 16 lanes of a half-warp (lanes l and l ^ 16 hold different data)
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// layout of the small-parameter slices a CTA keeps in shared memory (floats)
+struct SliceMap {
+    int w1, b2, w3, b3, n;     // w1: [(D+1)][32] (row D = b1), b2: [32], w3: [32][OUTP], b3: [16] (b3 | log sigma at 8)
+    __device__ __host__ SliceMap(int D) { w1 = 0; b2 = (D + 1) * 32; w3 = b2 + 32; b3 = w3 + 32 * OUTP; n = b3 + 16; }
+};
+
+__global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[4][64];           // cross-subpartition partial sums
+    __shared__ float s_misc[32];
+    __shared__ AdamS s_adam;
+    const fsrl_ppo_update_t& u = P.u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int net = blockIdx.x >> 5, c = blockIdx.x & 31, a = c >> 3, b = c & 7;
+    const bool is_g2 = c < 16;
+    const int ka = (c & 15) >> 2, q4 = c & 3;      // G2: (k block, row block) ; G3: (k block, o block)
+    const int D = u.D, A = u.A, C = u.C, H = H_;
+    const int out = (net == 0) ? A : 1;
+    const int n_cta = gridDim.x;
+    float* wsn = P.ws + (size_t)net * NET_WS;
+    float* sumsq_g = P.ws + (size_t)u.n_nets * NET_WS;
+    unsigned* fl_net = P.flags + (size_t)net * F_PER_NET * FLAG_LINE;
+    unsigned* fl_d2 = P.flags + (size_t)u.n_nets * F_PER_NET * FLAG_LINE;
+    unsigned char* ring = smem_raw;
+    float* small = reinterpret_cast<float*>(smem_raw + NSLOT * SLOT_BYTES);
+    const SliceMap sm(D);
+    float* sp_p = small;                 // parameters
+    float* sp_m = small + sm.n;          // Adam first moment
+    float* sp_v = small + 2 * sm.n;      // Adam second moment
+    float* sp_g = small + 3 * sm.n;      // reduced gradient of the current step
+
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        mbar_init(&bar_acc, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<TM_COLS>(&s_tmem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    // parameter offsets of this network inside the flat arena
+    const long long pbase = u.net_off[net];
+    const long long o_w1 = pbase, o_b1 = o_w1 + (long long)D * H, o_w2 = o_b1 + H, o_b2 = o_w2 + (long long)H * H,
+                    o_w3 = o_b2 + H, o_b3 = o_w3 + (long long)H * out, o_ls = o_b3 + out;
+
+    if (warp == 0) {
+        // ============================ bulk-copy producer ==========================================
+        if (lane == 0) {
+            unsigned qq = 0;
+            for (int t = 0; t < P.n_mb; ++t) {
+                if (!flag_wait_ge(fl_net + F_A * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 10);
+                fence_proxy_async();
+                for (int j = 0; j < 4; ++j, ++qq) {               // G1: K = k in chunks of 64
+                    const int s = qq % NSLOT;
+                    if (!mbar_wait(&bar_empty[s], ((qq / NSLOT) & 1) ^ 1, WAIT_CYCLES)) fail(P.err, 11);
+                    unsigned char* dst = ring + (size_t)s * SLOT_BYTES;
+                    mbar_expect_tx(&bar_full[s], 49152);
+                    const size_t ao = (size_t)a * 16384 + (size_t)j * 4096, bo = (size_t)b * 8192 + (size_t)j * 2048;
+                    bulk_g2s(dst, wsn + (size_t)I_H1A_HI * IMG + ao, 16384, &bar_full[s]);
+                    bulk_g2s(dst + 16384, wsn + (size_t)I_H1A_LO * IMG + ao, 16384, &bar_full[s]);
+                    bulk_g2s(dst + 32768, wsn + (size_t)I_W2A_HI * IMG + bo, 8192, &bar_full[s]);
+                    bulk_g2s(dst + 40960, wsn + (size_t)I_W2A_LO * IMG + bo, 8192, &bar_full[s]);
+                }
+                if (!flag_wait_ge(fl_net + F_C * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 12);
+                fence_proxy_async();
+                const int ia = is_g2 ? I_W2B_HI : I_DZT_HI, ib = is_g2 ? I_DZA_HI : I_H1T_HI;
+                const int blk_a = is_g2 ? ka : q4, blk_b = is_g2 ? q4 : ka;
+                for (int j = 0; j < 4; ++j, ++qq) {               // G2: K = o ; G3: K = r ; chunks of 64
+                    const int s = qq % NSLOT;
+                    if (!mbar_wait(&bar_empty[s], ((qq / NSLOT) & 1) ^ 1, WAIT_CYCLES)) fail(P.err, 13);
+                    unsigned char* dst = ring + (size_t)s * SLOT_BYTES;
+                    mbar_expect_tx(&bar_full[s], 65536);
+                    const size_t ao = (size_t)blk_a * 16384 + (size_t)j * 4096, bo = (size_t)blk_b * 16384 + (size_t)j * 4096;
+                    bulk_g2s(dst, wsn + (size_t)ia * IMG + ao, 16384, &bar_full[s]);
+                    bulk_g2s(dst + 16384, wsn + (size_t)(ia + 1) * IMG + ao, 16384, &bar_full[s]);
+                    bulk_g2s(dst + 32768, wsn + (size_t)ib * IMG + bo, 16384, &bar_full[s]);
+                    bulk_g2s(dst + 49152, wsn + (size_t)(ib + 1) * IMG + bo, 16384, &bar_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ==================================================
+        if (lane == 0) {
+            unsigned qq = 0;
+            const uint32_t ring_a = smem_u32(ring);
+            const uint32_t id16 = idesc_tf32(64, 16, false, false), id32 = idesc_tf32(64, 32, false, false);
+            for (int t = 0; t < P.n_mb; ++t) {
+                for (int j = 0; j < 4; ++j, ++qq) {               // ---- G1: D[64 r][32 o], two 16-column halves
+                    const int s = qq % NSLOT;
+                    if (!mbar_wait(&bar_full[s], (qq / NSLOT) & 1, WAIT_CYCLES)) fail(P.err, 20);
+                    tc_fence_after();
+                    const uint32_t base = ring_a + (uint32_t)s * SLOT_BYTES;
+#pragma unroll 2
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t ah = smem_desc(base + ks * 2048, 1024, 128);
+                        const uint64_t al = smem_desc(base + 16384 + ks * 2048, 1024, 128);
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint64_t bh = smem_desc(base + 32768 + ks * 1024 + sub * 256, 512, 128);
+                            const uint64_t bl = smem_desc(base + 40960 + ks * 1024 + sub * 256, 512, 128);
+                            const uint32_t d = tmem + ((uint32_t)(16 * sub) << 16);
+                            mma_tf32_ss(d, al, bh, id16, (j | ks) != 0);
+                            mma_tf32_ss(d, ah, bl, id16, true);
+                            mma_tf32_ss(d, ah, bh, id16, true);
+                        }
+                    }
+                    mma_commit(&bar_empty[s]);
+                }
+                mma_commit(&bar_acc);
+                for (int j = 0; j < 4; ++j, ++qq) {               // ---- G2 / G3: D[64][64], two 32-column halves
+                    const int s = qq % NSLOT;
+                    if (!mbar_wait(&bar_full[s], (qq / NSLOT) & 1, WAIT_CYCLES)) fail(P.err, 21);
+                    tc_fence_after();
+                    const uint32_t base = ring_a + (uint32_t)s * SLOT_BYTES;
+#pragma unroll 2
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t ah = smem_desc(base + ks * 2048, 1024, 128);
+                        const uint64_t al = smem_desc(base + 16384 + ks * 2048, 1024, 128);
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint64_t bh = smem_desc(base + 32768 + ks * 2048 + sub * 512, 1024, 128);
+                            const uint64_t bl = smem_desc(base + 49152 + ks * 2048 + sub * 512, 1024, 128);
+                            const uint32_t d = tmem + ((uint32_t)(16 * sub) << 16);
+                            mma_tf32_ss(d, al, bh, id32, (j | ks) != 0);
+                            mma_tf32_ss(d, ah, bl, id32, true);
+                            mma_tf32_ss(d, ah, bh, id32, true);
+                        }
+                    }
+                    mma_commit(&bar_empty[s]);
+                }
+                mma_commit(&bar_acc);
+            }
+        }
+    } else {
+        // ============================ epilogue warps ===============================================
+        const int et = tid - 64;                    // 0..127
+        const int sp = warp & 3;                    // tensor-memory subpartition of this warp
+        const int r16 = lane & 15, half = lane >> 4;
+        const int trow = 16 * sp + r16;             // row of the 64-row tile held by this lane
+        const uint32_t tm_lane = tmem + ((uint32_t)(32 * sp) << 16);
+        float* stat_base = u.stats;
+
+        // ---- initial state: small slices from the arena, the W2 tile (p, m, v) into tensor memory ----
+        for (int i = et; i < sm.n; i += NEPI) {
+            long long src = -1;
+            if (i < sm.b2) { const int d = i / 32, kk = i % 32; src = (d < D) ? o_w1 + (long long)d * H + 32 * b + kk : o_b1 + 32 * b + kk; }
+            else if (i < sm.w3) src = o_b2 + 32 * b + (i - sm.b2);
+            else if (i < sm.b3) { const int oo = (i - sm.w3) / OUTP, jj = (i - sm.w3) % OUTP; if (jj < out) src = o_w3 + (long long)(32 * b + oo) * out + jj; }
+            else { const int jj = i - sm.b3; if (jj < out) src = o_b3 + jj; else if (net == 0 && u.head_indep && jj >= 8 && jj < 8 + A) src = o_ls + (jj - 8); }
+            sp_p[i] = src >= 0 ? u.theta[src] : 0.f;
+            sp_m[i] = src >= 0 ? u.adam_m[src] : 0.f;
+            sp_v[i] = src >= 0 ? u.adam_v[src] : 0.f;
+            sp_g[i] = 0.f;
+        }
+        if (!is_g2) {
+            const int o = 64 * q4 + trow;
+            float pv[32], mv[32], vv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const long long idx = o_w2 + (long long)(64 * ka + 32 * half + j) * H + o;
+                pv[j] = u.theta[idx]; mv[j] = u.adam_m[idx]; vv[j] = u.adam_v[idx];
+            }
+            tmem_st32(tm_lane + TM_P, pv); tmem_st32(tm_lane + TM_M, mv); tmem_st32(tm_lane + TM_V, vv);
+        }
+        epi_bar();
+
+        unsigned acc_phase = 0;
+        for (int t = 0; t < P.n_mb; ++t) {
+            const long long row0 = (long long)t * MB;                 // first row of the minibatch in the gathered arrays
+            const int slot = P.slot0 + t;
+            if (et == 0) {   // Adam scalars of this step (torch.optim.Adam: python doubles -> f32 at the op)
+                const double tt = (double)(P.adam_t0 + t + 1);
+                const double bc1 = 1.0 - pow(u.beta1, tt), bc2 = 1.0 - pow(u.beta2, tt);
+                s_adam.w1 = (float)(1.0 - u.beta1); s_adam.b2 = (float)u.beta2; s_adam.w2 = (float)(1.0 - u.beta2);
+                s_adam.bc2s = (float)sqrt(bc2); s_adam.eps = (float)u.adam_eps; s_adam.neg_step = (float)(-(u.lr / bc1));
+            }
+            // rows of the NEXT minibatch towards L2 while this one is processed
+            if (t + 1 < P.n_mb && et < 64) {
+                const long long r = row0 + MB + 64 * a + et;
+                prefetch_l2(u.obs + r * D);
+                if (D > 32) prefetch_l2(u.obs + r * D + 32);
+                if (net == 0) { prefetch_l2(u.act + r * A); prefetch_l2(u.logp_old + r); prefetch_l2(u.adv + r); if (C > 1) prefetch_l2(u.adv + u.ld + r); }
+                else { prefetch_l2(u.ret + (long long)(net - 1) * u.ld + r); if (u.value_clip) prefetch_l2(u.values + (long long)(net - 1) * u.ld + r); }
+            }
+            // ---- S(a): publish the images of the owned W2 tile (from tensor memory) ------------------
+            if (!is_g2) {
+                float pv[32];
+                tmem_ld32(tm_lane + TM_P, pv);
+                const int o = 64 * q4 + trow;                   // output unit of this lane
+                float* w2a_hi = wsn + (size_t)I_W2A_HI * IMG + (size_t)(o >> 5) * 8192 + (size_t)(o & 31) * 4;
+                float* w2a_lo = w2a_hi + IMG;
+                float* w2b_hi = wsn + (size_t)I_W2B_HI * IMG + (size_t)ka * 16384 + (size_t)(o >> 2) * 256 + (o & 3);
+                float* w2b_lo = w2b_hi + IMG;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {                   // k = 64 ka + 32 half + 4 q + (0..3)
+                    float4 hi, lo;
+                    tf32_split(pv[4 * q], hi.x, lo.x); tf32_split(pv[4 * q + 1], hi.y, lo.y);
+                    tf32_split(pv[4 * q + 2], hi.z, lo.z); tf32_split(pv[4 * q + 3], hi.w, lo.w);
+                    const size_t plane = (size_t)(16 * ka + 8 * half + q) * 128;
+                    *reinterpret_cast<float4*>(w2a_hi + plane) = hi;
+                    *reinterpret_cast<float4*>(w2a_lo + plane) = lo;
+                    const int kl = 32 * half + 4 * q;           // k within the 64-block
+                    w2b_hi[(size_t)kl * 4] = hi.x; w2b_hi[(size_t)(kl + 1) * 4] = hi.y; w2b_hi[(size_t)(kl + 2) * 4] = hi.z; w2b_hi[(size_t)(kl + 3) * 4] = hi.w;
+                    w2b_lo[(size_t)kl * 4] = lo.x; w2b_lo[(size_t)(kl + 1) * 4] = lo.y; w2b_lo[(size_t)(kl + 2) * 4] = lo.z; w2b_lo[(size_t)(kl + 3) * 4] = lo.w;
+                }
+            }
+            // ---- S(b): h1 tile [64 rows of block a][32 columns of block b] ----------------------------
+            {
+                const int r = et & 63, kh = et >> 6;            // row, 16-column half
+                const float* x = u.obs + (row0 + 64 * a + r) * D;
+                float acc[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = sp_p[sm.w1 + D * 32 + 16 * kh + j];      // b1
+                for (int d = 0; d < D; ++d) {
+                    const float xv = __ldg(x + d);
+                    const float* w = sp_p + sm.w1 + d * 32 + 16 * kh;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, w[j], acc[j]);
+                }
+                const int rg = 64 * a + r;                      // row within the minibatch
+                float* a_hi = wsn + (size_t)I_H1A_HI * IMG + (size_t)a * 16384 + (size_t)r * 4;
+                float* t_hi = wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384 + (size_t)(rg >> 2) * 256 + (rg & 3);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 hi, lo;
+                    tf32_split(fmaxf(acc[4 * q], 0.f), hi.x, lo.x); tf32_split(fmaxf(acc[4 * q + 1], 0.f), hi.y, lo.y);
+                    tf32_split(fmaxf(acc[4 * q + 2], 0.f), hi.z, lo.z); tf32_split(fmaxf(acc[4 * q + 3], 0.f), hi.w, lo.w);
+                    const size_t plane = (size_t)(8 * b + 4 * kh + q) * 256;
+                    *reinterpret_cast<float4*>(a_hi + plane) = hi;
+                    *reinterpret_cast<float4*>(a_hi + IMG + plane) = lo;
+                    const int kl = 32 * (b & 1) + 16 * kh + 4 * q;     // column within the 64-block of H1T
+                    t_hi[(size_t)kl * 4] = hi.x; t_hi[(size_t)(kl + 1) * 4] = hi.y; t_hi[(size_t)(kl + 2) * 4] = hi.z; t_hi[(size_t)(kl + 3) * 4] = hi.w;
+                    float* t_lo = t_hi + IMG;
+                    t_lo[(size_t)kl * 4] = lo.x; t_lo[(size_t)(kl + 1) * 4] = lo.y; t_lo[(size_t)(kl + 2) * 4] = lo.z; t_lo[(size_t)(kl + 3) * 4] = lo.w;
+                }
+            }
+            epi_bar();
+            if (et == 0) flag_add_release(fl_net + F_A * FLAG_LINE);
+
+            // per-row loss inputs (independent of the GEMM): issued now, consumed after the head
+            const long long grow = row0 + 64 * a + trow;
+            float p_act[8], p_lpo = 0.f, p_adv0 = 0.f, p_adv1 = 0.f, p_ret = 0.f, p_val = 0.f, mean0 = 0.f, rstd0 = 1.f, mean1 = 0.f, rstd1 = 1.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p_act[j] = 0.f;
+            if (net == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < A) p_act[j] = __ldg(u.act + grow * A + j);
+                p_lpo = __ldg(u.logp_old + grow);
+                p_adv0 = __ldg(u.adv + grow);
+                if (C > 1) p_adv1 = __ldg(u.adv + u.ld + grow);
+                const float* ms = u.mb_stats + (size_t)t * 4;
+                mean0 = __ldg(ms); rstd0 = __ldg(ms + 1); mean1 = __ldg(ms + 2); rstd1 = __ldg(ms + 3);
+            } else {
+                p_ret = __ldg(u.ret + (long long)(net - 1) * u.ld + grow);
+                if (u.value_clip) p_val = __ldg(u.values + (long long)(net - 1) * u.ld + grow);
+            }
+
+            // ---- G1 epilogue: h2 = relu(acc + b2), head partial over this tile's 32 columns -------------
+            if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 30);
+            ++acc_phase;
+            tc_fence_after();
+            float h2[16];
+            tmem_ld16(tm_lane, h2);
+            float hp[OUTP];
+#pragma unroll
+            for (int j = 0; j < OUTP; ++j) hp[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                h2[j] = fmaxf(h2[j] + sp_p[sm.b2 + 16 * half + j], 0.f);
+                const float* w = sp_p + sm.w3 + (16 * half + j) * OUTP;
+#pragma unroll
+                for (int jj = 0; jj < OUTP; ++jj) hp[jj] = fmaf(h2[j], w[jj], hp[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < OUTP; ++jj) hp[jj] += __shfl_xor_sync(0xffffffffu, hp[jj], 16);
+            if (half == 0) {
+                float* dst = wsn + HEADP_OFF + ((size_t)(a * 8 + b) * 64 + trow) * OUTP;
+                *reinterpret_cast<float4*>(dst) = make_float4(hp[0], hp[1], hp[2], hp[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(hp[4], hp[5], hp[6], hp[7]);
+            }
+            tc_fence_before();
+            epi_bar();
+            if (et == 0) {
+                flag_add_release(fl_net + (F_B + a) * FLAG_LINE);
+                if (!flag_wait_ge(fl_net + (F_B + a) * FLAG_LINE, 8u * (t + 1), WAIT_CYCLES)) fail(P.err, 31);
+            }
+            epi_bar();
+            float outv[OUTP];
+#pragma unroll
+            for (int jj = 0; jj < OUTP; ++jj) outv[jj] = sp_p[sm.b3 + jj];
+#pragma unroll
+            for (int bb = 0; bb < 8; ++bb) {
+                const float* src = wsn + HEADP_OFF + ((size_t)(a * 8 + bb) * 64 + trow) * OUTP;
+                const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src));
+                const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                outv[0] += v0.x; outv[1] += v0.y; outv[2] += v0.z; outv[3] += v0.w;
+                outv[4] += v1.x; outv[5] += v1.y; outv[6] += v1.z; outv[7] += v1.w;
+            }
+            // ---- loss gradient at the head (ppo_lag.py:152-212): dd[j] = d loss / d head_j --------------
+            float dd[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dd[j] = 0.f;
+            float st_a = 0.f, st_b = 0.f, st_c = 0.f, st_d = 0.f;
+            {
+                const float invB = 1.0f / (float)MB;
+                if (net == 0) {
+                    float logp = 0.f, zz[8], sg[8], dmu[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        zz[j] = sg[j] = dmu[j] = 0.f;
+                        if (j < A) {
+                            const float ls = sp_p[sm.b3 + 8 + j];
+                            const float tnh = tanhf(outv[j]);
+                            const float mu = u.bounded ? u.max_action * tnh : outv[j];
+                            dmu[j] = u.bounded ? u.max_action * (1.0f - tnh * tnh) : 1.0f;
+                            sg[j] = expf(ls);
+                            zz[j] = (p_act[j] - mu) / sg[j];
+                            logp += -0.5f * zz[j] * zz[j] - ls - LOG_SQRT_2PI;
+                        }
+                    }
+                    const float ratio = expf(logp - p_lpo);
+                    const float ar = (p_adv0 - mean0) * rstd0;
+                    const float surr1 = ratio * ar;
+                    const float rc = fminf(fmaxf(ratio, 1.0f - u.eps_clip), 1.0f + u.eps_clip);
+                    const float surr2 = rc * ar;
+                    const bool inside = (ratio >= 1.0f - u.eps_clip) && (ratio <= 1.0f + u.eps_clip);
+                    float g_ratio, lrew;
+                    if (surr1 < surr2) { g_ratio = -ar; lrew = -surr1; }
+                    else if (surr1 > surr2) { g_ratio = inside ? -ar : 0.f; lrew = -surr2; }
+                    else { g_ratio = inside ? -ar : -0.5f * ar; lrew = -surr1; }
+                    if (u.dual_clip > 0.f && ar < 0.f) {
+                        const float c1 = fminf(surr1, surr2), c2 = u.dual_clip * ar;
+                        if (c2 > c1) { g_ratio = 0.f; lrew = -c2; }
+                        else if (c2 == c1) { g_ratio *= 0.5f; }
+                    }
+                    float g_saf = 0.f, lsaf = 0.f;
+                    if (u.use_lagrangian && C > 1) {
+                        const float ac = (p_adv1 - mean1) * rstd1;
+                        g_saf = ac * u.lagrangian;
+                        lsaf = ratio * ac * u.lagrangian;
+                    }
+                    const float gl = u.rescaling * (g_ratio + g_saf) * ratio * invB;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < A) {
+                            dd[j] = gl * (zz[j] / sg[j]) * dmu[j];
+                            dd[8 + j] = gl * (zz[j] * zz[j] - 1.0f);
+                        }
+                    }
+                    st_a = lrew * invB; st_b = lsaf * invB; st_c = (p_lpo - logp) * invB;
+                } else {
+                    const float v = outv[0], ret = p_ret;
+                    float lv, gv;
+                    if (u.value_clip) {
+                        const float vt = p_val;
+                        const float dv = fminf(fmaxf(v - vt, -u.eps_clip), u.eps_clip);
+                        const float vc = vt + dv;
+                        const float vf1 = (ret - v) * (ret - v), vf2 = (ret - vc) * (ret - vc);
+                        const bool in_clip = (v - vt > -u.eps_clip) && (v - vt < u.eps_clip);
+                        if (vf1 > vf2) { lv = vf1; gv = 2.0f * (v - ret); }
+                        else if (vf1 < vf2) { lv = vf2; gv = in_clip ? 2.0f * (vc - ret) : 0.f; }
+                        else { lv = vf1; gv = in_clip ? 2.0f * (v - ret) : (v - ret); }
+                    } else {
+                        lv = (ret - v) * (ret - v);
+                        gv = 2.0f * (v - ret);
+                    }
+                    dd[0] = u.vf_coef * gv * invB;
+                    st_d = lv * invB;
+                }
+            }
+            // ---- dz2 tile = (dOut W3^T) * relu'(h2): images DZA / DZT; partial db2, dW3, db3 ----------------
+            const int nfeed = (net == 0) ? A : 1;              // head columns that feed W3 (mu only)
+            float dz[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float* w = sp_p + sm.w3 + (16 * half + j) * OUTP;
+                float g = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < OUTP; ++jj) if (jj < nfeed) g = fmaf(dd[jj], w[jj], g);
+                dz[j] = h2[j] > 0.f ? g : 0.f;
+            }
+            {
+                const int rg = 64 * a + trow;
+                float* a_hi = wsn + (size_t)I_DZA_HI * IMG + (size_t)a * 16384 + (size_t)trow * 4;
+                float* t_hi = wsn + (size_t)I_DZT_HI * IMG + (size_t)(b >> 1) * 16384 + (size_t)(rg >> 2) * 256 + (rg & 3);
+                float* t_lo = t_hi + IMG;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 hi, lo;
+                    tf32_split(dz[4 * q], hi.x, lo.x); tf32_split(dz[4 * q + 1], hi.y, lo.y);
+                    tf32_split(dz[4 * q + 2], hi.z, lo.z); tf32_split(dz[4 * q + 3], hi.w, lo.w);
+                    const size_t plane = (size_t)(8 * b + 4 * half + q) * 256;
+                    *reinterpret_cast<float4*>(a_hi + plane) = hi;
+                    *reinterpret_cast<float4*>(a_hi + IMG + plane) = lo;
+                    const int ol = 32 * (b & 1) + 16 * half + 4 * q;
+                    t_hi[(size_t)ol * 4] = hi.x; t_hi[(size_t)(ol + 1) * 4] = hi.y; t_hi[(size_t)(ol + 2) * 4] = hi.z; t_hi[(size_t)(ol + 3) * 4] = hi.w;
+                    t_lo[(size_t)ol * 4] = lo.x; t_lo[(size_t)(ol + 1) * 4] = lo.y; t_lo[(size_t)(ol + 2) * 4] = lo.z; t_lo[(size_t)(ol + 3) * 4] = lo.w;
+                }
+            }
+            // column sums over this subpartition's 16 rows -> s_red[sp][...]; then over the 4 subpartitions
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float sdz = half_sum(dz[j]);
+                if (r16 == 0) s_red[sp][16 * half + j] = sdz;                       // db2 partial
+            }
+            epi_bar();
+            if (et < 32) wsn[DB2P_OFF + a * H + 32 * b + et] = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
+            epi_bar();
+            for (int jj = 0; jj < nfeed; ++jj) {               // dW3[o][jj] partial = sum_r h2[r][o] dOut[r][jj]
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float sv = half_sum(h2[j] * dd[jj]);
+                    if (r16 == 0) s_red[sp][16 * half + j] = sv;
+                }
+                epi_bar();
+                if (et < 32) wsn[DW3P_OFF + ((size_t)a * H + 32 * b + et) * OUTP + jj] = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
+                epi_bar();
+            }
+            if (b == 0) {                                       // db3 | d log sigma partial, loss statistics
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float sv = half_sum(dd[j]);
+                    if (lane == 0) s_red[sp][j] = sv;
+                }
+                const float sa = half_sum(st_a), sb = half_sum(st_b), sc = half_sum(st_c), sdv = half_sum(st_d);
+                if (lane == 0) { s_red[sp][16] = sa; s_red[sp][17] = sb; s_red[sp][18] = sc; s_red[sp][19] = sdv; }
+                epi_bar();
+                if (et < 16) wsn[DB3P_OFF + a * 16 + et] = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
+                if (et >= 16 && et < 20 && stat_base) {
+                    const float tot = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
+                    float* stat = stat_base + (size_t)slot * FSRL_PPO_STATS;
+                    if (net == 0) { if (et == 16) atomicAdd(stat + ST_ACTOR_REW, tot); if (et == 17) atomicAdd(stat + ST_ACTOR_SAFETY, tot); if (et == 18) atomicAdd(stat + ST_KL, tot); }
+                    else if (et == 19) atomicAdd(stat + ST_VF0 + (net - 1), tot);
+                }
+                if (net == 0 && a == 0 && et == 20 && stat_base) {
+                    float ent = 0.f;
+                    for (int j = 0; j < A; ++j) ent += 0.5f + LOG_SQRT_2PI + sp_p[sm.b3 + 8 + j];
+                    stat_base[(size_t)slot * FSRL_PPO_STATS + ST_ENTROPY] = ent;
+                }
+            }
+            epi_bar();
+            if (et == 0) flag_add_release(fl_net + F_C * FLAG_LINE);
+
+            // ---- G2 / G3 epilogue ---------------------------------------------------------------------------
+            if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 32);
+            ++acc_phase;
+            tc_fence_after();
+            float sq = 0.f;
+            if (is_g2) {
+                // lane: k = 64 ka + trow ; rows 32 half + j of row block q4
+                float v[32];
+                tmem_ld32(tm_lane, v);
+                const int k = 64 * ka + trow;
+                const float* msk = wsn + (size_t)I_H1A_HI * IMG + (size_t)q4 * 16384 + (size_t)(k >> 2) * 256 + (k & 3);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (__ldcg(msk + (size_t)(32 * half + j) * 4) > 0.f) ? v[j] : 0.f;
+                const float* xb = u.obs + (row0 + 64 * q4 + 32 * half) * D;
+                float* dst = wsn + DW1P_OFF + (size_t)q4 * (MAXD + 1) * H + k;
+                for (int d = 0; d < D; ++d) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s = fmaf(__ldg(xb + (size_t)j * D + d), v[j], s);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (half == 0) dst[(size_t)d * H] = s;
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s += v[j];
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (half == 0) dst[(size_t)D * H] = s;            // db1
+                tc_fence_before();
+                epi_bar();
+                if (et == 0) flag_add_release(fl_net + F_D1 * FLAG_LINE);
+            } else {
+                float g[32];
+                tmem_ld32(tm_lane, g);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sq = fmaf(g[j], g[j], sq);
+            }
+            // ---- small-parameter gradients: fixed-order sums of the row-block partials -----------------------
+            if (et == 0) { if (!flag_wait_ge(fl_net + F_D1 * FLAG_LINE, 16u * (t + 1), WAIT_CYCLES)) fail(P.err, 33); }
+            epi_bar();
+            for (int i = et; i < sm.n; i += NEPI) {
+                float gsum = 0.f;
+                bool real = true;
+                if (i < sm.b2) {
+                    const int d = i / 32, kk = i % 32;
+                    const float* src = wsn + DW1P_OFF + (size_t)d * H + 32 * b + kk;
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) gsum += __ldcg(src + (size_t)rb * (MAXD + 1) * H);
+                } else if (i < sm.w3) {
+                    const float* src = wsn + DB2P_OFF + 32 * b + (i - sm.b2);
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa) gsum += __ldcg(src + aa * H);
+                } else if (i < sm.b3) {
+                    const int oo = (i - sm.w3) / OUTP, jj = (i - sm.w3) % OUTP;
+                    real = jj < out;
+                    if (real) {
+                        const float* src = wsn + DW3P_OFF + ((size_t)32 * b + oo) * OUTP + jj;
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa) gsum += __ldcg(src + (size_t)aa * H * OUTP);
+                    }
+                } else {
+                    const int jj = i - sm.b3;
+                    real = (jj < out) || (net == 0 && u.head_indep && jj >= 8 && jj < 8 + A);
+                    if (real) {
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa) gsum += __ldcg(wsn + DB3P_OFF + aa * 16 + jj);
+                    }
+                }
+                sp_g[i] = real ? gsum : 0.f;
+                // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3/log sigma by CTA 0
+                if (a == 0 && real && (i < sm.b3 || b == 0)) sq = fmaf(gsum, gsum, sq);
+            }
+            // ---- global gradient norm: per-CTA partial -> device-wide hop -> same summation order everywhere --
+            sq = warp_sum(sq);
+            if (lane == 0) s_misc[sp] = sq;
+            epi_bar();
+            if (et == 0) {
+                sumsq_g[blockIdx.x] = s_misc[0] + s_misc[1] + s_misc[2] + s_misc[3];
+                flag_add_release(fl_d2);
+                if (!flag_wait_ge(fl_d2, (unsigned)n_cta * (t + 1), WAIT_CYCLES)) fail(P.err, 34);
+            }
+            epi_bar();
+            float nsq = 0.f;
+            for (int i = lane; i < n_cta; i += 32) nsq += __ldcg(sumsq_g + i);       // identical order in every warp of the grid
+            nsq = warp_sum(nsq);
+            float gscale = 1.0f;
+            if (u.max_grad_norm > 0.f) gscale = fminf(u.max_grad_norm / (sqrtf(nsq) + 1e-6f), 1.0f);
+            if (blockIdx.x == 0 && et == 0 && stat_base) stat_base[(size_t)slot * FSRL_PPO_STATS + ST_GRADNORM] = sqrtf(nsq);
+            const AdamS ad = s_adam;
+            // ---- clip + Adam: replicated small slices, then the owned W2 tile (tensor memory) --------------------
+            for (int i = et; i < sm.n; i += NEPI) {
+                float m = sp_m[i], v = sp_v[i];
+                sp_p[i] = adam_one(sp_p[i], sp_g[i] * gscale, m, v, ad);
+                sp_m[i] = m; sp_v[i] = v;
+            }
+            if (!is_g2) {
+                float g[32], pv[32], mv[32], vv[32];
+                tmem_ld32(tm_lane, g);
+                tmem_ld32(tm_lane + TM_P, pv); tmem_ld32(tm_lane + TM_M, mv); tmem_ld32(tm_lane + TM_V, vv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pv[j] = adam_one(pv[j], g[j] * gscale, mv[j], vv[j], ad);
+                tmem_st32(tm_lane + TM_P, pv); tmem_st32(tm_lane + TM_M, mv); tmem_st32(tm_lane + TM_V, vv);
+            }
+            tc_fence_before();
+            epi_bar();     // slices final before the next h1 tile / head reads them; s_adam may be rewritten
+        }
+
+        // ---- write the parameters and Adam moments back to the arena ------------------------------------------
+        if (a == 0) {
+            for (int i = et; i < sm.n; i += NEPI) {
+                long long dst = -1;
+                if (i < sm.b2) { const int d = i / 32, kk = i % 32; dst = (d < D) ? o_w1 + (long long)d * H + 32 * b + kk : o_b1 + 32 * b + kk; }
+                else if (i < sm.w3) dst = o_b2 + 32 * b + (i - sm.b2);
+                else if (i < sm.b3) { const int oo = (i - sm.w3) / OUTP, jj = (i - sm.w3) % OUTP; if (jj < out) dst = o_w3 + (long long)(32 * b + oo) * out + jj; }
+                else if (b == 0) { const int jj = i - sm.b3; if (jj < out) dst = o_b3 + jj; else if (net == 0 && u.head_indep && jj >= 8 && jj < 8 + A) dst = o_ls + (jj - 8); }
+                if (dst >= 0) { u.theta[dst] = sp_p[i]; u.adam_m[dst] = sp_m[i]; u.adam_v[dst] = sp_v[i]; }
+            }
+        }
+        if (!is_g2) {
+            float pv[32], mv[32], vv[32];
+            tmem_ld32(tm_lane + TM_P, pv); tmem_ld32(tm_lane + TM_M, mv); tmem_ld32(tm_lane + TM_V, vv);
+            const int o = 64 * q4 + trow;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const long long idx = o_w2 + (long long)(64 * ka + 32 * half + j) * H + o;
+                u.theta[idx] = pv[j]; u.adam_m[idx] = mv[j]; u.adam_v[idx] = vv[j];
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<TM_COLS>(tmem); }
+}
+
+static size_t smem_bytes(int D) { return (size_t)NSLOT * SLOT_BYTES + 4 * sizeof(float) * SliceMap(D).n; }
+
+}  // namespace pp
+
+size_t ppo_persist_ws_floats(int n_nets, int D, int H) {
+    (void)D; (void)H;
+    return (size_t)n_nets * pp::NET_WS + pp::SUMSQ_FLOATS + (size_t)(n_nets * pp::F_PER_NET + 1) * pp::FLAG_LINE + 32;
+}
+
+bool ppo_persist_supported(const fsrl_ppo_update_t& u, long long n_total, int batch_size) {
+    if (u.H != 256 || batch_size != pp::MB || n_total % pp::MB != 0 || n_total < pp::MB) return false;
+    if (u.world > 1 || u.mask != nullptr || u.gather == nullptr) return false;
+    if (u.D < 1 || u.D > pp::MAXD || u.A > 8 || u.n_nets < 1 || u.n_nets > 3) return false;
+    if (u.persist_ws == nullptr || (size_t)u.persist_ws_floats < ppo_persist_ws_floats(u.n_nets, u.D, u.H)) return false;
+    if (32 * u.n_nets > sm_count()) return false;
+    static int smem_optin = -1;
+    if (smem_optin < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return pp::smem_bytes(u.D) + 4096 <= (size_t)smem_optin;
+}
+
+// ug: descriptor whose batch pointers are the gathered (contiguous) arrays; mb_stats filled.
+int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long long adam_t0, cudaStream_t s) {
+    pp::Args a;
+    a.u = ug;
+    a.n_mb = n_mb; a.slot0 = stats_slot0; a.adam_t0 = adam_t0;
+    a.ws = ug.persist_ws;
+    const size_t fl_off = (size_t)ug.n_nets * pp::NET_WS + pp::SUMSQ_FLOATS;
+    a.flags = reinterpret_cast<unsigned*>(ug.persist_ws + fl_off);
+    const size_t n_flag_words = (size_t)(ug.n_nets * pp::F_PER_NET + 1) * pp::FLAG_LINE;
+    a.err = reinterpret_cast<int*>(a.flags + n_flag_words);
+    FSRL_CUDA(cudaMemsetAsync(a.flags, 0, (n_flag_words + 32) * sizeof(unsigned), s));
+    const size_t smem = pp::smem_bytes(ug.D);
+    static size_t set = 0;
+    if (smem > set) {
+        FSRL_CUDA(cudaFuncSetAttribute(pp::ppo_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set = smem;
+    }
+    pp::ppo_persist_kernel<<<32 * ug.n_nets, pp::TPB, smem, s>>>(a);
+    FSRL_LAUNCH_CHECK();
+    return FSRL_OK;
+}
+
+}  // namespace fsrl

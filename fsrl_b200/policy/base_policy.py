@@ -342,9 +342,17 @@ class BasePolicy(ABC, nn.Module):
         batch.end_flag = end_flag
         v = torch.empty((C, n), dtype=torch.float32, device=dev)
         vnext = torch.empty((C, n), dtype=torch.float32, device=dev)
-        # V(obs_next[i]) == V(obs[i+1]) inside a segment (the collector stores the same row
-        # twice), so only segment ends need a second critic pass
-        ends = torch.nonzero(end_flag, as_tuple=False).flatten().to(torch.int32)
+        # V(obs_next[i]) == V(obs[i+1]) wherever the collector stored the same row twice (inside an
+        # episode segment), so only the other rows need a second critic pass: segment ends, the last
+        # row, and every row whose successor in the batch is NOT its obs_next (an abandoned partial
+        # episode after a second collect without reset_buffer, or caller-chosen `indices`).  The test is
+        # on the data itself, so it holds for any index set (the reference always evaluates
+        # critic(obs_next), base_policy.py:427-428).
+        need = end_flag.to(torch.bool).clone()
+        need[-1] = True
+        if n > 1:
+            need[:-1] |= (batch.obs_next[:-1] != batch.obs[1:]).any(dim=1)
+        ends = torch.nonzero(need, as_tuple=False).flatten().to(torch.int32)
         for i in range(C):
             vi = self.net_forward(1 + i, batch.obs).flatten()
             v[i] = vi

@@ -132,6 +132,12 @@ class PPOLagrangian(LagrangianPolicy):
         u.mb_stats = self._mb_stats.data_ptr()
         u.batch_size = int(getattr(self, '_dp_batch', 0))
         u.barrier = self._norm_sq.data_ptr() + 8
+        # persistent tcgen05 path (csrc/ppo_persist.cu): operand images, partial buffers and flags
+        nws = int(_lib.lib.fsrl_ppo_persist_ws_floats(len(ar.slots), s0.D, s0.H))
+        if getattr(self, "_persist_ws", None) is None or self._persist_ws.numel() < nws:
+            self._persist_ws = torch.zeros(nws, dtype=torch.float32, device=ar.device)
+        u.persist_ws, u.persist_ws_floats = self._persist_ws.data_ptr(), self._persist_ws.numel()
+        u.persist_off = int(bool(getattr(self, "_persist_off", False)))
         dp = getattr(self, "_dp", None)
         u.world = 1
         if dp is not None and dp.world > 1:

@@ -189,9 +189,18 @@ typedef struct fsrl_ppo_update {
     float* p2p_part;               /* local [FSRL_P2P_PARTIALS]: per-CTA sums of g^2 (summed in a fixed
                                     * order by the Adam kernel: atomics would break rank lock-step) */
     int p2p_rank, p2p_on;
+    /* persistent tcgen05 path (csrc/ppo_persist.cu; H = 256, batch 256, single GPU): workspace of
+     * fsrl_ppo_persist_ws_floats() floats for the operand images / partials / flags; NULL or
+     * persist_off != 0 selects the three-launch chain */
+    float* persist_ws;
+    long long persist_ws_floats;
+    int persist_off, pad1;
 } fsrl_ppo_update_t;
 
 size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax);
+size_t fsrl_ppo_persist_ws_floats(int n_nets, int D, int H);
+/* 1 if fsrl_ppo_lag_epoch would take the persistent path for this descriptor / batch */
+int fsrl_ppo_persist_active(const fsrl_ppo_update_t* u, long long n_total, int batch_size);
 int fsrl_ppo_sync_mirror(const fsrl_ppo_update_t* u, void* stream);
 /* one repeat of learn()'s inner loop: all minibatches of Batch.split(batch_size,
  * merge_last=True) over u->perm[0..n_total); Adam step counter continues from adam_t0;

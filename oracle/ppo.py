@@ -42,7 +42,7 @@ def process(actor, critics, batch, gamma, gae_lambda, unfinished=None):
 
 def learn(actor, critics, optim, batch, batch_size, repeat, lagrangian, rescaling=True,
           eps_clip=0.2, vf_coef=0.25, max_grad_norm=None, target_kl=0.02, norm_adv=True,
-          dual_clip=None, use_lagrangian=True, max_steps=None, value_clip=False):
+          dual_clip=None, use_lagrangian=True, max_steps=None, value_clip=False, grads_out=None):
     """ppo_lag.py:214-257.  Returns a list of per-minibatch stat dicts (un-averaged)."""
     obs = torch.from_numpy(batch["obs"]); act = torch.from_numpy(batch["act"])
     logp_old_all = torch.from_numpy(batch["logp_old"])
@@ -51,6 +51,8 @@ def learn(actor, critics, optim, batch, batch_size, repeat, lagrangian, rescalin
     params = [p for m in [actor] + list(critics) for p in m.parameters()]
     stats = []
     n = obs.shape[0]
+    if grads_out is not None:
+        max_steps = 1
     resc = 1.0 / (lagrangian + 1.0) if (rescaling and use_lagrangian) else 1.0
     for step in range(repeat):
         kl_sum, iters = 0.0, 0
@@ -59,7 +61,9 @@ def learn(actor, critics, optim, batch, batch_size, repeat, lagrangian, rescalin
             mu, sigma = actor(obs[idx_t])
             dist = Independent(Normal(mu, sigma), 1)
             log_p = dist.log_prob(act[idx_t])
-            ratio = (log_p - logp_old_all[idx_t]).exp().float()
+            ratio = (log_p - logp_old_all[idx_t]).exp()
+            if ratio.dtype != torch.float64:            # the fp64 twin (drift studies) keeps its precision
+                ratio = ratio.float()                   # ppo_lag.py:176
             adv = advs_all[idx_t].clone()
             if norm_adv:                                                     # :178-182
                 for i in range(C):
@@ -94,6 +98,8 @@ def learn(actor, critics, optim, batch, batch_size, repeat, lagrangian, rescalin
             loss = loss_actor + vf_coef * loss_vf
             optim.zero_grad()
             loss.backward()
+            if grads_out is not None:                   # un-clipped gradients of the first minibatch (parity tests)
+                grads_out.extend(p.grad.detach().clone() for p in params)
             gn = None
             if max_grad_norm:
                 gn = torch.nn.utils.clip_grad_norm_(params, max_norm=max_grad_norm)
