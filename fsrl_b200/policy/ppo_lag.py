@@ -161,6 +161,14 @@ class PPOLagrangian(LagrangianPolicy):
         n = batch.n
         ar = self.arena
         self._dp_batch = int(batch_size)
+        dp = getattr(self, "_dp", None)
+        if dp is not None and dp.world > 1:
+            # every rank must run the same number of equally sized minibatches, or the per-step gradient
+            # exchanges fall out of step (a hang, or the 20 s peer timeout): fail loudly instead
+            lo_hi = dp.all_max([n, -n])
+            if int(lo_hi[0]) != -int(lo_hi[1]):
+                raise RuntimeError("data-parallel PPO update: ranks hold different batch sizes (%d..%d rows); "
+                                   "collect the same number of steps on every rank" % (-int(lo_hi[1]), int(lo_hi[0])))
         self._ensure_update_state(batch_size, n, repeat)
         lib = _lib.lib
         stream = self._stream()

@@ -25,7 +25,9 @@ class OffpolicyTrainer(BaseTrainer):
         buf = self.train_collector.buffer
         self.policy.pre_update_fn(stats_train=stats_train, batch_size=self.batch_size, buffer=buf,
                                   update_per_step=self.update_per_step)
-        n_updates = round(self.update_per_step * stats_train["n/st"])
+        # data-parallel ranks derive the number of gradient steps from the step count they agreed on
+        # (BaseTrainer._agreed_steps), so every rank joins the same number of gradient exchanges
+        n_updates = round(self.update_per_step * getattr(self, "_cycle_steps", stats_train["n/st"]))
         if hasattr(self.policy, "update_many"):
             # same gradient steps, launched back to back without returning to Python each time
             self.policy.update_many(n_updates, self.batch_size, buf)
