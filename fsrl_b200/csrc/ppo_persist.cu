@@ -27,6 +27,9 @@
 // by the producer (MN-major tf32 operands would need the 128B_BASE32B swizzle).
 #include "ppo_persist.cuh"
 #include "umma.cuh"
+#include <cstdlib>
+#include <cmath>
+#include <vector>
 
 namespace fsrl {
 namespace pp {
@@ -54,7 +57,8 @@ constexpr int SUMSQ_FLOATS = 128;                               // global tail: 
 // flag lines (32 unsigned each): per net A, C, D1, B[4]; global D2
 constexpr int FLAG_LINE = 32;
 constexpr int F_A = 0, F_C = 1, F_D1 = 2, F_B = 3, F_PER_NET = 7;
-constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,32) accumulators, Adam state
+constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,64) accumulators, Adam state
+constexpr int MAX_MB = 16384;                                    // minibatches per launch (Adam scalar table)
 constexpr long long WAIT_CYCLES = 6000000000LL;                  // ~3 s: a lost partner must not hang the GPU
 
 constexpr int ST_ACTOR_REW = 0, ST_ACTOR_SAFETY = 1, ST_KL = 2, ST_VF0 = 3, ST_ENTROPY = 5, ST_GRADNORM = 6;
@@ -67,20 +71,41 @@ struct Args {
     float* ws;
     unsigned* flags;
     int* err;
+    const float* adam_tab;   // [n_mb][2]: 1 / sqrt(1 - beta2^t), -(lr / (1 - beta1^t)) of every step (host doubles -> f32)
+    long long* dbg;          // optional [n_cta][DBG_N] clock stamps of step dbg_step
+    int dbg_step;
 };
+constexpr int DBG_N = 32;
+#define STAMP(i) do { if (P.dbg && t == P.dbg_step) P.dbg[(size_t)blockIdx.x * DBG_N + (i)] = clock64(); } while (0)
 
-struct AdamS { float w1, b2, w2, bc2s, eps, neg_step; };
+struct AdamS { float w1, b2, w2, rbc2s, eps, neg_step; };
+// torch.optim.Adam's single-tensor update.  The moments are the exact fp32 expressions; the parameter step
+// p += step * m / (sqrt(v) / sqrt(bc2) + eps) uses the SFU reciprocal square root / reciprocal (about 2 ulp each,
+// i.e. ~1e-10 absolute on a step of <= lr) instead of IEEE sqrt and division, whose slow-path calls serialise the
+// 32 elements a lane owns (measured: 19k cycles per step for the 64 x 64 tile with IEEE arithmetic).
 __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamS& a) {
     m = m + a.w1 * (g - m);                 // exp_avg.lerp_(grad, 1 - beta1)
     v = v * a.b2 + (a.w2 * g) * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    const float denom = sqrtf(v) / a.bc2s + a.eps;
-    return p + (a.neg_step * m) / denom;    // param.addcdiv_(exp_avg, denom, value=-step_size)
+    const float sq = v > 0.f ? v * rsqrtf(v) : 0.f;
+    const float denom = fmaf(sq, a.rbc2s, a.eps);
+    return p + __fdividef(a.neg_step * m, denom);
 }
 
 __device__ __forceinline__ void fail(int* err, int code) {
     *reinterpret_cast<volatile int*>(err) = code;
     __threadfence_system();
     asm volatile("trap;");
+}
+// one thread of a converged warp (CUTLASS elect_one_sync): lets the compiler issue the uniform-datapath
+// instructions (UTCHMMA, UBLKCP) of the region directly instead of wrapping each in a vote loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -101,6 +126,61 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// The M = 64 accumulators occupy the lower 16 lanes of every tensor-memory subpartition (one MMA per k-step
+// keeps the shared-memory operand traffic down -- the A tile is re-read by every instruction).  The upper 16
+// lanes of the warp take over the upper half of the columns: lane l >= 16 receives columns [NH, 2 NH) of lane
+// l - 16, so that all 32 lanes share the epilogue work.
+__device__ __forceinline__ void acc_ld_split16(uint32_t taddr, int lane, float (&v)[16]) {
+    float w[32];
+    tmem_ld32(taddr, w);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float x = __shfl_sync(0xffffffffu, w[16 + j], lane & 15);
+        v[j] = (lane & 16) ? x : w[j];
+    }
+}
+__device__ __forceinline__ void acc_ld_split32(uint32_t taddr, int lane, float (&v)[32]) {
+    float w[32];
+    tmem_ld32(taddr + 32, w);
+    tmem_ld32(taddr, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float x = __shfl_sync(0xffffffffu, w[j], lane & 15);
+        v[j] = (lane & 16) ? x : v[j];
+    }
+}
+
+// Transposed K-major image of a 64-row tile through shared memory.  Every epilogue thread holds NC consecutive
+// columns [c0, c0 + NC) of tile row `row` (hi / lo parts); the tile is 2 NC columns wide.  The transposed image
+// stores 4 consecutive ROWS of one column as 16 contiguous bytes: element (col, row) at
+//     img[(row_base + row) / 4 * 256 + (col_base + col) * 4 + (row_base + row) % 4],     lo image at + IMG.
+// Writing it straight from the registers costs NC scattered 4-byte stores per thread and image (16 sectors per warp
+// instruction); staged through `scr` (an idle operand-ring slot, row stride 65: conflict-free) it becomes
+// float4 stores, 512 contiguous bytes per warp instruction.
+template <int NC>
+__device__ __forceinline__ void store_transposed(float* scr, const float (&hi)[NC], const float (&lo)[NC], int row, int c0,
+                                                 int et, float* img_hi, int row_base, int col_base) {
+    constexpr int W = 2 * NC, LO = W * 65;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        scr[(c0 + j) * 65 + row] = hi[j];
+        scr[LO + (c0 + j) * 65 + row] = lo[j];
+    }
+    epi_bar();
+    const int col = et % W;
+    constexpr int GPT = 16 / (NEPI / W);                       // row groups (of 4 rows) per thread
+    const int g0 = (et / W) * GPT;
+    float* dst = img_hi + (size_t)(row_base >> 2) * 256 + (size_t)(col_base + col) * 4;
+#pragma unroll
+    for (int q = 0; q < GPT; ++q) {
+        const int g = g0 + q;
+        const float* sh = scr + col * 65 + 4 * g;
+        *reinterpret_cast<float4*>(dst + (size_t)g * 256) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+        *reinterpret_cast<float4*>(dst + IMG + (size_t)g * 256) = make_float4(sh[LO], sh[LO + 1], sh[LO + 2], sh[LO + 3]);
+    }
+    epi_bar();                                                 // scratch may be reused
+}
+
 // sum over the 16 lanes of a half-warp (lanes l and l ^ 16 hold different data)
 __device__ __forceinline__ float half_sum(float v) {
 #pragma unroll
@@ -118,7 +198,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_acc;
     __shared__ uint32_t s_tmem;
-    __shared__ float s_red[4][64];           // cross-subpartition partial sums
+    __shared__ float s_red[4][320];          // cross-subpartition partial sums
     __shared__ float s_misc[32];
     __shared__ AdamS s_adam;
     const fsrl_ppo_update_t& u = P.u;
@@ -159,10 +239,11 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
 
     if (warp == 0) {
         // ============================ bulk-copy producer ==========================================
-        if (lane == 0) {
+        if (elect_one()) {
             unsigned qq = 0;
             for (int t = 0; t < P.n_mb; ++t) {
                 if (!flag_wait_ge(fl_net + F_A * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 10);
+                STAMP(12);
                 fence_proxy_async();
                 for (int j = 0; j < 4; ++j, ++qq) {               // G1: K = k in chunks of 64
                     const int s = qq % NSLOT;
@@ -175,7 +256,9 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     bulk_g2s(dst + 32768, wsn + (size_t)I_W2A_HI * IMG + bo, 8192, &bar_full[s]);
                     bulk_g2s(dst + 40960, wsn + (size_t)I_W2A_LO * IMG + bo, 8192, &bar_full[s]);
                 }
+                STAMP(13);
                 if (!flag_wait_ge(fl_net + F_C * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 12);
+                STAMP(14);
                 fence_proxy_async();
                 const int ia = is_g2 ? I_W2B_HI : I_DZT_HI, ib = is_g2 ? I_DZA_HI : I_H1T_HI;
                 const int blk_a = is_g2 ? ka : q4, blk_b = is_g2 ? q4 : ka;
@@ -194,55 +277,53 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ==================================================
-        if (lane == 0) {
+        if (elect_one()) {
             unsigned qq = 0;
             const uint32_t ring_a = smem_u32(ring);
-            const uint32_t id16 = idesc_tf32(64, 16, false, false), id32 = idesc_tf32(64, 32, false, false);
+            const uint32_t id32 = idesc_tf32(64, 32, false, false), id64 = idesc_tf32(64, 64, false, false);
             for (int t = 0; t < P.n_mb; ++t) {
                 for (int j = 0; j < 4; ++j, ++qq) {               // ---- G1: D[64 r][32 o], two 16-column halves
                     const int s = qq % NSLOT;
                     if (!mbar_wait(&bar_full[s], (qq / NSLOT) & 1, WAIT_CYCLES)) fail(P.err, 20);
                     tc_fence_after();
+                    if (j == 0) STAMP(16);
+                    if (j == 3) STAMP(17);
                     const uint32_t base = ring_a + (uint32_t)s * SLOT_BYTES;
-#pragma unroll 2
+#pragma unroll 4
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint64_t ah = smem_desc(base + ks * 2048, 1024, 128);
                         const uint64_t al = smem_desc(base + 16384 + ks * 2048, 1024, 128);
-#pragma unroll
-                        for (int sub = 0; sub < 2; ++sub) {
-                            const uint64_t bh = smem_desc(base + 32768 + ks * 1024 + sub * 256, 512, 128);
-                            const uint64_t bl = smem_desc(base + 40960 + ks * 1024 + sub * 256, 512, 128);
-                            const uint32_t d = tmem + ((uint32_t)(16 * sub) << 16);
-                            mma_tf32_ss(d, al, bh, id16, (j | ks) != 0);
-                            mma_tf32_ss(d, ah, bl, id16, true);
-                            mma_tf32_ss(d, ah, bh, id16, true);
-                        }
+                        const uint64_t bh = smem_desc(base + 32768 + ks * 1024, 512, 128);
+                        const uint64_t bl = smem_desc(base + 40960 + ks * 1024, 512, 128);
+                        mma_tf32_ss(tmem, al, bh, id32, (j | ks) != 0);
+                        mma_tf32_ss(tmem, ah, bl, id32, true);
+                        mma_tf32_ss(tmem, ah, bh, id32, true);
                     }
                     mma_commit(&bar_empty[s]);
                 }
                 mma_commit(&bar_acc);
+                STAMP(18);
                 for (int j = 0; j < 4; ++j, ++qq) {               // ---- G2 / G3: D[64][64], two 32-column halves
                     const int s = qq % NSLOT;
                     if (!mbar_wait(&bar_full[s], (qq / NSLOT) & 1, WAIT_CYCLES)) fail(P.err, 21);
                     tc_fence_after();
+                    if (j == 0) STAMP(19);
+                    if (j == 3) STAMP(20);
                     const uint32_t base = ring_a + (uint32_t)s * SLOT_BYTES;
-#pragma unroll 2
+#pragma unroll 4
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint64_t ah = smem_desc(base + ks * 2048, 1024, 128);
                         const uint64_t al = smem_desc(base + 16384 + ks * 2048, 1024, 128);
-#pragma unroll
-                        for (int sub = 0; sub < 2; ++sub) {
-                            const uint64_t bh = smem_desc(base + 32768 + ks * 2048 + sub * 512, 1024, 128);
-                            const uint64_t bl = smem_desc(base + 49152 + ks * 2048 + sub * 512, 1024, 128);
-                            const uint32_t d = tmem + ((uint32_t)(16 * sub) << 16);
-                            mma_tf32_ss(d, al, bh, id32, (j | ks) != 0);
-                            mma_tf32_ss(d, ah, bl, id32, true);
-                            mma_tf32_ss(d, ah, bh, id32, true);
-                        }
+                        const uint64_t bh = smem_desc(base + 32768 + ks * 2048, 1024, 128);
+                        const uint64_t bl = smem_desc(base + 49152 + ks * 2048, 1024, 128);
+                        mma_tf32_ss(tmem, al, bh, id64, (j | ks) != 0);
+                        mma_tf32_ss(tmem, ah, bl, id64, true);
+                        mma_tf32_ss(tmem, ah, bh, id64, true);
                     }
                     mma_commit(&bar_empty[s]);
                 }
                 mma_commit(&bar_acc);
+                STAMP(21);
             }
         }
     } else {
@@ -282,29 +363,29 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         for (int t = 0; t < P.n_mb; ++t) {
             const long long row0 = (long long)t * MB;                 // first row of the minibatch in the gathered arrays
             const int slot = P.slot0 + t;
-            if (et == 0) {   // Adam scalars of this step (torch.optim.Adam: python doubles -> f32 at the op)
-                const double tt = (double)(P.adam_t0 + t + 1);
-                const double bc1 = 1.0 - pow(u.beta1, tt), bc2 = 1.0 - pow(u.beta2, tt);
+            if (et == 0) {   // Adam scalars of this step (torch.optim.Adam: python doubles -> f32 at the op; host table)
                 s_adam.w1 = (float)(1.0 - u.beta1); s_adam.b2 = (float)u.beta2; s_adam.w2 = (float)(1.0 - u.beta2);
-                s_adam.bc2s = (float)sqrt(bc2); s_adam.eps = (float)u.adam_eps; s_adam.neg_step = (float)(-(u.lr / bc1));
+                s_adam.rbc2s = __ldg(P.adam_tab + 2 * t); s_adam.eps = (float)u.adam_eps; s_adam.neg_step = __ldg(P.adam_tab + 2 * t + 1);
+                STAMP(0);
+                if (P.dbg && t == P.dbg_step) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.dbg[(size_t)blockIdx.x * DBG_N + 30] = gt; }
             }
             // rows of the NEXT minibatch towards L2 while this one is processed
             if (t + 1 < P.n_mb && et < 64) {
                 const long long r = row0 + MB + 64 * a + et;
                 prefetch_l2(u.obs + r * D);
                 if (D > 32) prefetch_l2(u.obs + r * D + 32);
+                if (is_g2) { prefetch_l2(u.obs + (r + 128) * D); if (D > 32) prefetch_l2(u.obs + (r + 128) * D + 32); }
                 if (net == 0) { prefetch_l2(u.act + r * A); prefetch_l2(u.logp_old + r); prefetch_l2(u.adv + r); if (C > 1) prefetch_l2(u.adv + u.ld + r); }
                 else { prefetch_l2(u.ret + (long long)(net - 1) * u.ld + r); if (u.value_clip) prefetch_l2(u.values + (long long)(net - 1) * u.ld + r); }
             }
             // ---- S(a): publish the images of the owned W2 tile (from tensor memory) ------------------
+            float* scratch = reinterpret_cast<float*>(ring);       // the operand ring is idle outside the GEMM phases
             if (!is_g2) {
-                float pv[32];
+                float pv[32], phi[32], plo[32];
                 tmem_ld32(tm_lane + TM_P, pv);
                 const int o = 64 * q4 + trow;                   // output unit of this lane
                 float* w2a_hi = wsn + (size_t)I_W2A_HI * IMG + (size_t)(o >> 5) * 8192 + (size_t)(o & 31) * 4;
                 float* w2a_lo = w2a_hi + IMG;
-                float* w2b_hi = wsn + (size_t)I_W2B_HI * IMG + (size_t)ka * 16384 + (size_t)(o >> 2) * 256 + (o & 3);
-                float* w2b_lo = w2b_hi + IMG;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {                   // k = 64 ka + 32 half + 4 q + (0..3)
                     float4 hi, lo;
@@ -313,43 +394,44 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     const size_t plane = (size_t)(16 * ka + 8 * half + q) * 128;
                     *reinterpret_cast<float4*>(w2a_hi + plane) = hi;
                     *reinterpret_cast<float4*>(w2a_lo + plane) = lo;
-                    const int kl = 32 * half + 4 * q;           // k within the 64-block
-                    w2b_hi[(size_t)kl * 4] = hi.x; w2b_hi[(size_t)(kl + 1) * 4] = hi.y; w2b_hi[(size_t)(kl + 2) * 4] = hi.z; w2b_hi[(size_t)(kl + 3) * 4] = hi.w;
-                    w2b_lo[(size_t)kl * 4] = lo.x; w2b_lo[(size_t)(kl + 1) * 4] = lo.y; w2b_lo[(size_t)(kl + 2) * 4] = lo.z; w2b_lo[(size_t)(kl + 3) * 4] = lo.w;
+                    phi[4 * q] = hi.x; phi[4 * q + 1] = hi.y; phi[4 * q + 2] = hi.z; phi[4 * q + 3] = hi.w;
+                    plo[4 * q] = lo.x; plo[4 * q + 1] = lo.y; plo[4 * q + 2] = lo.z; plo[4 * q + 3] = lo.w;
                 }
+                // W2B (MN = k, K = o): "rows" are the output units o, "columns" the 64 k of block ka
+                store_transposed<32>(scratch, phi, plo, trow, 32 * half, et, wsn + (size_t)I_W2B_HI * IMG + (size_t)ka * 16384, 64 * q4, 0);
             }
-            // ---- S(b): h1 tile [64 rows of block a][32 columns of block b] ----------------------------
-            {
-                const int r = et & 63, kh = et >> 6;            // row, 16-column half
-                const float* x = u.obs + (row0 + 64 * a + r) * D;
-                float acc[16];
+            // ---- S(b): h1 tiles [64 rows][32 columns of block b].  The CTAs that own a W2 tile are busy with its Adam
+            // step and images, so the other half of the grid (CTAs 0-15: a in {0, 1}) computes the tiles of row
+            // blocks a and a + 2 -- same column block, hence the same W1 slice.
+            if (is_g2) {
+                for (int rep = 0; rep < 2; ++rep) {
+                    const int aa = a + 2 * rep;
+                    const int r = et & 63, kh = et >> 6;        // row, 16-column half
+                    const float* x = u.obs + (row0 + 64 * aa + r) * D;
+                    float acc[16], hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = sp_p[sm.w1 + D * 32 + 16 * kh + j];      // b1
-                for (int d = 0; d < D; ++d) {
-                    const float xv = __ldg(x + d);
-                    const float* w = sp_p + sm.w1 + d * 32 + 16 * kh;
+                    for (int j = 0; j < 16; ++j) acc[j] = sp_p[sm.w1 + D * 32 + 16 * kh + j];      // b1
+                    for (int d = 0; d < D; ++d) {
+                        const float xv = __ldg(x + d);
+                        const float* w = sp_p + sm.w1 + d * 32 + 16 * kh;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, w[j], acc[j]);
-                }
-                const int rg = 64 * a + r;                      // row within the minibatch
-                float* a_hi = wsn + (size_t)I_H1A_HI * IMG + (size_t)a * 16384 + (size_t)r * 4;
-                float* t_hi = wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384 + (size_t)(rg >> 2) * 256 + (rg & 3);
+                        for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, w[j], acc[j]);
+                    }
+                    float* a_hi = wsn + (size_t)I_H1A_HI * IMG + (size_t)aa * 16384 + (size_t)r * 4;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 hi, lo;
-                    tf32_split(fmaxf(acc[4 * q], 0.f), hi.x, lo.x); tf32_split(fmaxf(acc[4 * q + 1], 0.f), hi.y, lo.y);
-                    tf32_split(fmaxf(acc[4 * q + 2], 0.f), hi.z, lo.z); tf32_split(fmaxf(acc[4 * q + 3], 0.f), hi.w, lo.w);
-                    const size_t plane = (size_t)(8 * b + 4 * kh + q) * 256;
-                    *reinterpret_cast<float4*>(a_hi + plane) = hi;
-                    *reinterpret_cast<float4*>(a_hi + IMG + plane) = lo;
-                    const int kl = 32 * (b & 1) + 16 * kh + 4 * q;     // column within the 64-block of H1T
-                    t_hi[(size_t)kl * 4] = hi.x; t_hi[(size_t)(kl + 1) * 4] = hi.y; t_hi[(size_t)(kl + 2) * 4] = hi.z; t_hi[(size_t)(kl + 3) * 4] = hi.w;
-                    float* t_lo = t_hi + IMG;
-                    t_lo[(size_t)kl * 4] = lo.x; t_lo[(size_t)(kl + 1) * 4] = lo.y; t_lo[(size_t)(kl + 2) * 4] = lo.z; t_lo[(size_t)(kl + 3) * 4] = lo.w;
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) tf32_split(fmaxf(acc[4 * q + e], 0.f), hi[4 * q + e], lo[4 * q + e]);
+                        const size_t plane = (size_t)(8 * b + 4 * kh + q) * 256;
+                        *reinterpret_cast<float4*>(a_hi + plane) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                        *reinterpret_cast<float4*>(a_hi + IMG + plane) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                    }
+                    // H1T (MN = k, K = r): block b / 2, columns 32 (b & 1) ..
+                    store_transposed<16>(scratch, hi, lo, r, 16 * kh, et, wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384, 64 * aa, 32 * (b & 1));
                 }
             }
             epi_bar();
-            if (et == 0) flag_add_release(fl_net + F_A * FLAG_LINE);
+            if (et == 0) { STAMP(1); flag_add_release(fl_net + F_A * FLAG_LINE); }
 
             // per-row loss inputs (independent of the GEMM): issued now, consumed after the head
             const long long grow = row0 + 64 * a + trow;
@@ -373,8 +455,9 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 30);
             ++acc_phase;
             tc_fence_after();
+            if (et == 0) STAMP(2);
             float h2[16];
-            tmem_ld16(tm_lane, h2);
+            acc_ld_split16(tm_lane, lane, h2);
             float hp[OUTP];
 #pragma unroll
             for (int j = 0; j < OUTP; ++j) hp[j] = 0.f;
@@ -395,8 +478,10 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             tc_fence_before();
             epi_bar();
             if (et == 0) {
+                STAMP(3);
                 flag_add_release(fl_net + (F_B + a) * FLAG_LINE);
                 if (!flag_wait_ge(fl_net + (F_B + a) * FLAG_LINE, 8u * (t + 1), WAIT_CYCLES)) fail(P.err, 31);
+                STAMP(4);
             }
             epi_bar();
             float outv[OUTP];
@@ -482,6 +567,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     st_d = lv * invB;
                 }
             }
+            if (et == 0) STAMP(26);
             // ---- dz2 tile = (dOut W3^T) * relu'(h2): images DZA / DZT; partial db2, dW3, db3 ----------------
             const int nfeed = (net == 0) ? A : 1;              // head columns that feed W3 (mu only)
             float dz[16];
@@ -494,164 +580,215 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                 dz[j] = h2[j] > 0.f ? g : 0.f;
             }
             {
-                const int rg = 64 * a + trow;
+                float hi[16], lo[16];
                 float* a_hi = wsn + (size_t)I_DZA_HI * IMG + (size_t)a * 16384 + (size_t)trow * 4;
-                float* t_hi = wsn + (size_t)I_DZT_HI * IMG + (size_t)(b >> 1) * 16384 + (size_t)(rg >> 2) * 256 + (rg & 3);
-                float* t_lo = t_hi + IMG;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float4 hi, lo;
-                    tf32_split(dz[4 * q], hi.x, lo.x); tf32_split(dz[4 * q + 1], hi.y, lo.y);
-                    tf32_split(dz[4 * q + 2], hi.z, lo.z); tf32_split(dz[4 * q + 3], hi.w, lo.w);
-                    const size_t plane = (size_t)(8 * b + 4 * half + q) * 256;
-                    *reinterpret_cast<float4*>(a_hi + plane) = hi;
-                    *reinterpret_cast<float4*>(a_hi + IMG + plane) = lo;
-                    const int ol = 32 * (b & 1) + 16 * half + 4 * q;
-                    t_hi[(size_t)ol * 4] = hi.x; t_hi[(size_t)(ol + 1) * 4] = hi.y; t_hi[(size_t)(ol + 2) * 4] = hi.z; t_hi[(size_t)(ol + 3) * 4] = hi.w;
-                    t_lo[(size_t)ol * 4] = lo.x; t_lo[(size_t)(ol + 1) * 4] = lo.y; t_lo[(size_t)(ol + 2) * 4] = lo.z; t_lo[(size_t)(ol + 3) * 4] = lo.w;
-                }
-            }
-            // column sums over this subpartition's 16 rows -> s_red[sp][...]; then over the 4 subpartitions
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float sdz = half_sum(dz[j]);
-                if (r16 == 0) s_red[sp][16 * half + j] = sdz;                       // db2 partial
+                    for (int e = 0; e < 4; ++e) tf32_split(dz[4 * q + e], hi[4 * q + e], lo[4 * q + e]);
+                    const size_t plane = (size_t)(8 * b + 4 * half + q) * 256;
+                    *reinterpret_cast<float4*>(a_hi + plane) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                    *reinterpret_cast<float4*>(a_hi + IMG + plane) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                }
+                // DZT (MN = o, K = r): block b / 2, columns 32 (b & 1) ..
+                store_transposed<16>(scratch, hi, lo, trow, 16 * half, et, wsn + (size_t)I_DZT_HI * IMG + (size_t)(b >> 1) * 16384, 64 * a, 32 * (b & 1));
             }
-            epi_bar();
-            if (et < 32) wsn[DB2P_OFF + a * H + 32 * b + et] = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
-            epi_bar();
-            for (int jj = 0; jj < nfeed; ++jj) {               // dW3[o][jj] partial = sum_r h2[r][o] dOut[r][jj]
+            if (et == 0) STAMP(27);
+            // partial sums over this tile's 64 rows: half-warp butterflies (16 rows of a subpartition), one shared
+            // memory exchange, then 4-way sums.  s_red row: [0,32) db2 | [32,32+32 nfeed) dW3 | [288,304) db3, dlog sigma | [304,308) loss sums
+            {
+                float* row = &s_red[sp][0];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float sv = half_sum(h2[j] * dd[jj]);
-                    if (r16 == 0) s_red[sp][16 * half + j] = sv;
+                    const float sdz = half_sum(dz[j]);
+                    if (r16 == 0) row[16 * half + j] = sdz;
                 }
-                epi_bar();
-                if (et < 32) wsn[DW3P_OFF + ((size_t)a * H + 32 * b + et) * OUTP + jj] = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
-                epi_bar();
+#pragma unroll
+                for (int jj = 0; jj < OUTP; ++jj) {
+                    if (jj < nfeed) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float sv = half_sum(h2[j] * dd[jj]);
+                            if (r16 == 0) row[32 + 32 * jj + 16 * half + j] = sv;
+                        }
+                    }
+                }
+                if (b == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float sv = half_sum(dd[j]);
+                        if (lane == 0) row[288 + j] = sv;
+                    }
+                    const float sa = half_sum(st_a), sb = half_sum(st_b), sc = half_sum(st_c), sdv = half_sum(st_d);
+                    if (lane == 0) { row[304] = sa; row[305] = sb; row[306] = sc; row[307] = sdv; }
+                }
+            }
+            epi_bar();
+            if (et == 0) STAMP(28);
+            for (int i = et; i < 32 + 32 * nfeed; i += NEPI) {
+                const float tot = ((s_red[0][i] + s_red[1][i]) + s_red[2][i]) + s_red[3][i];
+                if (i < 32) wsn[DB2P_OFF + a * H + 32 * b + i] = tot;
+                else wsn[DW3P_OFF + ((size_t)a * H + 32 * b + ((i - 32) & 31)) * OUTP + ((i - 32) >> 5)] = tot;
             }
             if (b == 0) {                                       // db3 | d log sigma partial, loss statistics
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float sv = half_sum(dd[j]);
-                    if (lane == 0) s_red[sp][j] = sv;
-                }
-                const float sa = half_sum(st_a), sb = half_sum(st_b), sc = half_sum(st_c), sdv = half_sum(st_d);
-                if (lane == 0) { s_red[sp][16] = sa; s_red[sp][17] = sb; s_red[sp][18] = sc; s_red[sp][19] = sdv; }
-                epi_bar();
-                if (et < 16) wsn[DB3P_OFF + a * 16 + et] = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
-                if (et >= 16 && et < 20 && stat_base) {
-                    const float tot = s_red[0][et] + s_red[1][et] + s_red[2][et] + s_red[3][et];
-                    float* stat = stat_base + (size_t)slot * FSRL_PPO_STATS;
-                    if (net == 0) { if (et == 16) atomicAdd(stat + ST_ACTOR_REW, tot); if (et == 17) atomicAdd(stat + ST_ACTOR_SAFETY, tot); if (et == 18) atomicAdd(stat + ST_KL, tot); }
-                    else if (et == 19) atomicAdd(stat + ST_VF0 + (net - 1), tot);
+                if (et < 20) {
+                    const int i = 288 + et;
+                    const float tot = ((s_red[0][i] + s_red[1][i]) + s_red[2][i]) + s_red[3][i];
+                    if (et < 16) wsn[DB3P_OFF + a * 16 + et] = tot;
+                    else if (stat_base) {
+                        float* stat = stat_base + (size_t)slot * FSRL_PPO_STATS;
+                        if (net == 0) { if (et == 16) atomicAdd(stat + ST_ACTOR_REW, tot); if (et == 17) atomicAdd(stat + ST_ACTOR_SAFETY, tot); if (et == 18) atomicAdd(stat + ST_KL, tot); }
+                        else if (et == 19) atomicAdd(stat + ST_VF0 + (net - 1), tot);
+                    }
                 }
                 if (net == 0 && a == 0 && et == 20 && stat_base) {
                     float ent = 0.f;
-                    for (int j = 0; j < A; ++j) ent += 0.5f + LOG_SQRT_2PI + sp_p[sm.b3 + 8 + j];
+                    for (int jq = 0; jq < A; ++jq) ent += 0.5f + LOG_SQRT_2PI + sp_p[sm.b3 + 8 + jq];
                     stat_base[(size_t)slot * FSRL_PPO_STATS + ST_ENTROPY] = ent;
                 }
             }
             epi_bar();
-            if (et == 0) flag_add_release(fl_net + F_C * FLAG_LINE);
+            if (et == 0) { STAMP(5); flag_add_release(fl_net + F_C * FLAG_LINE); }
 
             // ---- G2 / G3 epilogue ---------------------------------------------------------------------------
-            if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 32);
-            ++acc_phase;
-            tc_fence_after();
-            float sq = 0.f;
+            // G2: what does not depend on the accumulators is requested BEFORE waiting for them -- the ReLU mask of
+            // this lane's h1 entries (image H1A, complete since flag A) and this thread's share of the 64 x D
+            // observation block of row block q4
+            float mreg[32];
+            float xr[(64 * MAXD + NEPI - 1) / NEPI];
+            const int nx = (64 * D + NEPI - 1) / NEPI;
             if (is_g2) {
-                // lane: k = 64 ka + trow ; rows 32 half + j of row block q4
-                float v[32];
-                tmem_ld32(tm_lane, v);
                 const int k = 64 * ka + trow;
                 const float* msk = wsn + (size_t)I_H1A_HI * IMG + (size_t)q4 * 16384 + (size_t)(k >> 2) * 256 + (k & 3);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (__ldcg(msk + (size_t)(32 * half + j) * 4) > 0.f) ? v[j] : 0.f;
-                const float* xb = u.obs + (row0 + 64 * q4 + 32 * half) * D;
+                for (int jq = 0; jq < 32; ++jq) mreg[jq] = __ldcg(msk + (size_t)(32 * half + jq) * 4);
+                const float* xb = u.obs + (row0 + 64 * q4) * D;
+#pragma unroll
+                for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q)
+                    xr[q] = (q < nx && et + q * NEPI < 64 * D) ? __ldg(xb + et + q * NEPI) : 0.f;
+            }
+            if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 32);
+            ++acc_phase;
+            tc_fence_after();
+            if (et == 0) STAMP(6);
+            float sq = 0.f;
+            if (is_g2) {
+                // the operand ring is idle from here until the next step's flag A: slot 0 serves as scratch for the
+                // observation block (row r at r * D + (r >> 5): the two half-warps read different banks)
+                float* xs = reinterpret_cast<float*>(ring);
+#pragma unroll
+                for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q) {
+                    const int e = et + q * NEPI;
+                    if (q < nx && e < 64 * D) { const int r = e / D; xs[e + (r >> 5)] = xr[q]; }
+                }
+                // lane: k = 64 ka + trow ; rows 32 half + j of row block q4
+                float v[32];
+                acc_ld_split32(tm_lane, lane, v);
+                const int k = 64 * ka + trow;
+#pragma unroll
+                for (int jq = 0; jq < 32; ++jq) v[jq] = (mreg[jq] > 0.f) ? v[jq] : 0.f;
+                epi_bar();
+                if (et == 0) STAMP(22);
+                const float* xh = xs + (size_t)(32 * half) * D + half;
                 float* dst = wsn + DW1P_OFF + (size_t)q4 * (MAXD + 1) * H + k;
                 for (int d = 0; d < D; ++d) {
-                    float s = 0.f;
+                    float sacc = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) s = fmaf(__ldg(xb + (size_t)j * D + d), v[j], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 16);
-                    if (half == 0) dst[(size_t)d * H] = s;
+                    for (int jq = 0; jq < 32; ++jq) sacc = fmaf(xh[jq * D + d], v[jq], sacc);
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+                    if (half == 0) dst[(size_t)d * H] = sacc;
                 }
-                float s = 0.f;
+                float sb1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s += v[j];
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                if (half == 0) dst[(size_t)D * H] = s;            // db1
+                for (int jq = 0; jq < 32; ++jq) sb1 += v[jq];
+                sb1 += __shfl_xor_sync(0xffffffffu, sb1, 16);
+                if (half == 0) dst[(size_t)D * H] = sb1;          // db1
+                if (et == 0) STAMP(23);
                 tc_fence_before();
                 epi_bar();
                 if (et == 0) flag_add_release(fl_net + F_D1 * FLAG_LINE);
             } else {
                 float g[32];
-                tmem_ld32(tm_lane, g);
+                acc_ld_split32(tm_lane, lane, g);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sq = fmaf(g[j], g[j], sq);
+                for (int jq = 0; jq < 32; ++jq) sq = fmaf(g[jq], g[jq], sq);
             }
-            // ---- small-parameter gradients: fixed-order sums of the row-block partials -----------------------
-            if (et == 0) { if (!flag_wait_ge(fl_net + F_D1 * FLAG_LINE, 16u * (t + 1), WAIT_CYCLES)) fail(P.err, 33); }
-            epi_bar();
-            for (int i = et; i < sm.n; i += NEPI) {
-                float gsum = 0.f;
-                bool real = true;
-                if (i < sm.b2) {
-                    const int d = i / 32, kk = i % 32;
-                    const float* src = wsn + DW1P_OFF + (size_t)d * H + 32 * b + kk;
+            // ---- small-parameter gradients: fixed-order sums of the row-block partials.  The b2 / W3 / b3 partials
+            // are complete since flag C: they are summed while flag D1 (the dW1 partials) is still on its way.
+            auto reduce_slices = [&](int lo, int hi) {
+                for (int i0 = lo + et; i0 < hi; i0 += 4 * NEPI) {    // 4 elements x 4 partials in flight per thread
+                    float pv[4][4];
+                    bool real[4];
 #pragma unroll
-                    for (int rb = 0; rb < 4; ++rb) gsum += __ldcg(src + (size_t)rb * (MAXD + 1) * H);
-                } else if (i < sm.w3) {
-                    const float* src = wsn + DB2P_OFF + 32 * b + (i - sm.b2);
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = i0 + e * NEPI;
+                        const float* src = wsn;
+                        size_t stride = 0;
+                        real[e] = false;
+                        if (i < hi) {
+                            if (i < sm.b2) { src = wsn + DW1P_OFF + (size_t)(i / 32) * H + 32 * b + (i % 32); stride = (size_t)(MAXD + 1) * H; real[e] = true; }
+                            else if (i < sm.w3) { src = wsn + DB2P_OFF + 32 * b + (i - sm.b2); stride = H; real[e] = true; }
+                            else if (i < sm.b3) {
+                                const int oo = (i - sm.w3) / OUTP, jj = (i - sm.w3) % OUTP;
+                                real[e] = jj < out;
+                                src = wsn + DW3P_OFF + ((size_t)32 * b + oo) * OUTP + jj; stride = (size_t)H * OUTP;
+                            } else {
+                                const int jj = i - sm.b3;
+                                real[e] = (jj < out) || (net == 0 && u.head_indep && jj >= 8 && jj < 8 + A);
+                                src = wsn + DB3P_OFF + jj; stride = 16;
+                            }
+                        }
 #pragma unroll
-                    for (int aa = 0; aa < 4; ++aa) gsum += __ldcg(src + aa * H);
-                } else if (i < sm.b3) {
-                    const int oo = (i - sm.w3) / OUTP, jj = (i - sm.w3) % OUTP;
-                    real = jj < out;
-                    if (real) {
-                        const float* src = wsn + DW3P_OFF + ((size_t)32 * b + oo) * OUTP + jj;
-#pragma unroll
-                        for (int aa = 0; aa < 4; ++aa) gsum += __ldcg(src + (size_t)aa * H * OUTP);
+                        for (int q = 0; q < 4; ++q) pv[e][q] = real[e] ? __ldcg(src + q * stride) : 0.f;
                     }
-                } else {
-                    const int jj = i - sm.b3;
-                    real = (jj < out) || (net == 0 && u.head_indep && jj >= 8 && jj < 8 + A);
-                    if (real) {
 #pragma unroll
-                        for (int aa = 0; aa < 4; ++aa) gsum += __ldcg(wsn + DB3P_OFF + aa * 16 + jj);
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = i0 + e * NEPI;
+                        if (i < hi) {
+                            const float gsum = ((pv[e][0] + pv[e][1]) + pv[e][2]) + pv[e][3];
+                            sp_g[i] = gsum;
+                            // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3/log sigma by CTA 0
+                            if (a == 0 && real[e] && (i < sm.b3 || b == 0)) sq = fmaf(gsum, gsum, sq);
+                        }
                     }
                 }
-                sp_g[i] = real ? gsum : 0.f;
-                // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3/log sigma by CTA 0
-                if (a == 0 && real && (i < sm.b3 || b == 0)) sq = fmaf(gsum, gsum, sq);
-            }
+            };
+            reduce_slices(sm.b2, sm.n);
+            if (et == 0) { STAMP(7); if (!flag_wait_ge(fl_net + F_D1 * FLAG_LINE, 16u * (t + 1), WAIT_CYCLES)) fail(P.err, 33); STAMP(8); }
+            epi_bar();
+            reduce_slices(0, sm.b2);
             // ---- global gradient norm: per-CTA partial -> device-wide hop -> same summation order everywhere --
             sq = warp_sum(sq);
             if (lane == 0) s_misc[sp] = sq;
             epi_bar();
             if (et == 0) {
                 sumsq_g[blockIdx.x] = s_misc[0] + s_misc[1] + s_misc[2] + s_misc[3];
+                STAMP(9);
                 flag_add_release(fl_d2);
                 if (!flag_wait_ge(fl_d2, (unsigned)n_cta * (t + 1), WAIT_CYCLES)) fail(P.err, 34);
+                STAMP(10);
             }
             epi_bar();
-            float nsq = 0.f;
-            for (int i = lane; i < n_cta; i += 32) nsq += __ldcg(sumsq_g + i);       // identical order in every warp of the grid
+            float nq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nq[q] = (lane + 32 * q < n_cta) ? __ldcg(sumsq_g + lane + 32 * q) : 0.f;
+            float nsq = ((nq[0] + nq[1]) + nq[2]) + nq[3];                          // identical order in every warp of the grid
             nsq = warp_sum(nsq);
             float gscale = 1.0f;
             if (u.max_grad_norm > 0.f) gscale = fminf(u.max_grad_norm / (sqrtf(nsq) + 1e-6f), 1.0f);
             if (blockIdx.x == 0 && et == 0 && stat_base) stat_base[(size_t)slot * FSRL_PPO_STATS + ST_GRADNORM] = sqrtf(nsq);
             const AdamS ad = s_adam;
+            if (et == 0) STAMP(24);
             // ---- clip + Adam: replicated small slices, then the owned W2 tile (tensor memory) --------------------
             for (int i = et; i < sm.n; i += NEPI) {
                 float m = sp_m[i], v = sp_v[i];
                 sp_p[i] = adam_one(sp_p[i], sp_g[i] * gscale, m, v, ad);
                 sp_m[i] = m; sp_v[i] = v;
             }
+            if (et == 0) STAMP(25);
             if (!is_g2) {
                 float g[32], pv[32], mv[32], vv[32];
-                tmem_ld32(tm_lane, g);
+                acc_ld_split32(tm_lane, lane, g);
                 tmem_ld32(tm_lane + TM_P, pv); tmem_ld32(tm_lane + TM_M, mv); tmem_ld32(tm_lane + TM_V, vv);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) pv[j] = adam_one(pv[j], g[j] * gscale, mv[j], vv[j], ad);
@@ -659,6 +796,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             }
             tc_fence_before();
             epi_bar();     // slices final before the next h1 tile / head reads them; s_adam may be rewritten
+            if (et == 0) STAMP(11);
         }
 
         // ---- write the parameters and Adam moments back to the arena ------------------------------------------
@@ -694,11 +832,12 @@ static size_t smem_bytes(int D) { return (size_t)NSLOT * SLOT_BYTES + 4 * sizeof
 
 size_t ppo_persist_ws_floats(int n_nets, int D, int H) {
     (void)D; (void)H;
-    return (size_t)n_nets * pp::NET_WS + pp::SUMSQ_FLOATS + (size_t)(n_nets * pp::F_PER_NET + 1) * pp::FLAG_LINE + 32;
+    return (size_t)n_nets * pp::NET_WS + pp::SUMSQ_FLOATS + (size_t)(n_nets * pp::F_PER_NET + 1) * pp::FLAG_LINE + 32 +
+           2 * (size_t)pp::MAX_MB + 2 * (size_t)32 * n_nets * pp::DBG_N;
 }
 
 bool ppo_persist_supported(const fsrl_ppo_update_t& u, long long n_total, int batch_size) {
-    if (u.H != 256 || batch_size != pp::MB || n_total % pp::MB != 0 || n_total < pp::MB) return false;
+    if (u.H != 256 || batch_size != pp::MB || n_total % pp::MB != 0 || n_total < pp::MB || n_total / pp::MB > pp::MAX_MB) return false;
     if (u.world > 1 || u.mask != nullptr || u.gather == nullptr) return false;
     if (u.D < 1 || u.D > pp::MAXD || u.A > 8 || u.n_nets < 1 || u.n_nets > 3) return false;
     if (u.persist_ws == nullptr || (size_t)u.persist_ws_floats < ppo_persist_ws_floats(u.n_nets, u.D, u.H)) return false;
@@ -709,7 +848,7 @@ bool ppo_persist_supported(const fsrl_ppo_update_t& u, long long n_total, int ba
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
-    return pp::smem_bytes(u.D) + 4096 <= (size_t)smem_optin;
+    return pp::smem_bytes(u.D) + 8192 <= (size_t)smem_optin;
 }
 
 // ug: descriptor whose batch pointers are the gathered (contiguous) arrays; mb_stats filled.
@@ -723,6 +862,23 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
     const size_t n_flag_words = (size_t)(ug.n_nets * pp::F_PER_NET + 1) * pp::FLAG_LINE;
     a.err = reinterpret_cast<int*>(a.flags + n_flag_words);
     FSRL_CUDA(cudaMemsetAsync(a.flags, 0, (n_flag_words + 32) * sizeof(unsigned), s));
+    // Adam bias corrections of every step, computed like torch.optim.Adam does (python doubles)
+    float* tab_dev = reinterpret_cast<float*>(a.err + 32);
+    static std::vector<float> tab;
+    tab.resize(2 * (size_t)n_mb);
+    for (int t = 0; t < n_mb; ++t) {
+        const double tt = (double)(adam_t0 + t + 1);
+        const double bc1 = 1.0 - pow(ug.beta1, tt), bc2 = 1.0 - pow(ug.beta2, tt);
+        tab[2 * t] = (float)(1.0 / sqrt(bc2));
+        tab[2 * t + 1] = (float)(-(ug.lr / bc1));
+    }
+    FSRL_CUDA(cudaMemcpyAsync(tab_dev, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    a.adam_tab = tab_dev;
+    a.dbg = nullptr; a.dbg_step = -1;
+    if (const char* e = getenv("FSRL_PPO_PERSIST_DBG")) {
+        a.dbg = reinterpret_cast<long long*>(tab_dev + 2 * (size_t)pp::MAX_MB);
+        a.dbg_step = atoi(e);
+    }
     const size_t smem = pp::smem_bytes(ug.D);
     static size_t set = 0;
     if (smem > set) {

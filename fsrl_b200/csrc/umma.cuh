@@ -3,15 +3,15 @@
 // cp.async.bulk) completing on mbarriers, and the device-scope flag barriers that chain the
 // CTAs of the persistent grid.  Inline PTX only -- no CUTLASS / CuTe dependency.
 //
-// Operand layout ("plane layout", no swizzle).  A matrix X[row][col] of fp32 words is stored as
-//       X_img[col / 4][row][col % 4]            (planes of R rows x 16 bytes, R = rows of the block)
-// This single image serves BOTH operand orientations of tcgen05.mma with SWIZZLE_NONE descriptors:
-//   * K-major  (MN = row, K = col): 8 x 16 B core matrices are 8 consecutive rows of one plane:
-//         SBO (next 8 rows)  = 128 B,   LBO (next 4 columns = next plane) = 16 * R bytes
-//   * MN-major (MN = col, K = row): core matrix = 8 rows (K) x 4 columns (MN), again 128 B contiguous:
-//         SBO (next 4 columns = next plane) = 16 * R bytes,   LBO (next 8 rows) = 128 B
-// (canonical layouts: CUTLASS cute/atom/mma_traits_sm100.hpp, make_umma_desc, "INTERLEAVE" rows).
-// One MMA instruction consumes K = 8 tf32 values: 2 planes (K-major) or 8 rows (MN-major).
+// Operand layout ("plane layout", no swizzle).  A matrix X[mn][k] of fp32 words is stored as
+//       X_img[k / 4][mn][k % 4]            (planes of R rows x 16 bytes, R = MN extent of the block)
+// which is the canonical K-major SWIZZLE_NONE layout of tcgen05.mma (CUTLASS cute/atom/mma_traits_sm100.hpp,
+// make_umma_desc, "INTERLEAVE" rows): 8 x 16 B core matrices are 8 consecutive rows of one plane,
+//         SBO (next 8 rows) = 128 B,   LBO (next 4 k = next plane) = 16 * R bytes,
+// and one MMA instruction consumes K = 8 tf32 values = 2 planes.  tf32 operands can be read MN-major only from
+// the 128B_BASE32B swizzled layout (measured: tools/micro/umma_probe.cu -- the SWIZZLE_NONE MN-major
+// descriptor silently yields zeros), so an operand that is contracted over its other index is published by its
+// producer as a second, transposed K-major image.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -145,6 +145,7 @@ __device__ __forceinline__ bool flag_wait_ge(const unsigned* ctr, unsigned targe
     const long long t0 = clock64();
     while (flag_ld_acquire(ctr) < target) {
         if (clock64() - t0 > timeout_cycles) return false;
+        __nanosleep(20);     // leave the issue slots to the warps that share this scheduler
     }
     return true;
 }

@@ -84,7 +84,8 @@ def main():
                 print("    net %d %-3s max |m diff| %.3e of %.3e" % (i, name, dm, mm))
     # decode the images (they hold the operands of the LAST step = the only step)
     ws = policy._persist_ws.detach().cpu().numpy()
-    lib_net_ws = (ws.size - 128 - (3 * 7 + 1) * 32 - 32) // 3
+    from fsrl_b200 import _lib as _fl
+    lib_net_ws = int(_fl.lib.fsrl_ppo_persist_ws_floats(2, 8, 256)) - int(_fl.lib.fsrl_ppo_persist_ws_floats(1, 8, 256)) - 7 * 32 - 2 * 32 * 32
     x = sub.obs.cpu().double().numpy()
     perm = None
     for net in range(3):
@@ -135,6 +136,28 @@ def main():
                 run(policy2, batch2, 256, persist, seed=5)
             dt = (time.time() - t0) / 3
             print("  c2 epoch (2400 steps) %s: %.1f ms -> %.2f us / step" % ("persistent" if persist else "chain", dt * 1e3, dt * 1e6 / 2400))
+        # per-phase clock stamps of one step in the middle of the epoch (FSRL_PPO_PERSIST_DBG=<step>)
+        os.environ["FSRL_PPO_PERSIST_DBG"] = "1000"
+        run(policy2, batch2, 256, True, seed=5)
+        del os.environ["FSRL_PPO_PERSIST_DBG"]
+        ws = policy2._persist_ws.detach().cpu().numpy()
+        dbg = ws[-2 * 96 * 32:].view(np.int64).reshape(96, 32)
+        names = {1: "S done (h1 tile + W2 images)", 2: "G1 accumulators ready", 3: "head partial written", 4: "flag B passed",
+                 5: "dz2 + partials written", 6: "G2/G3 accumulators ready", 7: "G2/G3 epilogue done", 8: "flag D1 passed",
+                 9: "slices reduced, sumsq out", 10: "flag D2 passed", 11: "Adam done (step end)", 12: "[producer] flag A passed",
+                 13: "[producer] G1 copies issued", 14: "[producer] flag C passed", 16: "[mma] G1 first chunk landed",
+                 17: "[mma] G1 last chunk landed", 18: "[mma] G1 issued", 19: "[mma] G2/3 first chunk landed",
+                 20: "[mma] G2/3 last chunk landed", 21: "[mma] G2/3 issued", 22: "G2: mask applied", 23: "G2: dW1 partial stored",
+                 24: "norm known", 25: "small slices stepped", 26: "head gathered, loss gradient", 27: "dz2 images stored",
+                 28: "partial sums exchanged"}
+        rel = dbg - dbg[:, :1]
+        for grp, sel in (("G2 CTAs", [i for i in range(96) if i % 32 < 16]), ("G3 CTAs", [i for i in range(96) if i % 32 >= 16])):
+            print("  --- %s: cycles since step start (mean / min / max over CTAs) ---" % grp)
+            for i in sorted(names):
+                v = rel[sel, i]
+                print("    %2d %-34s %8.0f %8d %8d" % (i, names[i], v.mean(), v.min(), v.max()))
+        gt = dbg[:, 30]
+        print("  step start skew across CTAs (globaltimer ns): %d" % (gt.max() - gt.min()))
 
 
 if __name__ == "__main__":
