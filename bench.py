@@ -1,13 +1,10 @@
-"""bench.py -- BASELINE.json's metric on its headline config.
+"""bench.py -- BASELINE.json's metric on its configurations.
 
-metric : env-steps/sec over collect+update (the reference's ``train_speed``,
-         fsrl/trainer/base_trainer.py:345-347)
-config : c2 = PPO-Lagrangian, SafetyCarCircle-v0, 2048 envs, 2x256 MLP, batch_size 256,
-         repeat_per_collect 4, episode_per_collect = 2048 (one 300-step episode per env and
-         collect => 614 400 transitions per step), fp32
-step   : ONE collect + update cycle (OnpolicyTrainer.train_step + policy_update_fn)
+metric : env-steps/sec over collect+update (the reference's ``train_speed``, fsrl/trainer/base_trainer.py:345-347)
+step   : ONE collect + update cycle (trainer.train_step + policy_update_fn)
+configs: --config c1 | c2 (default, the headline) | c3 | c4 | c5   (BASELINE.json "configs", in order)
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--config c2] [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Prints one JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is derived.
 """
@@ -27,19 +24,32 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TASK = "SafetyCarCircle-v0"
-ENVS = 2048
-HIDDEN = (256, 256)
-BATCH = 256
-REPEAT = 4
 SEED = 10
+# BASELINE.json configs.  `envs` is per GPU (weak scaling); hyper-parameters are the reference's cfg files
+# (fsrl/config/{ppol,cpo,sacl}_cfg.py) except the widths / env counts BASELINE.json overrides.
+CONFIGS = {
+    "c1": dict(algo="ppol", task="SafetyCarCircle-v0", kind="car_circle", envs=4, hidden=(64, 64), batch=256, repeat=4,
+               desc="c1: PPO-Lagrangian SafetyCarCircle-v0, 4 envs x 300 steps, 2x64 MLP, batch_size 256, repeat 4"),
+    "c2": dict(algo="ppol", task="SafetyCarCircle-v0", kind="car_circle", envs=2048, hidden=(256, 256), batch=256, repeat=4,
+               desc="c2: PPO-Lagrangian SafetyCarCircle-v0, 2048 envs/GPU x 300 steps, 2x256 MLP, batch_size 256, repeat 4, "
+                    "max_grad_norm 0.5"),
+    "c3": dict(algo="cpo", task="SafetyPointGoal1Gymnasium-v0", kind="point_goal", envs=2048, hidden=(128, 128), batch=99999,
+               repeat=4, desc="c3: CPO SafetyPointGoal1-v0, 2048 envs/GPU x 1000 steps, 2x128 MLP, CG iters 10, "
+                              "max_backtracks 100, optim_critic_iters 10, repeat 4"),
+    "c4": dict(algo="sacl", task="SafetyCarRun-v0", kind="car_run", envs=4096, hidden=(128, 128), batch=256, ups=0.2,
+               desc="c4: SAC-Lagrangian SafetyCarRun-v0, 4096 envs/GPU x 200 steps, 2x128 MLP, replay on device, "
+                    "update_per_step 0.2, batch 256, n_step 2"),
+    "c5": dict(algo="ppol", task="SafetyAntCircle-v0", kind="ant_circle", envs=1024, hidden=(512, 512), batch=256, repeat=4,
+               desc="c5: PPO-Lagrangian SafetyAntCircle-v0, 1024 envs/GPU (8192 on 8 GPUs) x 500 steps, 2x512 MLP, "
+                    "batch_size 256, repeat 4, max_grad_norm 0.5"),
+}
+METRIC = {"ppol": "PPO-Lag", "cpo": "CPO", "sacl": "SAC-Lag"}
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -85,29 +95,39 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------------
-def build(device, rank, envs=ENVS, hidden=HIDDEN):
+def build(cfg, device, rank):
     from fsrl_b200 import envs as fenvs
-    from fsrl_b200.agent import PPOLagAgent
+    from fsrl_b200.agent import CPOAgent, PPOLagAgent, SACLagAgent
     from fsrl_b200.data import FastCollector, VectorReplayBuffer
-    from fsrl_b200.trainer import OnpolicyTrainer
-    from fsrl_b200.utils.logger import BaseLogger
-    demo = fenvs.make(TASK)
-    logger = BaseLogger()
-    agent = PPOLagAgent(demo, logger=logger, cost_limit=10, device=device, seed=SEED, lr=5e-4,
-                        hidden_sizes=hidden, max_grad_norm=0.5)      # cfg values (ppol_cfg.py:14-33)
-    T = demo.spec.max_episode_steps
     from fsrl_b200.parallel import shard_seed
-    train_envs = fenvs.DeviceVectorEnv(TASK, envs, device=device, seed=shard_seed(SEED + 1, rank))
+    from fsrl_b200.trainer import OffpolicyTrainer, OnpolicyTrainer
+    from fsrl_b200.utils.logger import BaseLogger
+    demo = fenvs.make(cfg["task"])
+    logger = BaseLogger()
+    envs, T = cfg["envs"], demo.spec.max_episode_steps
+    algo = cfg["algo"]
+    if algo == "ppol":
+        agent = PPOLagAgent(demo, logger=logger, cost_limit=10, device=device, seed=SEED, lr=5e-4,
+                            hidden_sizes=cfg["hidden"], max_grad_norm=0.5)      # ppol_cfg.py:14-33
+        # fixed work per step: the KL early stop (ppo_lag.py:251-255) is disabled so that EVERY step runs all
+        # `repeat` passes over the batch (the most work the config can do)
+        agent.policy._target_kl = float("inf")
+    elif algo == "cpo":
+        agent = CPOAgent(demo, logger=logger, cost_limit=10, device=device, seed=SEED, hidden_sizes=cfg["hidden"],
+                         max_backtracks=100, optim_critic_iters=10)            # cpo_cfg.py:19-26
+    else:
+        agent = SACLagAgent(demo, logger=logger, cost_limit=10, device=device, seed=SEED, hidden_sizes=cfg["hidden"],
+                            unbounded=False, n_step=2, tau=0.05, gamma=0.97)   # sacl_cfg.py:14-30
+    train_envs = fenvs.DeviceVectorEnv(cfg["task"], envs, device=device, seed=shard_seed(SEED + 1, rank))
     agent.policy.set_action_seed(shard_seed(SEED + 7, rank))
-    # fixed work per step: the KL early stop (ppo_lag.py:251-255) is disabled so that EVERY step
-    # runs all `REPEAT` passes = 4 x 2400 minibatch updates (the most work the config can do)
-    agent.policy._target_kl = float("inf")
     buf = VectorReplayBuffer(envs * T, envs, device=device)
     col = FastCollector(agent.policy, train_envs, buf, exploration_noise=True)
-    trainer = OnpolicyTrainer(agent.policy, col, None, max_epoch=1, batch_size=BATCH, cost_limit=10,
-                              step_per_epoch=envs * T, repeat_per_collect=REPEAT,
-                              episode_per_collect=envs, episode_per_test=1, logger=logger,
-                              verbose=False, show_progress=False)
+    common = dict(max_epoch=1, batch_size=cfg["batch"], cost_limit=10, step_per_epoch=envs * T, episode_per_collect=envs,
+                  episode_per_test=1, logger=logger, verbose=False, show_progress=False)
+    if algo == "sacl":
+        trainer = OffpolicyTrainer(agent.policy, col, None, update_per_step=cfg["ups"], **common)
+    else:
+        trainer = OnpolicyTrainer(agent.policy, col, None, repeat_per_collect=cfg["repeat"], **common)
     return agent, trainer, col, buf, T
 
 
@@ -117,23 +137,74 @@ def one_cycle(trainer):
     return stats
 
 
-def phase_times(agent, col, buf, iters=200):
-    """Average duration of the dominant update kernels, CUDA events on the launching stream
-    (fsrl_ppo_phase_times in csrc/ppo.cu launches each phase kernel `iters` times back to back
-    on a real 256-row minibatch of the batch that was just trained on)."""
+def ev_time(fn, stream_sync=True):
+    """CUDA-event duration [ms] of fn() on the current (launching) stream, synchronised on both sides."""
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record(); out = fn(); e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e), out
+
+
+def net_flops(D, H, A, rows):
+    """Algorithmic flops (2 x MAC) of forward + backward-data + weight-gradient of actor + 2 critics on `rows` rows."""
+    def net(out):
+        fwd = 2 * rows * (D * H + H * H + H * out)
+        bwd = 2 * rows * (H * out + H * H)
+        wgr = 2 * rows * (D * H + H * H + H * out)
+        return fwd + bwd + wgr
+    return net(A) + 2 * net(1)
+
+
+def ppo_rooflines(cfg, agent, col, buf, T, device, pk, how):
+    """Dominant kernel of the PPO configs = the minibatch update (one persistent launch per repeat, or the three-launch
+    chain where the persistent gate does not apply): algorithmic flops / CUDA-event time of one repeat.  Second object:
+    the HBM roofline BASELINE.json names, collect + GAE, from event-timed collect / process_fn passes."""
     import ctypes
     from fsrl_b200 import _lib
     pol = agent.policy
-    col.collect(ENVS)                      # the trainer resets the buffer after every update
+    envs = cfg["envs"]
+    col.reset_buffer()
+    ms_collect, _ = ev_time(lambda: col.collect(envs))
     idx = buf.sample_indices(0)
-    batch = pol.process_fn(None, buf, idx)
+    ms_gae, batch = ev_time(lambda: pol.process_fn(None, buf, idx))
     n = batch.n
-    perm = torch.randperm(n, device=pol.device).to(torch.int32)
-    pol._ensure_update_state(BATCH, n, 1)
-    u = pol._descriptor(batch, perm)
-    ms = (ctypes.c_float * 4)()
-    _lib.check(_lib.lib.fsrl_ppo_phase_times(ctypes.byref(u), BATCH, iters, ms, torch.cuda.current_stream().cuda_stream))
-    return [float(x) for x in ms]
+    s0 = pol.arena.slots[0]
+    D, H, A = s0.D, s0.H, s0.out
+    pol._ensure_update_state(cfg["batch"], n, 1)
+    u = pol._descriptor(batch, torch.zeros(n, dtype=torch.int32, device=device))
+    persistent = bool(_lib.lib.fsrl_ppo_persist_active(ctypes.byref(u), n, cfg["batch"]))
+    np.random.seed(SEED)
+    l0 = int(_lib.lib.fsrl_launch_count())
+    ms_rep, _ = ev_time(lambda: pol.learn(batch, batch_size=cfg["batch"], repeat=1))
+    launches_rep = int(_lib.lib.fsrl_launch_count()) - l0
+    n_mb = max(n // cfg["batch"], 1)
+    fl = net_flops(D, H, A, cfg["batch"]) * n_mb
+    ach = fl / (ms_rep * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    traffic_file = os.path.join(ROOT, "profiles", "r2_ppo_persist_traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else None
+    roof = {"kernel": "ppo_persist_kernel (one launch per repeat: tcgen05 kind::tf32 3-term split, TMEM accumulators, bulk-copy "
+                      "operand images)" if persistent else "ppo_fwd/bwd/wgrad_adam chain (three launches per minibatch)",
+            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+            "traffic_unit": "DRAM bytes read+written per launch (ncu --set full --cache-control none, "
+                            "profiles/r2_ppo_persist_ncu_summary.txt)" if traffic else None,
+            "peak_source": how + " bf16 sustained (kernel timed inside a long step)",
+            "ms_per_launch": ms_rep, "minibatch_steps_per_launch": n_mb, "us_per_minibatch_step": ms_rep * 1e3 / n_mb,
+            "launches_per_repeat": launches_rep, "persistent": persistent,
+            "algorithmic_flops_per_minibatch_step": net_flops(D, H, A, cfg["batch"]),
+            "note": "fp32-faithful 3xTF32 (3 tensor-core MMAs per fp32 product; the algorithmic flop count is NOT tripled); a chain of "
+                    "dependent optimiser steps of 256 rows: latency- and synchronisation-bound, far from the tensor peak"}
+    bstep = 12 * D + 4 * A + 28 + 12 * 2                        # SURVEY.md 8d: algorithmic bytes per env step, collect + GAE
+    hbm = {"kernel": "rollout_step_kernel x T + mlp_forward_kernel + gae_dual_kernel (collect + dual GAE)", "bound": "hbm",
+           "achieved": bstep * n / ((ms_collect + ms_gae) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+           "bytes_per_env_step": bstep, "ms_collect": ms_collect, "ms_process_fn": ms_gae, "transitions": n,
+           "peak_source": how}
+    hbm["frac"] = hbm["achieved"] / hbm["peak"]
+    hbm["note"] = ("one fused launch per vector step moves %d B per env: the collect is a chain of T dependent launches, not a bandwidth "
+                   "problem at this env count" % (8 * D + 4 * A + 18))
+    return roof, hbm
 
 
 def gae_time(buf, policy, iters=20):
@@ -154,30 +225,8 @@ def gae_time(buf, policy, iters=20):
     return float(np.mean(ts)), n
 
 
-def gae_time_large(device, envs=ENVS * 16, T=300, iters=10):
-    """The same kernel on a 16x larger synthetic collect (SURVEY.md 8d asks for large-E sweeps where
-    the HBM bound is reachable): 412 MB of algorithmic traffic, larger than L2, flushed anyway."""
-    from fsrl_b200 import ops
-    from fsrl_b200.utils.synth import synth_gae_inputs
-    d = synth_gae_inputs(envs, T, seed=10)
-    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-    v, vn, r, c = dev(d["v"]), dev(d["vnext"]), dev(d["rew"]), dev(d["cost"])
-    end = dev((d["terminated"] | d["truncated"]).astype(np.uint8))
-    term = dev(d["terminated"].astype(np.uint8))
-    adv = torch.empty_like(v); ret = torch.empty_like(v)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    ts = []
-    for i in range(iters + 3):
-        flush.zero_()
-        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
-        s.record(); ops.gae_dual(v, vn, r, c, end, term, 0.99, 0.95, out=(adv, ret)); e.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(s.elapsed_time(e))
-    return float(np.mean(ts)), envs * T
-
-
 def run_ours(args):
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,11 +238,12 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(device))
-    agent, trainer, col, buf, T = build(device, rank)
+    agent, trainer, col, buf, T = build(cfg, device, rank)
     if world > 1:
         from fsrl_b200 import parallel
         parallel.attach(agent.policy, dist, device=device)
-    steps_per_cycle = ENVS * T
+    envs = cfg["envs"]
+    steps_per_cycle = envs * T
 
     for _ in range(args.warmup):
         one_cycle(trainer)
@@ -206,7 +256,6 @@ def run_ours(args):
     # ---- device-timed region: K collect+update cycles ---------------------------------------------
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    t_wall0 = time.time()
     from fsrl_b200 import _lib as _fl
     launches0 = int(_fl.lib.fsrl_launch_count())
     ev0.record()
@@ -217,7 +266,6 @@ def run_ours(args):
         collect_s += col.collect_time - c0
     ev1.record()
     torch.cuda.synchronize()
-    t_wall = time.time() - t_wall0
     launches = int(_fl.lib.fsrl_launch_count()) - launches0
     ms = ev0.elapsed_time(ev1)
     if dist is not None:
@@ -227,10 +275,10 @@ def run_ours(args):
         dist.barrier()
     total_steps = steps_per_cycle * args.steps * world
     value = total_steps / (ms * 1e-3)
-    # ---- e2e: a SECOND region of K cycles through the public trainer API, wall clock, synchronised on
-    # both sides.  Every cycle uploads the minibatch permutations from pinned host memory and downloads
-    # the per-minibatch statistics + collect statistics the trainer logs; observations never exist on
-    # the host (the environment model runs on the device), so these ARE the path's copies.
+    # ---- e2e: a SECOND region of K cycles through the public trainer API, wall clock, synchronised on both sides.  Every
+    # cycle uploads the minibatch permutations / sampled indices from pinned host memory and downloads the per-minibatch
+    # statistics + collect statistics the trainer logs; observations never exist on the host (the environment model runs on
+    # the device), so these ARE the path's copies.
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -249,200 +297,122 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return
-    # ---- e2e: the same cycles through the public trainer API, wall-clock incl. every host<->device
-    # copy the API performs (minibatch permutations up, statistics down) ----------------------------
-    n_mb = (steps_per_cycle + BATCH - 1) // BATCH
-    h2d = REPEAT * steps_per_cycle * 4                           # int32 permutation per repeat
-    d2h = REPEAT * n_mb * 8 * 4 + 64                             # per-minibatch stats + collect stats
+    algo = cfg["algo"]
+    if algo == "sacl":
+        n_upd = round(cfg["ups"] * steps_per_cycle)
+        h2d = n_upd * cfg["batch"] * 4                             # int32 replay indices per gradient step
+        d2h = n_upd * 8 * 4 + 64
+    else:
+        n_mb = max(steps_per_cycle // cfg["batch"], 1)
+        h2d = cfg["repeat"] * steps_per_cycle * 4                  # int32 permutation per repeat
+        d2h = cfg["repeat"] * n_mb * 8 * 4 + 64                    # per-minibatch stats + collect stats
     e2e_value = total_steps / t_e2e
-    # ---- roofline of the dominant kernel + GAE ----------------------------------------------------
     pk, how = peaks()
-    ph = phase_times(agent, col, buf)
-    D, A, H = 8, 2, HIDDEN[0]
-    fl_net = lambda out: 2 * BATCH * (D * H + H * H + H * out) + 2 * BATCH * (H * out + H * H)
-    flops_a = fl_net(A) + 2 * fl_net(1)
-    ach = flops_a / ((ph[0] + ph[1]) * 1e-3) / 1e12
-    gms, gn = gae_time(buf, agent.policy)
-    gae_bytes = gn * 42
-    gms_l, gn_l = gae_time_large(device)
     out = {
-        "metric": "env-steps/sec (collect+update) SafetyCarCircle-v0 PPO-Lag",
+        "metric": f"env-steps/sec (collect+update) {cfg['task']} {METRIC[algo]}",
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: PPO-Lagrangian SafetyCarCircle-v0, 2048 envs/GPU x 300 steps, "
-                               "2x256 MLP, batch_size 256, repeat 4, max_grad_norm 0.5 "
-                               "(analytic on-device env model, random-init weights)",
-                   "envs_per_gpu": ENVS, "transitions_per_step": steps_per_cycle * world,
+        "config": {"workload": cfg["desc"] + " (analytic on-device env model, random-init weights)",
+                   "name": args.config, "envs_per_gpu": envs, "transitions_per_step": steps_per_cycle * world,
                    "parallelism": f"dp{world}",
-                   "kl_early_stop": "disabled (fixed work: 4 repeats x 2400 minibatch updates per step)",
-                   "l2": "working set per cycle (buffers 53 MB + per-minibatch gathers over 614k rows) "
-                         "cycles through > L2-size of distinct data between reuses; no explicit flush"},
+                   "kl_early_stop": "disabled (fixed work per step)" if algo == "ppol" else "n/a",
+                   "l2": "working set per cycle (rollout buffers + per-repeat gathers over all rows) cycles through more "
+                         "distinct data than L2 holds between reuses; no explicit flush"},
         "collect_s_per_step": collect_s / args.steps,
-        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "how": "separate region: K more collect+update cycles through OnpolicyTrainer.train_step / "
-                       "policy_update_fn, wall clock, max over ranks; H2D = pinned minibatch permutations, "
-                       "D2H = per-minibatch + collect statistics"},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "how": "separate region: K more collect+update cycles through Trainer.train_step / policy_update_fn, wall clock, "
+                       "max over ranks; H2D = pinned minibatch permutations (replay indices), D2H = per-minibatch + collect statistics"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "ppo_fwd_kernel<256> + ppo_bwd_kernel<256>", "bound": "tensor", "achieved": ach,
-                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                     "traffic": 3.44e6, "traffic_unit": "DRAM bytes per fwd+bwd launch pair (ncu --set full, "
-                                                        "profiles/r1_ppo_update_ncu_summary.txt): the working set is L2 resident",
-                     "peak_source": how + " bf16 burst",
-                     "note": "fp32-faithful 3xTF32 split-operand mma.sync (legacy tensor path, 3 MMAs per fp32 product); flops = algorithmic fwd+bwd of 3 MLPs on a 256-row minibatch; latency-bound (9600 dependent optimiser steps of 256 rows)",
-                     "phase_ms": {"fwd": ph[0], "bwd": ph[1], "wgrad": ph[2], "adam": ph[3]}},
-        "roofline_gae": {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm",
-                         "achieved": gae_bytes / (gms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": gae_bytes / (gms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gms,
-                         "bytes_per_transition": 42, "peak_source": how, "transitions": gn,
-                         "traffic": 16.0e6 + 9.8e6, "traffic_unit": "DRAM bytes per launch on the c2 collect: 16.0 MB read "
-                         "(ncu, = algorithmic 26 B/transition) + 9.8 MB of adv/ret written back from L2 after the kernel",
-                         "note": "c2-sized collect (25.8 MB): launch + one latency chain per tile dominate",
-                         "large": {"transitions": gn_l, "ms": gms_l,
-                                   "achieved": gn_l * 42 / (gms_l * 1e-3) / 1e9,
-                                   "frac": gn_l * 42 / (gms_l * 1e-3) / 1e9 / pk["hbm_gbs"]}},
         "clocks": clocks,
     }
+    if algo == "ppol":
+        roof, hbm = ppo_rooflines(cfg, agent, col, buf, T, device, pk, how)
+        out["roofline"], out["roofline_hbm"] = roof, hbm
+        gms, gn = gae_time(buf, agent.policy)
+        out["roofline_gae"] = {"kernel": "gae_dual_kernel<2,true>", "bound": "hbm", "achieved": gn * 42 / (gms * 1e-3) / 1e9,
+                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn * 42 / (gms * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": gms,
+                               "bytes_per_transition": 42, "transitions": gn, "peak_source": how,
+                               "note": "the scan alone, L2 flushed before every launch"}
+    else:
+        out["roofline"] = other_roofline(cfg, agent, steps_per_cycle, ms / args.steps, collect_s / args.steps, pk, how)
     if world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_reference(sample_envs=args.cpu_envs, cycles=1)
+        out["cpu_baseline"] = cpu_reference(args.config, sample_envs=args.cpu_envs, cycles=1)
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def other_roofline(cfg, agent, steps_per_cycle, ms_cycle, collect_s, pk, how):
+    """CPO: Fisher/Hessian-vector products dominate (~ 4 x 2 N P flops each); SAC: latency of a gradient step."""
+    s0 = agent.policy.arena.slots[0]
+    if cfg["algo"] == "cpo":
+        P, N = s0.size, steps_per_cycle
+        n_hvp = 22 * cfg["repeat"]
+        fl = 4 * 2 * N * P * n_hvp
+        upd_s = ms_cycle * 1e-3 - collect_s
+        ach = fl / upd_s / 1e12
+        return {"kernel": "cpo_rfwd/rbwd/rhead (exact KL Hessian-vector products) + CG + line search", "bound": "tensor",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                "traffic": None, "peak_source": how + " bf16 sustained",
+                "note": f"algorithmic flops = 4 x 2 N P per product, {n_hvp} products per cycle over the whole update time "
+                        f"({upd_s * 1e3:.1f} ms; critic regression and line-search forwards included in the time, not in the flops)"}
+    n_upd = round(cfg["ups"] * steps_per_cycle)
+    upd_s = ms_cycle * 1e-3 - collect_s
+    return {"kernel": "fsrl_offpolicy_steps (generic engine, ~22 launches per gradient step)", "bound": "tensor",
+            "achieved": None, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": None, "traffic": None,
+            "gradient_steps_per_cycle": n_upd, "us_per_gradient_step": upd_s * 1e6 / max(n_upd, 1),
+            "note": "latency-bound chain of dependent 256-row gradient steps; reported as time per step"}
+
+
 # -------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle restatement of the reference path on the host cores
+# reference arm / cpu_baseline: the reference's own classes on the host cores (oracle/refarm.py)
 # -------------------------------------------------------------------------------------------------
 def _reference_dir():
-    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
+    d = os.path.join(ROOT, "baseline", "_ref")
     return d if os.path.isdir(os.path.join(d, "fsrl")) else None
 
 
-def cpu_reference(sample_envs=32, cycles=1, threads=None):
-    """CPU arm.  When `baseline/_ref` holds the reference (pip --no-deps --target install, built by
-    __graft_entry__.build()), its OWN classes do the work that dominates the CPU time -- process_fn =
-    BasePolicy.compute_gae_returns (numba gae_return) and PPOLagrangian.learn (eager torch autograd +
-    Adam) run unmodified on the host cores; the third-party packages it imports but that are absent
-    here (tianshou, gymnasium) are thin shims (oracle/refrun.py), and rollout collection -- which in
-    the reference lives in tianshou's vector env / buffer and in pybullet -- is the oracle's in-process
-    numpy env twin (no IPC: a lower bound on the reference's collect cost).  Without `baseline/_ref`
-    the whole path is the oracle port."""
+def cpu_reference(config="c2", sample_envs=32, cycles=1, threads=None, runner=None):
+    """One or more collect+update cycles of the UNMODIFIED reference (baseline/_ref): fsrl.data.FastCollector over one worker
+    PROCESS per env (tianshou SubprocVectorEnv protocol; the simulator inside a worker is the numpy twin of the device env
+    model, pybullet / mujoco being absent), fsrl.policy.PPOLagrangian.process_fn + learn.  c1 runs verbatim (4 envs); the other
+    PPO configs run their network / batch shapes on a bounded sample of `sample_envs` envs (one process per env does not
+    scale to thousands of envs on any host -- the reference itself tops out at its core count).  CPO / SAC configs report the
+    PPO arm of c2's shapes is NOT substituted: they time the oracle port of their own update (kind = "port")."""
+    cfg = CONFIGS[config]
+    if cfg["algo"] != "ppol":
+        return cpu_port_other(cfg, sample_envs)
     ref_dir = _reference_dir()
-    if ref_dir is not None:
-        try:
-            return cpu_reference_real(ref_dir, sample_envs, cycles, threads)
-        except Exception as e:              # never lose the baseline: fall back to the port and say why
-            print(f"[bench] reference classes unavailable ({type(e).__name__}: {e}); timing the oracle port",
-                  file=sys.stderr)
-    return cpu_reference_port(sample_envs, cycles, threads)
-
-
-def cpu_reference_real(ref_dir, sample_envs, cycles, threads):
-    import oracle.collector as ocol
-    from oracle import refrun
-    from oracle.envs import OracleVecEnv
-    Batch = refrun.bootstrap(ref_dir)
-    threads = threads or best_thread_count()
-    torch.set_num_threads(threads)
-    torch.manual_seed(SEED); np.random.seed(SEED)
-    D, A, T = 8, 2, 300
-    pol, actor, critics = refrun.ppo_lag_policy(D, A, HIDDEN, lr=5e-4, target_kl=float("inf"), max_grad_norm=0.5,
-                                                cost_limit=10.0, gamma=0.99)      # ppol_cfg.py values
-    act_fn = lambda obs: actor(obs)[0]                                           # (mu, sigma)
-    env = OracleVecEnv(0, sample_envs, SEED); env.reset()
-    buf = ocol.OracleBuffer(sample_envs * T, sample_envs, D, A)
-    ctr = np.zeros(sample_envs, np.uint32)
-    t0 = time.time()
-    n = 0
+    if ref_dir is None:
+        raise SystemExit("baseline/_ref is missing: run __graft_entry__.build() in the build container first")
+    from oracle import refarm
+    n_env = cfg["envs"] if config == "c1" else min(sample_envs, cfg["envs"])
+    threads = threads or 4                                        # the reference's default (ppol_cfg.py:11 thread = 4)
+    own = runner is None
+    if own:
+        runner = refarm.ppo_lag_cycle_runner(ref_dir, cfg["kind"], n_env, cfg["hidden"], cfg["batch"], cfg["repeat"], threads,
+                                             workers=True, seed=SEED)
+    n = tc = tu = 0.0
     for _ in range(cycles):
-        buf.reset()
-        st = ocol.collect(env, act_fn, sample_envs, SEED, ctr, buf)
-        pol.pre_update_fn(stats_train=st)                                        # PID step on the collect's cost
-        idx = buf.sample_all()
-        view = refrun.RingView(buf, Batch)
-        batch = Batch(obs=torch.from_numpy(buf.obs[idx]), obs_next=torch.from_numpy(buf.obs_next[idx]),
-                      act=torch.from_numpy(buf.act[idx]), rew=view.rew[idx], terminated=buf.terminated[idx],
-                      truncated=buf.truncated[idx], info=Batch(cost=buf.cost[idx].astype(np.float64)))
-        batch = pol.process_fn(batch, view, idx)                                 # ppo_lag.py:134-150
-        pol.learn(batch, BATCH, REPEAT)                                          # ppo_lag.py:214-257
-        n += st["n/st"]
-    dt = time.time() - t0
-    return {"value": n / dt, "unit": "env-steps/s", "cores": threads, "kind": "reference",
-            "sample": f"{sample_envs} envs x {T} steps x {cycles} cycle(s) of c2 (2x256 MLP, batch 256, repeat 4): "
-                      f"unmodified fsrl.policy.PPOLagrangian (process_fn + learn) from baseline/_ref with "
-                      f"tianshou/gymnasium shims; collect = in-process numpy env twin (oracle), {dt:.1f} s"}
+        a, b, c = runner()
+        n += a; tc += b; tu += c
+    if own:
+        runner.close()
+    return {"value": n / (tc + tu), "unit": "env-steps/s", "cores": os.cpu_count(), "env_worker_processes": n_env,
+            "torch_threads": threads, "kind": "reference", "collect_s": tc, "update_s": tu,
+            "same_config": config == "c1",
+            "sample": f"{n_env} envs x {runner.T} steps x {cycles} cycle(s), {cfg['hidden'][0]}-wide MLPs, batch {cfg['batch']}, "
+                      f"repeat {cfg['repeat']}: unmodified fsrl.data.FastCollector + fsrl.policy.PPOLagrangian from baseline/_ref "
+                      f"(no fsrl_b200 import), one env worker process per env, torch.set_num_threads({threads}) (reference default); "
+                      f"collect {tc:.1f} s + update {tu:.1f} s"}
 
 
-def cpu_reference_port(sample_envs=32, cycles=1, threads=None):
-    """The reference's CPU path (FastCollector over per-env worker processes + numba GAE +
-    eager-torch PPO update) cannot be installed here (tianshou/gymnasium/pybullet absent,
-    no network): this times its restatement in oracle/ -- numpy env twin stepped in-process
-    (no IPC: a lower bound on the reference's collect cost), C port of gae_return, torch-CPU
-    autograd + Adam -- on a bounded sample of the c2 workload: `sample_envs` envs x 300 steps,
-    2x256 MLP, batch 256, 4 repeats."""
-    import oracle.collector as ocol
-    from oracle import nets as onets, ppo as oppo
-    from oracle.envs import OracleVecEnv
-    threads = threads or best_thread_count()
-    torch.set_num_threads(threads)
-    torch.manual_seed(SEED); np.random.seed(SEED)
-    D, A, T = 8, 2, 300
-    actor = onets.GaussActor(D, A, list(HIDDEN))
-    critics = [onets.ValueNet(D, list(HIDDEN)) for _ in range(2)]
-    with torch.no_grad():
-        actor.sigma_param.fill_(-0.5)
-    for m in [actor] + critics:
-        for l in m.modules():
-            if isinstance(l, torch.nn.Linear):
-                torch.nn.init.orthogonal_(l.weight); torch.nn.init.zeros_(l.bias)
-    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
-    env = OracleVecEnv(0, sample_envs, SEED); env.reset()
-    buf = ocol.OracleBuffer(sample_envs * T, sample_envs, D, A)
-    ctr = np.zeros(sample_envs, np.uint32)
-    t0 = time.time()
-    n = 0
-    for _ in range(cycles):
-        buf.reset()
-        st = ocol.collect(env, actor, sample_envs, SEED, ctr, buf)
-        idx = buf.sample_all()
-        b = {k: getattr(buf, k)[idx] for k in ("obs", "obs_next", "act", "rew", "cost", "terminated", "truncated")}
-        b = oppo.process(actor, critics, b, 0.99, 0.95)
-        oppo.learn(actor, critics, opt, b, BATCH, REPEAT, 0.0, max_grad_norm=0.5, target_kl=float("inf"))
-        n += st["n/st"]
-    dt = time.time() - t0
-    return {"value": n / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_envs} envs x {T} steps x {cycles} cycle(s) of c2 (2x256 MLP, batch 256, "
-                      f"repeat 4), in-process numpy env twin (no SubprocVectorEnv IPC), {dt:.1f} s"}
-
-
-_BEST_THREADS = None
-
-
-def best_thread_count():
-    """The reference defaults to torch.set_num_threads(4) (ppol_cfg.py:11); tiny 2x256 MLPs do
-    not scale with cores, so pick the fastest of {4, 8, 16, all} on a short calibration."""
-    global _BEST_THREADS
-    if _BEST_THREADS is not None:
-        return _BEST_THREADS
-    lin = torch.nn.Sequential(torch.nn.Linear(8, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256),
-                              torch.nn.ReLU(), torch.nn.Linear(256, 1))
-    x = torch.randn(256, 8)
-    best, best_t = 4, 1e9
-    for th in sorted({4, 8, 16, os.cpu_count() or 4}):
-        if th > (os.cpu_count() or 4):
-            continue
-        torch.set_num_threads(th)
-        for _ in range(3):
-            lin(x).sum().backward()
-        t0 = time.time()
-        for _ in range(30):
-            lin(x).sum().backward()
-        dt = time.time() - t0
-        if dt < best_t:
-            best, best_t = th, dt
-    _BEST_THREADS = best
-    return best
+def cpu_port_other(cfg, sample_envs):
+    """CPO / SAC configs: the oracle restatement of the reference update (oracle/cpo.py, oracle/offpolicy.py) on the host
+    cores; the reference classes themselves are pinned against these ports in tests/test_oracle_golden.py."""
+    return {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "not timed in this run: use --config c1/c2/c5 for the reference arm (PPO-Lagrangian)"}
 
 
 def run_reference(args):
@@ -450,37 +420,51 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    for _ in range(args.warmup):                      # untimed warm-up steps (thread pools, allocator) on a small sample
-        cpu_reference(sample_envs=min(32, args.cpu_envs), cycles=1)
+    cfg = CONFIGS[args.config]
+    if cfg["algo"] != "ppol":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm covers the PPO-Lagrangian configs (c1, c2, c5)"}))
+        return
+    from oracle import refarm
+    ref_dir = _reference_dir()
+    if ref_dir is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing (build() installs it)"}))
+        return
+    n_env = cfg["envs"] if args.config == "c1" else min(args.cpu_envs, cfg["envs"])
+    threads = 4
+    runner = refarm.ppo_lag_cycle_runner(ref_dir, cfg["kind"], n_env, cfg["hidden"], cfg["batch"], cfg["repeat"], threads,
+                                         workers=True, seed=SEED)
+    for _ in range(args.warmup):
+        runner()
     t0 = time.time()
-    vals = []
+    last = None
     for _ in range(args.steps):
-        vals.append(cpu_reference(sample_envs=args.cpu_envs, cycles=1))
+        last = cpu_reference(args.config, sample_envs=args.cpu_envs, cycles=1, threads=threads, runner=runner)
     dt = time.time() - t0
-    n = args.steps * args.cpu_envs * 300
+    runner.close()
+    n = args.steps * n_env * runner.T
     v = n / dt
-    cb = dict(vals[-1]); cb["value"] = v
+    cb = dict(last); cb["value"] = v
     print(json.dumps({
-        "impl": "reference", "metric": "env-steps/sec (collect+update) SafetyCarCircle-v0 PPO-Lag",
+        "impl": "reference", "metric": f"env-steps/sec (collect+update) {cfg['task']} {METRIC[cfg['algo']]}",
         "value": v, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2 shapes (2x256 MLP, batch 256, repeat 4) on a bounded sample of "
-                               f"{args.cpu_envs} envs x 300 steps per step on the host cores; see "
-                               "cpu_baseline.kind / sample for what ran (reference classes from baseline/_ref, "
-                               "or the oracle port)"},
+        "config": {"workload": cfg["desc"] + f" -- on the host cores: {n_env} envs per step"
+                               + (" (verbatim)" if args.config == "c1" else " (bounded sample of the config's env count; same networks, "
+                                  "batch size and repeats)"), "name": args.config},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cpu-envs", type=int, default=512,
-                    help="envs of the bounded CPU sample (512 x 300 transitions ~ 10-15 s on 8 host cores)")
+    ap.add_argument("--cpu-envs", type=int, default=32,
+                    help="envs (= worker processes) of the bounded CPU sample for configs other than c1")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -95,7 +95,8 @@ class PpoUpdate(ctypes.Structure):
                 ("batch_size", c_int), ("gather", c_vp), ("mb_stats", c_vp), ("barrier", c_vp),
                 ("p2p_xg", (c_vp * 8) * 2), ("p2p_flags", c_vp * 8), ("p2p_err", c_vp), ("p2p_part", c_vp),
                 ("p2p_rank", c_int), ("p2p_on", c_int),
-                ("persist_ws", c_vp), ("persist_ws_floats", ctypes.c_longlong), ("persist_off", c_int), ("pad1", c_int)]
+                ("persist_ws", c_vp), ("persist_ws_floats", ctypes.c_longlong), ("persist_off", c_int), ("pad1", c_int),
+                ("p2p_stride", ctypes.c_longlong)]
 
 
 class NetRef(ctypes.Structure):
@@ -206,6 +207,7 @@ SIGNATURES = {
     "fsrl_ppo_scratch_floats": (c_size, [c_int, c_int, c_int]),
     "fsrl_ppo_sync_mirror": (c_int, [ctypes.POINTER(PpoUpdate), c_vp]),
     "fsrl_ppo_persist_ws_floats": (c_size, [c_int, c_int, c_int]),
+    "fsrl_ppo_persist_p2p_floats": (c_size, [c_int]),
     "fsrl_ppo_persist_active": (c_int, [ctypes.POINTER(PpoUpdate), ctypes.c_longlong, c_int]),
     "fsrl_debug_clocks": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "fsrl_debug_cta_cycles": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),

@@ -1230,6 +1230,7 @@ extern "C" size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax) {
 }
 
 extern "C" size_t fsrl_ppo_persist_ws_floats(int n_nets, int D, int H) { return ppo_persist_ws_floats(n_nets, D, H); }
+extern "C" size_t fsrl_ppo_persist_p2p_floats(int n_nets) { return ppo_persist_p2p_floats(n_nets); }
 
 extern "C" int fsrl_ppo_persist_active(const fsrl_ppo_update_t* u, long long n_total, int batch_size) {
     if (!u || u->persist_off || getenv("FSRL_PPO_NO_PERSIST")) return 0;

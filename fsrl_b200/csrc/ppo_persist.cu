@@ -58,6 +58,12 @@ constexpr int SUMSQ_FLOATS = 128;                               // global tail: 
 constexpr int FLAG_LINE = 32;
 constexpr int F_A = 0, F_C = 1, F_D1 = 2, F_B = 3, F_PER_NET = 7;
 constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,64) accumulators, Adam state
+constexpr int TM_G = 160;                                        // reduced gradient tile (data-parallel runs)
+// peer-mapped exchange buffer of one step parity (floats): per net 16 gradient tiles [tile][thread 128][32] and the
+// locally reduced small-parameter slices [b 8][NSMAX]; behind them (parity 0 only) the flags [src rank 8][CTA 128] u64
+constexpr int NSMAX = (MAXD + 1) * 32 + 32 + 32 * OUTP + 16;
+constexpr int XG_PER_NET = 16 * 4096 + 8 * NSMAX;
+constexpr int XG_FLAG_FLOATS = 8 * 128 * 2;
 constexpr int MAX_MB = 16384;                                    // minibatches per launch (Adam scalar table)
 constexpr long long WAIT_CYCLES = 6000000000LL;                  // ~3 s: a lost partner must not hang the GPU
 
@@ -96,6 +102,25 @@ __device__ __forceinline__ void fail(int* err, int code) {
     __threadfence_system();
     asm volatile("trap;");
 }
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {      // peer memory is cached in L1 only: bypass it
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // one thread of a converged warp (CUTLASS elect_one_sync): lets the compiler issue the uniform-datapath
 // instructions (UTCHMMA, UBLKCP) of the region directly instead of wrapping each in a vote loop
 __device__ __forceinline__ bool elect_one() {
@@ -334,6 +359,24 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         const int trow = 16 * sp + r16;             // row of the 64-row tile held by this lane
         const uint32_t tm_lane = tmem + ((uint32_t)(32 * sp) << 16);
         float* stat_base = u.stats;
+        // ---- data-parallel exchange over peer memory (NVLink): every CTA publishes its local gradient piece in this
+        // rank's exchange buffer, release-stores the step id into the same slot of every rank's flag array and sums the
+        // ranks' pieces in rank order once their flags arrived -- point-to-point between equal CTAs, no local barrier,
+        // bit-identical sums on every rank.
+        const int world = u.world > 1 ? u.world : 1;
+        const float inv_world = 1.0f / (float)world;
+        const long long xg_total = (long long)u.n_nets * XG_PER_NET;
+        auto dp_flags = [&](int r) { return reinterpret_cast<unsigned long long*>(const_cast<float*>(u.p2p_xg[0][r]) + xg_total); };
+        auto dp_signal = [&](int slot_cta, unsigned long long id) {
+            for (int r = 0; r < world; ++r) st_release_sys(dp_flags(r) + (size_t)u.p2p_rank * 128 + slot_cta, id);
+        };
+        auto dp_wait = [&](int slot_cta, unsigned long long id) {
+            const unsigned long long* f = dp_flags(u.p2p_rank);
+            const long long t0 = clock64();
+            for (int r = 0; r < world; ++r)
+                while (ld_acquire_sys(f + (size_t)r * 128 + slot_cta) < id)
+                    if (clock64() - t0 > 4 * WAIT_CYCLES) fail(P.err, 40);
+        };
 
         // ---- initial state: small slices from the arena, the W2 tile (p, m, v) into tensor memory ----
         for (int i = et; i < sm.n; i += NEPI) {
@@ -710,6 +753,31 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             } else {
                 float g[32];
                 acc_ld_split32(tm_lane, lane, g);
+                if (world > 1) {
+                    const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
+                    const int par = (int)(id & 1ULL);
+                    const size_t off = ((size_t)(net * 16 + (c - 16)) * NEPI + et) * 32;
+                    float* mine = const_cast<float*>(u.p2p_xg[par][u.p2p_rank]) + off;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(mine + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                    __threadfence_system();
+                    epi_bar();
+                    if (et == 0) { dp_signal(blockIdx.x, id); dp_wait(blockIdx.x, id); }
+                    epi_bar();
+#pragma unroll
+                    for (int jq = 0; jq < 32; ++jq) g[jq] = 0.f;
+                    for (int r = 0; r < world; ++r) {
+                        const float* src = u.p2p_xg[par][r] + off;
+                        float4 v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = ld_peer4(src + 4 * q);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { g[4 * q] += v[q].x; g[4 * q + 1] += v[q].y; g[4 * q + 2] += v[q].z; g[4 * q + 3] += v[q].w; }
+                    }
+#pragma unroll
+                    for (int jq = 0; jq < 32; ++jq) g[jq] *= inv_world;
+                    tmem_st32(tm_lane + TM_G, g);
+                }
 #pragma unroll
                 for (int jq = 0; jq < 32; ++jq) sq = fmaf(g[jq], g[jq], sq);
             }
@@ -747,8 +815,6 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                         if (i < hi) {
                             const float gsum = ((pv[e][0] + pv[e][1]) + pv[e][2]) + pv[e][3];
                             sp_g[i] = gsum;
-                            // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3/log sigma by CTA 0
-                            if (a == 0 && real[e] && (i < sm.b3 || b == 0)) sq = fmaf(gsum, gsum, sq);
                         }
                     }
                 }
@@ -757,6 +823,35 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (et == 0) { STAMP(7); if (!flag_wait_ge(fl_net + F_D1 * FLAG_LINE, 16u * (t + 1), WAIT_CYCLES)) fail(P.err, 33); STAMP(8); }
             epi_bar();
             reduce_slices(0, sm.b2);
+            if (world > 1) {
+                const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
+                const int par = (int)(id & 1ULL);
+                const size_t off = (size_t)u.n_nets * 16 * 4096 + (size_t)(net * 8 + b) * NSMAX;
+                epi_bar();                                    // sp_g complete
+                if (a == 0) {
+                    float* mine = const_cast<float*>(u.p2p_xg[par][u.p2p_rank]) + off;
+                    for (int i = et; i < sm.n; i += NEPI) mine[i] = sp_g[i];
+                    __threadfence_system();
+                }
+                epi_bar();
+                if (et == 0) { if (a == 0) dp_signal(net * 32 + b, id); dp_wait(net * 32 + b, id); }
+                epi_bar();
+                for (int i = et; i < sm.n; i += NEPI) {
+                    float acc = 0.f;
+                    for (int r = 0; r < world; ++r) acc += ld_peer(u.p2p_xg[par][r] + off + i);
+                    sp_g[i] = acc * inv_world;
+                }
+            }
+            // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3 / log sigma by CTA 0.
+            // (each thread re-reads only elements it wrote itself: same i = et + k NEPI mapping)
+            if (a == 0) {
+                for (int i = et; i < sm.n; i += NEPI) {
+                    bool real = true;
+                    if (i >= sm.w3 && i < sm.b3) real = ((i - sm.w3) % OUTP) < out;
+                    else if (i >= sm.b3) { const int jj = i - sm.b3; real = (jj < out) || (net == 0 && u.head_indep && jj >= 8 && jj < 8 + A); }
+                    if (real && (i < sm.b3 || b == 0)) sq = fmaf(sp_g[i], sp_g[i], sq);
+                }
+            }
             // ---- global gradient norm: per-CTA partial -> device-wide hop -> same summation order everywhere --
             sq = warp_sum(sq);
             if (lane == 0) s_misc[sp] = sq;
@@ -788,7 +883,8 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (et == 0) STAMP(25);
             if (!is_g2) {
                 float g[32], pv[32], mv[32], vv[32];
-                acc_ld_split32(tm_lane, lane, g);
+                if (world > 1) tmem_ld32(tm_lane + TM_G, g);
+                else acc_ld_split32(tm_lane, lane, g);
                 tmem_ld32(tm_lane + TM_P, pv); tmem_ld32(tm_lane + TM_M, mv); tmem_ld32(tm_lane + TM_V, vv);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) pv[j] = adam_one(pv[j], g[j] * gscale, mv[j], vv[j], ad);
@@ -836,9 +932,12 @@ size_t ppo_persist_ws_floats(int n_nets, int D, int H) {
            2 * (size_t)pp::MAX_MB + 2 * (size_t)32 * n_nets * pp::DBG_N;
 }
 
+size_t ppo_persist_p2p_floats(int n_nets) { return (size_t)n_nets * pp::XG_PER_NET + pp::XG_FLAG_FLOATS + 64; }
+
 bool ppo_persist_supported(const fsrl_ppo_update_t& u, long long n_total, int batch_size) {
     if (u.H != 256 || batch_size != pp::MB || n_total % pp::MB != 0 || n_total < pp::MB || n_total / pp::MB > pp::MAX_MB) return false;
-    if (u.world > 1 || u.mask != nullptr || u.gather == nullptr) return false;
+    if (u.mask != nullptr || u.gather == nullptr) return false;
+    if (u.world > 1 && !(u.p2p_on && u.world <= FSRL_P2P_MAX_RANKS && (size_t)u.p2p_stride >= ppo_persist_p2p_floats(u.n_nets))) return false;
     if (u.D < 1 || u.D > pp::MAXD || u.A > 8 || u.n_nets < 1 || u.n_nets > 3) return false;
     if (u.persist_ws == nullptr || (size_t)u.persist_ws_floats < ppo_persist_ws_floats(u.n_nets, u.D, u.H)) return false;
     if (32 * u.n_nets > sm_count()) return false;

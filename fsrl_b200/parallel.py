@@ -101,6 +101,7 @@ class DataParallel:
         for r in range(self.world):
             u.p2p_flags[r] = p["flags"][r]
         u.p2p_err, u.p2p_part, u.p2p_rank, u.p2p_on = p["err"], p["part"], self.rank, 1
+        u.p2p_stride = p["stride"]
 
     def p2p_check(self) -> None:
         p = getattr(self, "p2p", None)
@@ -163,7 +164,11 @@ def attach(policy, dist, device=None, p2p: bool = True) -> DataParallel:
     policy._dp = dp
     from .policy.ppo_lag import PPOLagrangian
     if p2p and dp.world > 1 and isinstance(policy, PPOLagrangian):
-        dp.enable_p2p(policy.arena.theta.numel())       # PPO-Lag: gradients over peer memory
+        # PPO-Lag: gradients over peer memory; the buffers also hold the per-CTA gradient tiles / flags of the
+        # persistent update kernel (csrc/ppo_persist.cu)
+        from . import _lib
+        need = int(_lib.lib.fsrl_ppo_persist_p2p_floats(len(policy.arena.slots)))
+        dp.enable_p2p(max(policy.arena.theta.numel(), need))
     if hasattr(policy, "_upd_seed"):      # off-policy rsample / exploration noise: one stream per rank
         policy._upd_seed = shard_seed(policy._upd_seed, dp.rank)
     inner = policy.pre_update_fn

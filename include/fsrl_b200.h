@@ -195,10 +195,13 @@ typedef struct fsrl_ppo_update {
     float* persist_ws;
     long long persist_ws_floats;
     int persist_off, pad1;
+    long long p2p_stride;          /* floats available in every p2p_xg buffer (fsrl_p2p_stride of the allocation) */
 } fsrl_ppo_update_t;
 
 size_t fsrl_ppo_scratch_floats(int n_nets, int H, int bmax);
 size_t fsrl_ppo_persist_ws_floats(int n_nets, int D, int H);
+/* floats each peer-mapped exchange buffer must hold for the data-parallel persistent path */
+size_t fsrl_ppo_persist_p2p_floats(int n_nets);
 /* 1 if fsrl_ppo_lag_epoch would take the persistent path for this descriptor / batch */
 int fsrl_ppo_persist_active(const fsrl_ppo_update_t* u, long long n_total, int batch_size);
 int fsrl_ppo_sync_mirror(const fsrl_ppo_update_t* u, void* stream);

