@@ -175,8 +175,12 @@ class PPOLagrangian(LagrangianPolicy):
         slot = 0
         self._stats_dev.zero_()
         rows = []
-        perm_dev = torch.empty(n, dtype=torch.int32, device=ar.device)
-        perm_host = torch.empty(n, dtype=torch.int32).pin_memory()
+        # staging buffers of the minibatch permutation: allocated once (pinning is a millisecond-scale system call)
+        if getattr(self, "_perm_n", -1) != n:
+            self._perm_dev = torch.empty(n, dtype=torch.int32, device=ar.device)
+            self._perm_host = torch.empty(n, dtype=torch.int32).pin_memory()
+            self._perm_n = n
+        perm_dev, perm_host = self._perm_dev, self._perm_host
         next_perm = None
         with torch.cuda.device(ar.device):
             if self._mirror_dirty:

@@ -84,7 +84,9 @@ def _persistent_update(rank, dist):
     stats = col.collect(n_episode=64)
     policy.pre_update_fn(stats_train=stats)
     idx = buf.sample_indices(0)
-    batch = policy.process_fn(None, buf, idx)
+    from test_ppo_scale_gpu import _sub_batch
+    full = policy.process_fn(None, buf, idx)
+    batch = _sub_batch(policy, full, 8 * 256)            # 8 optimiser steps: short enough to compare element-wise
     policy._target_kl = 1e9
     policy._dp_batch = 256
     policy._ensure_update_state(256, batch.n, 1)
@@ -135,9 +137,9 @@ def test_two_rank_persistent_update_matches_chain_exchange():
     assert np.array_equal(pers0, pers1), np.abs(pers0 - pers1).max()      # lock-step: bit-identical parameters
     assert np.array_equal(chain0, chain1)
     assert moved0 > 0 and np.isfinite(pers0).all()
-    # same global-minibatch update as the chain's exchange kernel, up to fp32 summation order (75 Adam steps)
+    # same global-minibatch update as the chain's exchange kernel, up to fp32 summation order (8 Adam steps)
     d = np.abs(pers0 - chain0)
-    assert (d > 2e-5).mean() <= 2e-3 and d.max() <= 0.5 * 5e-4 * 75, (d.max(), (d > 2e-5).mean())
+    assert (d > 2e-5).mean() <= 1e-3 and d.max() <= 2 * 5e-4 * 8, (d.max(), (d > 2e-5).mean())   # (an element can move lr per step either way)
 
 
 # ---------------------------------------------------------------------------------------------------
