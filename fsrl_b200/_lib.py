@@ -194,6 +194,7 @@ SIGNATURES = {
     "fsrl_cpo_head": (c_int, [ctypes.POINTER(Cpo), c_int, c_vp, c_vp]),
     "fsrl_focops_head": (c_int, [ctypes.POINTER(Cpo), c_f64, c_f64, c_f64, c_vp, c_vp]),
     "fsrl_cpo_hvp": (c_int, [ctypes.POINTER(Cpo), c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "fsrl_cg_solve": (c_int, [ctypes.POINTER(Cpo), c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_longlong, c_int, c_f64, c_f64, c_vp]),
     "fsrl_vec_dot": (c_int, [c_vp, c_vp, ctypes.c_longlong, c_vp, c_vp]),
     "fsrl_vec_axpby": (c_int, [c_f64, c_vp, c_f64, c_vp, ctypes.c_longlong, c_vp]),
     "fsrl_vec_add_scaled": (c_int, [c_vp, c_f64, c_vp, c_vp, ctypes.c_longlong, c_vp]),

@@ -505,6 +505,70 @@ extern "C" int fsrl_vec_add_scaled(const float* a, double s, const float* b, flo
     return FSRL_OK;
 }
 
+// ---- conjugate gradients with every scalar on the device (cpo.py:184-204, trpo_lag.py:261-283) -------------------
+// state (doubles): [0] rs_old  [1] p.z / r.r scratch  [2] alpha  [3] beta  [4] done flag (0 / 1)
+__global__ void cg_alpha_kernel(double* st) {          // after dot(p, z) -> st[1]
+    if (st[4] == 0.0) st[2] = st[0] / st[1];
+}
+__global__ void cg_beta_kernel(double* st, double tol) {   // after dot(r, r) -> st[1]
+    if (st[4] != 0.0) return;
+    const double rs_new = st[1];
+    if (rs_new < tol) { st[4] = 1.0; return; }              // the reference's `break`: x, r updated, p not
+    st[3] = rs_new / st[0];
+    st[0] = rs_new;
+}
+// x += alpha p ; r -= alpha z      (python: vec_axpby((float)alpha, p, 1, x), vec_axpby((float)-alpha, z, 1, r))
+__global__ void cg_step_xr_kernel(const double* st, const float* __restrict__ p, const float* __restrict__ z,
+                                  float* __restrict__ x, float* __restrict__ r, long long n) {
+    if (st[4] != 0.0) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = (float)st[2], ma = (float)(-st[2]);
+    x[i] = a * p[i] + 1.0f * x[i];
+    r[i] = ma * z[i] + 1.0f * r[i];
+}
+// p = r + beta p                   (python: vec_axpby(1, r, (float)beta, p))
+__global__ void cg_step_p_kernel(const double* st, const float* __restrict__ r, float* __restrict__ p, long long n) {
+    if (st[4] != 0.0) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p[i] = 1.0f * r[i] + (float)st[3] * p[i];
+}
+
+// x = CG(H, rhs) with H v = fsrl_cpo_hvp(v): `nsteps` iterations enqueued back to back, no host synchronisation -- the
+// residual test of the reference's loop (`if rs_new < tol: break`) is a device flag that turns the remaining
+// iterations into no-ops, so the result equals the host-driven loop's.  work = 4 vectors of P floats (x, r, p, z are
+// carved from it; x_out may alias none of them), state_dev = 8 doubles.  Replaces the per-iteration .item() round
+// trips of policy/trust_region.py::_cg (single-GPU runs; data-parallel runs all-reduce every product on the host side).
+extern "C" int fsrl_cg_solve(const fsrl_cpo_t* d, const float* rhs, float* x_out, float* work, float* v_w2n_scratch,
+                             double* state_dev, long long P, int nsteps, double tol, double damping, void* stream) {
+    int rc = cpo_check(d);
+    if (rc) return rc;
+    FSRL_REQUIRE(rhs && x_out && work && v_w2n_scratch && state_dev && P > 0 && nsteps >= 0, "cg_solve: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float *x = work, *r = work + P, *p = work + 2 * P, *z = work + 3 * P;
+    const unsigned nb = (unsigned)((P + 255) / 256);
+    FSRL_CUDA(cudaMemsetAsync(x, 0, sizeof(float) * P, s));
+    FSRL_CUDA(cudaMemcpyAsync(r, rhs, sizeof(float) * P, cudaMemcpyDeviceToDevice, s));
+    FSRL_CUDA(cudaMemcpyAsync(p, rhs, sizeof(float) * P, cudaMemcpyDeviceToDevice, s));
+    FSRL_CUDA(cudaMemsetAsync(state_dev, 0, sizeof(double) * 8, s));
+    vec_dot_kernel<<<1, 1024, 0, s>>>(r, r, P, state_dev + 0);      // rs_old
+    FSRL_LAUNCH_CHECK();
+    for (int it = 0; it < nsteps; ++it) {
+        rc = fsrl_cpo_hvp(d, p, v_w2n_scratch, z, damping, stream);
+        if (rc) return rc;
+        vec_dot_kernel<<<1, 1024, 0, s>>>(p, z, P, state_dev + 1);
+        cg_alpha_kernel<<<1, 1, 0, s>>>(state_dev);
+        cg_step_xr_kernel<<<nb, 256, 0, s>>>(state_dev, p, z, x, r, P);
+        vec_dot_kernel<<<1, 1024, 0, s>>>(r, r, P, state_dev + 1);
+        cg_beta_kernel<<<1, 1, 0, s>>>(state_dev, tol);
+        cg_step_p_kernel<<<nb, 256, 0, s>>>(state_dev, r, p, P);
+        FSRL_LAUNCH_CHECK();
+    }
+    FSRL_CUDA(cudaMemcpyAsync(x_out, x, sizeof(float) * P, cudaMemcpyDeviceToDevice, s));
+    return FSRL_OK;
+}
+
 // wgrad of the listed nets into an arbitrary destination vector (theta layout of ONE net): used for
 // g = grad objective and b = grad(-cost surrogate)
 extern "C" int fsrl_engine_wgrad_to(const fsrl_engine_t* e, const fsrl_netlist_t* nl, const fsrl_eng_input_t* in,

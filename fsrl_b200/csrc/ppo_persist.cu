@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         if (elect_one()) {
             unsigned qq = 0;
             for (int t = 0; t < P.n_mb; ++t) {
-                if (!flag_wait_ge(fl_net + F_A * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 10);
+                if (!flag_wait_ge<true>(fl_net + F_A * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 10);
                 STAMP(12);
                 fence_proxy_async();
                 for (int j = 0; j < 4; ++j, ++qq) {               // G1: K = k in chunks of 64
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     bulk_g2s(dst + 40960, wsn + (size_t)I_W2A_LO * IMG + bo, 8192, &bar_full[s]);
                 }
                 STAMP(13);
-                if (!flag_wait_ge(fl_net + F_C * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 12);
+                if (!flag_wait_ge<true>(fl_net + F_C * FLAG_LINE, 32u * (t + 1), WAIT_CYCLES)) fail(P.err, 12);
                 STAMP(14);
                 fence_proxy_async();
                 const int ia = is_g2 ? I_W2B_HI : I_DZT_HI, ib = is_g2 ? I_DZA_HI : I_H1T_HI;

@@ -227,6 +227,60 @@ class PPOLagrangian(LagrangianPolicy):
         self._log_stats(np.concatenate(rows, axis=0), u)
         self.logger.store(gradient_steps=self.gradient_steps, tab="update")
 
+    # ---- the reference's per-piece loss hooks (ppo_lag.py:152-212) ------------------------------------------------
+    # ``learn`` never calls these: the persistent launch / kernel chain evaluates both losses, their gradients and the
+    # optimiser step fused.  They exist for code written against the reference that calls the pieces itself (custom
+    # training loops, examples/customized): eager autograd on the device through the policy's nn.Modules, whose
+    # parameters alias the kernels' arena -- so gradients taken from these losses update the same weights.
+    def _piece(self, minibatch, name: str, i: int = None) -> torch.Tensor:
+        x = getattr(minibatch, name)
+        x = x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))
+        x = x.to(self.device)
+        return x if i is None else x[..., i]
+
+    def critics_loss(self, minibatch):
+        """Sum over critics of the (optionally clipped) squared return error; ``(loss, stats)`` like the reference."""
+        total, stats = 0.0, {}
+        obs = self._piece(minibatch, "obs").float()
+        for i, critic in enumerate(self.critics):
+            v = critic(obs).flatten()
+            target = self._piece(minibatch, "rets", i)
+            err = (target - v) ** 2
+            if self._value_clip:
+                v_old = self._piece(minibatch, "values", i)
+                v_lim = v_old + torch.clamp(v - v_old, -self._eps_clip, self._eps_clip)
+                err = torch.maximum(err, (target - v_lim) ** 2)
+            loss_i = err.mean()
+            total = total + loss_i
+            stats["loss/vf" + str(i)] = loss_i.item()
+        stats["loss/vf_total"] = total.item()
+        return total, stats
+
+    def policy_loss(self, batch, dist):
+        """Clipped surrogate on the reward advantage + lambda-weighted cost-advantage terms, rescaled by
+        1 / (sum(lambda) + 1); advantages are standardised per call, in place, like the reference does."""
+        act, logp_old = self._piece(batch, "act"), self._piece(batch, "logp_old")
+        logp = dist.log_prob(act)
+        ratio = torch.exp(logp - logp_old).float()
+        ratio = ratio.reshape(ratio.shape[0], -1).t()
+        advs = self._piece(batch, "advs")
+        if self._norm_adv:
+            for i in range(self.critics_num):
+                col = advs[..., i]
+                advs[..., i] = (col - col.mean()) / col.std()
+        a_r = advs[..., 0]
+        unclipped, clipped = ratio * a_r, torch.clamp(ratio, 1.0 - self._eps_clip, 1.0 + self._eps_clip) * a_r
+        lower = torch.minimum(unclipped, clipped)
+        if self._dual_clip:
+            lower = torch.where(a_r < 0, torch.maximum(lower, self._dual_clip * a_r), lower)
+        loss_rew = -lower.mean()
+        cost_terms = [ratio * advs[..., i] for i in range(1, self.critics_num)] if self.use_lagrangian else []
+        loss_safety, stats = self.safety_loss(cost_terms)
+        loss = stats["loss/rescaling"] * (loss_rew + loss_safety)
+        stats.update({"loss/actor_rew": loss_rew.item(), "loss/actor_total": loss.item(),
+                      "loss/kl": (logp_old - logp).mean().item()})
+        return loss, stats
+
     def _log_stats(self, st: np.ndarray, u) -> None:
         """Rebuild the reference's per-minibatch ``loss/*`` keys (ppo_lag.py:169-170,205-211,247;
         lagrangian_base.py:158-165) from the device statistics: one D2H copy per repeat."""

@@ -119,8 +119,19 @@ class TrustRegionMixin:
         self._gvec(out)      # H = sum_r w_r H_r (the damping term carries through: sum_r w_r = 1)
 
     def _cg(self, d, rhs: torch.Tensor, out: torch.Tensor, nsteps: int = 10, residual_tol: float = 1e-8):
-        """cpo.py:184-204, vectors on the device, two scalars per iteration on the host."""
+        """cpo.py:184-204.  Single GPU: the whole solve is enqueued by ``fsrl_cg_solve`` -- vectors AND scalars stay on
+        the device, no host round trip per iteration.  Data parallel: every Hessian-vector product is all-reduced
+        (``_hvp`` -> ``_gvec``), so the loop is driven from the host with two scalar reads per iteration."""
         v = self._vec
+        if self._dpw is None:
+            n = rhs.numel()
+            if getattr(self, "_cg_work", None) is None or self._cg_work.numel() < 4 * n:
+                self._cg_work = torch.empty(4 * n, dtype=torch.float32, device=rhs.device)
+                self._cg_state = torch.zeros(8, dtype=torch.float64, device=rhs.device)
+            _lib.check(_lib.lib.fsrl_cg_solve(ctypes.byref(d), rhs.data_ptr(), out.data_ptr(), self._cg_work.data_ptr(),
+                                              self._v_w2n.data_ptr(), self._cg_state.data_ptr(), n, int(nsteps),
+                                              float(residual_tol), float(self._damping_coeff), self._s()))
+            return
         x, r, p, z = v["x"], v["r"], v["p"], v["z"]
         x.zero_(); r.copy_(rhs); p.copy_(rhs)
         rs_old = self._dotp(r, r)

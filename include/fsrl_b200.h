@@ -353,6 +353,11 @@ int fsrl_focops_head(const fsrl_cpo_t* d, double inv_lambda, double nu, double e
                      void* stream);
 int fsrl_cpo_hvp(const fsrl_cpo_t* d, const float* v, float* v_w2n_scratch, float* hv, double damping,
                  void* stream);
+/* x_out = CG(H, rhs), H v = fsrl_cpo_hvp(v): CPO._conjugate_gradients (fsrl/policy/cpo.py:184-204) / TRPOLagrangian
+ * (trpo_lag.py:261-283) with every scalar on the device -- `nsteps` iterations enqueued without host synchronisation,
+ * the reference's residual break is a device flag.  work: 4 P floats, state_dev: 8 doubles. */
+int fsrl_cg_solve(const fsrl_cpo_t* d, const float* rhs, float* x_out, float* work, float* v_w2n_scratch,
+                  double* state_dev, long long P, int nsteps, double tol, double damping, void* stream);
 int fsrl_vec_dot(const float* a, const float* b, long long n, double* out_dev, void* stream);
 int fsrl_vec_axpby(double a, const float* x, double b, float* y, long long n, void* stream);
 int fsrl_vec_add_scaled(const float* a, double s, const float* b, float* out, long long n, void* stream);

@@ -156,6 +156,10 @@ def main():
             for i in sorted(names):
                 v = rel[sel, i]
                 print("    %2d %-34s %8.0f %8d %8d" % (i, names[i], v.mean(), v.min(), v.max()))
+        for net in range(3):
+            sel = list(range(32 * net, 32 * net + 32))
+            print("  net %d: dz2 done %6.0f  slices reduced %6.0f  step end %6.0f (mean cycles since step start)" % (
+                net, rel[sel, 5].mean(), rel[sel, 9].mean(), rel[sel, 11].mean()))
         gt = dbg[:, 30]
         print("  step start skew across CTAs (globaltimer ns): %d" % (gt.max() - gt.min()))
 
