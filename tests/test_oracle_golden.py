@@ -700,7 +700,8 @@ def test_public_attributes_and_safety_loss_match_reference(golden_dir):
              "SACLagrangian": "sacl", "DDPGLagrangian": "ddpgl"}
     for cls, kind in kinds.items():
         pol = _our_policy(kind)
-        missing = [n for n in g["attrs"][cls] if not hasattr(pol, n) and n not in fused]
+        # PPOLagrangian carries eager-autograd versions of the per-piece hooks; the other learners' pieces are fused
+        missing = [n for n in g["attrs"][cls] if not hasattr(pol, n) and (n not in fused or kind == "ppol")]
         # compute_nstep_returns lives on the off-policy learners (it needs their replay descriptor)
         missing = [n for n in missing if not (n == "compute_nstep_returns" and kind in ("ppol", "cpo", "trpol", "focops"))]
         assert not missing, (cls, missing)

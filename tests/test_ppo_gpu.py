@@ -237,3 +237,36 @@ def test_ppo_value_clip_and_dual_clip_match_oracle():
         want = np.array([s[key] for s in ostats]); got = np.asarray(st[key])
         np.testing.assert_allclose(got[:K], want[:K], rtol=3e-4, atol=3e-6, err_msg=key)
         np.testing.assert_allclose(got, want, rtol=5e-2, atol=5e-4, err_msg=key)
+
+
+def test_piecewise_loss_hooks_match_oracle():
+    """policy_loss / critics_loss (ppo_lag.py:152-212), the hooks custom training code calls: eager autograd through the
+    arena-backed modules, against the oracle's losses on the same (whole-batch) minibatch; their gradients land in the
+    parameters the kernels read."""
+    from oracle import ppo as oppo
+    from fsrl_b200.data import Batch
+    hidden, lag = (64, 64), 0.6
+    policy, venv, buf, col = build_ppo("SafetyCarCircle-v0", hidden=hidden, n_env=2, max_grad_norm=None)
+    col.collect(n_episode=2)
+    policy.lag_optims[0].lagrangian = lag
+    actor, critics = oracle_nets(policy, hidden)
+    idx = buf.sample_indices(0)
+    batch = policy.process_fn(None, buf, idx)
+    g = lambda t: t.detach().cpu().numpy().copy()
+    ob = dict(obs=g(batch.obs), act=g(batch.act), advs=g(batch.advs), rets=g(batch.rets), values=g(batch.values), logp_old=g(batch.logp_old))
+    n = batch.n
+    opt = torch.optim.Adam([p for m in [actor] + critics for p in m.parameters()], lr=5e-4)
+    np.random.seed(1)
+    want = oppo.learn(actor, critics, opt, ob, n, 1, lag, max_grad_norm=None, target_kl=1e9)[0]
+    mb = Batch(obs=batch.obs, act=batch.act, logp_old=batch.logp_old, advs=batch.advs.clone(), rets=batch.rets, values=batch.values)
+    dist = policy(mb).dist
+    loss_a, st_a = policy.policy_loss(mb, dist)
+    loss_c, st_c = policy.critics_loss(mb)
+    for key in ("loss/actor_rew", "loss/actor_safety", "loss/actor_total", "loss/kl"):
+        assert st_a[key] == pytest.approx(want[key], rel=3e-4, abs=3e-6), key
+    for key in ("loss/vf0", "loss/vf1", "loss/vf_total"):
+        assert st_c[key] == pytest.approx(want[key], rel=3e-4, abs=3e-6), key
+    assert float(loss_a + 0.25 * loss_c) == pytest.approx(want["loss/total"], rel=3e-4, abs=3e-6)
+    (loss_a + 0.25 * loss_c).backward()
+    gw = policy.critics[0].last.model[0].weight.grad
+    assert gw is not None and torch.isfinite(gw).all() and gw.abs().sum() > 0
