@@ -160,6 +160,11 @@ def main():
             sel = list(range(32 * net, 32 * net + 32))
             print("  net %d: dz2 done %6.0f  slices reduced %6.0f  step end %6.0f (mean cycles since step start)" % (
                 net, rel[sel, 5].mean(), rel[sel, 9].mean(), rel[sel, 11].mean()))
+            print("         G1 ready %6.0f | head out %6.0f | B passed %6.0f | loss %6.0f | images %6.0f | sums %6.0f | C arrive %6.0f" % tuple(
+                rel[sel, i].mean() for i in (2, 3, 4, 26, 27, 28, 5)))
+            b0 = [i for i in sel if i % 8 == 0]
+            print("         (b == 0 CTAs)        B passed %6.0f | loss %6.0f | images %6.0f | sums %6.0f | C arrive %6.0f" % tuple(
+                rel[b0, i].mean() for i in (4, 26, 27, 28, 5)))
         gt = dbg[:, 30]
         print("  step start skew across CTAs (globaltimer ns): %d" % (gt.max() - gt.min()))
 
