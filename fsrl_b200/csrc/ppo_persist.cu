@@ -493,6 +493,14 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                 p_ret = __ldg(u.ret + (long long)(net - 1) * u.ld + grow);
                 if (u.value_clip) p_val = __ldg(u.values + (long long)(net - 1) * u.ld + grow);
             }
+            // the Gaussian's scale does not depend on the head: sigma and 1 / sigma before the GEMM wait (the actor's loss
+            // phase is the longest of the three networks and every network waits for it at the global-norm hop)
+            float p_ls[8], p_rsg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                p_ls[j] = (net == 0 && j < A) ? sp_p[sm.b3 + 8 + j] : 0.f;
+                p_rsg[j] = 1.0f / expf(p_ls[j]);
+            }
 
             // ---- G1 epilogue: h2 = relu(acc + b2), head partial over this tile's 32 columns -------------
             if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 30);
@@ -546,18 +554,16 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             {
                 const float invB = 1.0f / (float)MB;
                 if (net == 0) {
-                    float logp = 0.f, zz[8], sg[8], dmu[8];
+                    float logp = 0.f, zz[8], dmu[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        zz[j] = sg[j] = dmu[j] = 0.f;
+                        zz[j] = dmu[j] = 0.f;
                         if (j < A) {
-                            const float ls = sp_p[sm.b3 + 8 + j];
                             const float tnh = tanhf(outv[j]);
                             const float mu = u.bounded ? u.max_action * tnh : outv[j];
                             dmu[j] = u.bounded ? u.max_action * (1.0f - tnh * tnh) : 1.0f;
-                            sg[j] = expf(ls);
-                            zz[j] = (p_act[j] - mu) / sg[j];
-                            logp += -0.5f * zz[j] * zz[j] - ls - LOG_SQRT_2PI;
+                            zz[j] = (p_act[j] - mu) * p_rsg[j];
+                            logp += -0.5f * zz[j] * zz[j] - p_ls[j] - LOG_SQRT_2PI;
                         }
                     }
                     const float ratio = expf(logp - p_lpo);
@@ -585,7 +591,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (j < A) {
-                            dd[j] = gl * (zz[j] / sg[j]) * dmu[j];
+                            dd[j] = gl * (zz[j] * p_rsg[j]) * dmu[j];
                             dd[8 + j] = gl * (zz[j] * zz[j] - 1.0f);
                         }
                     }
