@@ -34,6 +34,9 @@ class CPOAgent(OnpolicyAgent):
         seed_all(seed)
         torch.set_num_threads(thread)
         if device == "cpu":
+            # the reference's default device; this engine has a GPU path only -- say so instead of remapping silently
+            import warnings
+            warnings.warn("fsrl_b200 runs on CUDA devices only: device='cpu' is mapped to 'cuda'", RuntimeWarning, stacklevel=2)
             device = "cuda"
         state_shape, action_shape = env.observation_space.shape, env.action_space.shape
         max_action = float(env.action_space.high[0])

@@ -53,7 +53,10 @@ class PPOLagAgent(OnpolicyAgent):
         seed_all(seed)
         torch.set_num_threads(thread)
         if device == "cpu":
-            device = "cuda"          # the reference's default; this engine only has a GPU path
+            # the reference's default device; this engine has a GPU path only -- say so instead of remapping silently
+            import warnings
+            warnings.warn("fsrl_b200 runs on CUDA devices only: device='cpu' is mapped to 'cuda'", RuntimeWarning, stacklevel=2)
+            device = "cuda"
         state_shape = env.observation_space.shape
         action_shape = env.action_space.shape
         max_action = float(env.action_space.high[0])

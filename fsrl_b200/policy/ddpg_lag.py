@@ -71,7 +71,12 @@ class DDPGLagrangian(OffPolicyLagrangian):
         super().fill_rollout(r, exploration_noise)
         # exploration_noise (ddpg_lag.py:225-231): only when the collector asks for it
         if exploration_noise and self._noise is not None and self.training:
-            r.expl_sigma = float(self._noise._sigma)
+            # the rollout kernel adds N(0, sigma^2) itself (ddpg_lag.py:225-231 with tianshou's GaussianNoise): other
+            # noise processes (OU noise, a non-zero mean, arbitrary callables) have no device twin -- refuse, don't drop
+            sigma = getattr(self._noise, "_sigma", None)
+            if sigma is None or float(getattr(self._noise, "_mu", 0.0)) != 0.0:
+                raise TypeError("the device rollout supports zero-mean GaussianNoise(sigma) exploration only, got %r" % (self._noise,))
+            r.expl_sigma = float(sigma)
 
     def sync_weight(self) -> None:
         g = self._groups()

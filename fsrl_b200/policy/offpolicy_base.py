@@ -81,6 +81,19 @@ class OffPolicyLagrangian(LagrangianPolicy):
         d.use_lagrangian = int(self.use_lagrangian and self.critics_num > 1)
         d.seed = self._upd_seed
         d.gamma, d.tau = self._gamma, self.tau
+        # learning rates are read from the caller's optimizers every time (an lr scheduler stepping them takes effect); the
+        # engine's Adam uses torch's default betas / eps -- anything else is rejected loudly instead of being ignored
+        a_opt, c_opt = getattr(self, "actor_optim", None), getattr(self, "critics_optim", None)
+        for opt in (a_opt, c_opt):
+            if opt is not None and hasattr(opt, "param_groups"):
+                g0 = opt.param_groups[0]
+                if tuple(g0.get("betas", (0.9, 0.999))) != (0.9, 0.999) or g0.get("eps", 1e-8) != 1e-8 or g0.get("weight_decay", 0) != 0:
+                    raise ValueError("the off-policy engine runs Adam with betas=(0.9, 0.999), eps=1e-8, weight_decay=0; got %r"
+                                     % {k: g0.get(k) for k in ("betas", "eps", "weight_decay")})
+        if a_opt is not None and hasattr(a_opt, "param_groups"):
+            self._actor_lr = float(a_opt.param_groups[0]["lr"])
+        if c_opt is not None and hasattr(c_opt, "param_groups"):
+            self._critic_lr = float(c_opt.param_groups[0]["lr"])
         d.critic_lr, d.actor_lr = self._critic_lr, self._actor_lr
         d.max_action = float(self.actor._max)
         d.sigma_min, d.sigma_max = SIGMA_MIN, SIGMA_MAX
