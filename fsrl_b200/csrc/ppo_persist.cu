@@ -36,8 +36,11 @@ namespace pp {
 
 using namespace umma;
 
-constexpr int TPB = 192;                 // warp 0: copy producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int NEPI = 128;
+constexpr int WQ = 2;                    // epilogue warps per tensor-memory subpartition (1 or 2)
+constexpr int NEPI = 128 * WQ;           // epilogue threads: warps 2 .. 2 + 4 WQ - 1
+constexpr int TPB = 64 + NEPI;           // warp 0: copy producer, warp 1: MMA issuer, then the epilogue warps
+constexpr int C1 = 16 / WQ;              // columns a thread owns of a 32-column tile (G1: h2 / dz2)
+constexpr int C2 = 32 / WQ;              // columns a thread owns of a 64-column tile (G2 / G3 and the W2 tile)
 constexpr int RB = 64;                   // rows per row block
 constexpr int MB = 256;                  // rows per minibatch
 constexpr int SLOT_BYTES = 65536, NSLOT = 3;
@@ -52,7 +55,7 @@ constexpr int DW3P_OFF = DB2P_OFF + 4 * H_;                     // [4 a][H][OUTP
 constexpr int DB3P_OFF = DW3P_OFF + 4 * H_ * OUTP;              // [4 a][16]
 constexpr int DW1P_OFF = DB3P_OFF + 4 * 16;                     // [4 rb][MAXD + 1][H]
 constexpr int MAXD = 40;
-constexpr int NET_WS = DW1P_OFF + 4 * (MAXD + 1) * H_;
+constexpr int NET_WS = DW1P_OFF + 4 * WQ * (MAXD + 1) * H_;   // [row block 4][warp-in-subpartition WQ][MAXD + 1][H]
 constexpr int SUMSQ_FLOATS = 128;                               // global tail: per-CTA sums of squares
 // flag lines (32 unsigned each): per net A, C, D1, B[4]; global D2
 constexpr int FLAG_LINE = 32;
@@ -132,7 +135,7 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
@@ -150,42 +153,63 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-
-// The M = 64 accumulators occupy the lower 16 lanes of every tensor-memory subpartition (one MMA per k-step
-// keeps the shared-memory operand traffic down -- the A tile is re-read by every instruction).  The upper 16
-// lanes of the warp take over the upper half of the columns: lane l >= 16 receives columns [NH, 2 NH) of lane
-// l - 16, so that all 32 lanes share the epilogue work.
-__device__ __forceinline__ void acc_ld_split16(uint32_t taddr, int lane, float (&v)[16]) {
-    float w[32];
-    tmem_ld32(taddr, w);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float x = __shfl_sync(0xffffffffu, w[16 + j], lane & 15);
-        v[j] = (lane & 16) ? x : w[j];
-    }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void acc_ld_split32(uint32_t taddr, int lane, float (&v)[32]) {
-    float w[32];
-    tmem_ld32(taddr + 32, w);
-    tmem_ld32(taddr, v);
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// NC = 8 / 16 / 32 consecutive columns of this thread's tensor-memory lane
+template <int NC> __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[NC]) {
+    if constexpr (NC == 8) tmem_ld8(taddr, v);
+    else if constexpr (NC == 16) tmem_ld16(taddr, v);
+    else tmem_ld32(taddr, v);
+}
+template <int NC> __device__ __forceinline__ void tmem_stn(uint32_t taddr, const float (&v)[NC]) {
+    static_assert(NC == 16 || NC == 32, "tensor-memory store widths in use");
+    if constexpr (NC == 16) tmem_st16(taddr, v);
+    else tmem_st32(taddr, v);
+}
+
+// The M = 64 accumulators occupy the lower 16 lanes of every tensor-memory subpartition (one MMA per k-step keeps the
+// shared-memory operand traffic down -- the A tile is re-read by every instruction).  All 32 lanes of the WQ warps that
+// share a subpartition split the columns: lane l < 16 of warp-in-subpartition wq keeps columns [col_lo, col_lo + NC), lane
+// l + 16 receives columns [col_hi, col_hi + NC) of lane l.
+template <int NC>
+__device__ __forceinline__ void acc_ld_split(uint32_t taddr, int lane, int col_lo, int col_hi, float (&v)[NC]) {
+    float w[NC];
+    tmem_ldn<NC>(taddr + col_hi, w);
+    tmem_ldn<NC>(taddr + col_lo, v);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
         const float x = __shfl_sync(0xffffffffu, w[j], lane & 15);
         v[j] = (lane & 16) ? x : v[j];
     }
 }
 
 // Transposed K-major image of a 64-row tile through shared memory.  Every epilogue thread holds NC consecutive
-// columns [c0, c0 + NC) of tile row `row` (hi / lo parts); the tile is 2 NC columns wide.  The transposed image
+// columns [c0, c0 + NC) of tile row `row` (hi / lo parts); the tile is W columns wide.  The transposed image
 // stores 4 consecutive ROWS of one column as 16 contiguous bytes: element (col, row) at
 //     img[(row_base + row) / 4 * 256 + (col_base + col) * 4 + (row_base + row) % 4],     lo image at + IMG.
-// Writing it straight from the registers costs NC scattered 4-byte stores per thread and image (16 sectors per warp
+// (W = tile width in columns.)  Writing it straight from the registers costs NC scattered 4-byte stores per thread and image (16 sectors per warp
 // instruction); staged through `scr` (an idle operand-ring slot, row stride 65: conflict-free) it becomes
 // float4 stores, 512 contiguous bytes per warp instruction.
-template <int NC>
+template <int NC, int W>
 __device__ __forceinline__ void store_transposed(float* scr, const float (&hi)[NC], const float (&lo)[NC], int row, int c0,
                                                  int et, float* img_hi, int row_base, int col_base) {
-    constexpr int W = 2 * NC, LO = W * 65;
+    constexpr int LO = W * 65;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
         scr[(c0 + j) * 65 + row] = hi[j];
@@ -353,10 +377,13 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         }
     } else {
         // ============================ epilogue warps ===============================================
-        const int et = tid - 64;                    // 0..127
+        const int et = tid - 64;                    // 0 .. NEPI - 1
         const int sp = warp & 3;                    // tensor-memory subpartition of this warp
+        const int wq = (warp - 2) >> 2;             // which of the WQ warps of that subpartition
         const int r16 = lane & 15, half = lane >> 4;
         const int trow = 16 * sp + r16;             // row of the 64-row tile held by this lane
+        const int cb1 = 16 * half + C1 * wq;        // first of this thread's C1 columns of a 32-column tile
+        const int cb2 = 32 * half + C2 * wq;        // first of this thread's C2 columns of a 64-column tile
         const uint32_t tm_lane = tmem + ((uint32_t)(32 * sp) << 16);
         float* stat_base = u.stats;
         // ---- data-parallel exchange over peer memory (NVLink): every CTA publishes its local gradient piece in this
@@ -392,13 +419,13 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         }
         if (!is_g2) {
             const int o = 64 * q4 + trow;
-            float pv[32], mv[32], vv[32];
+            float pv[C2], mv[C2], vv[C2];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const long long idx = o_w2 + (long long)(64 * ka + 32 * half + j) * H + o;
+            for (int j = 0; j < C2; ++j) {
+                const long long idx = o_w2 + (long long)(64 * ka + cb2 + j) * H + o;
                 pv[j] = u.theta[idx]; mv[j] = u.adam_m[idx]; vv[j] = u.adam_v[idx];
             }
-            tmem_st32(tm_lane + TM_P, pv); tmem_st32(tm_lane + TM_M, mv); tmem_st32(tm_lane + TM_V, vv);
+            tmem_stn<C2>(tm_lane + TM_P + C2 * wq, pv); tmem_stn<C2>(tm_lane + TM_M + C2 * wq, mv); tmem_stn<C2>(tm_lane + TM_V + C2 * wq, vv);
         }
         epi_bar();
 
@@ -424,24 +451,24 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             // ---- S(a): publish the images of the owned W2 tile (from tensor memory) ------------------
             float* scratch = reinterpret_cast<float*>(ring);       // the operand ring is idle outside the GEMM phases
             if (!is_g2) {
-                float pv[32], phi[32], plo[32];
-                tmem_ld32(tm_lane + TM_P, pv);
+                float pv[C2], phi[C2], plo[C2];
+                tmem_ldn<C2>(tm_lane + TM_P + C2 * wq, pv);
                 const int o = 64 * q4 + trow;                   // output unit of this lane
                 float* w2a_hi = wsn + (size_t)I_W2A_HI * IMG + (size_t)(o >> 5) * 8192 + (size_t)(o & 31) * 4;
                 float* w2a_lo = w2a_hi + IMG;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {                   // k = 64 ka + 32 half + 4 q + (0..3)
+                for (int q = 0; q < C2 / 4; ++q) {              // k = 64 ka + cb2 + 4 q + (0..3)
                     float4 hi, lo;
                     tf32_split(pv[4 * q], hi.x, lo.x); tf32_split(pv[4 * q + 1], hi.y, lo.y);
                     tf32_split(pv[4 * q + 2], hi.z, lo.z); tf32_split(pv[4 * q + 3], hi.w, lo.w);
-                    const size_t plane = (size_t)(16 * ka + 8 * half + q) * 128;
+                    const size_t plane = (size_t)(16 * ka + (cb2 >> 2) + q) * 128;
                     *reinterpret_cast<float4*>(w2a_hi + plane) = hi;
                     *reinterpret_cast<float4*>(w2a_lo + plane) = lo;
                     phi[4 * q] = hi.x; phi[4 * q + 1] = hi.y; phi[4 * q + 2] = hi.z; phi[4 * q + 3] = hi.w;
                     plo[4 * q] = lo.x; plo[4 * q + 1] = lo.y; plo[4 * q + 2] = lo.z; plo[4 * q + 3] = lo.w;
                 }
                 // W2B (MN = k, K = o): "rows" are the output units o, "columns" the 64 k of block ka
-                store_transposed<32>(scratch, phi, plo, trow, 32 * half, et, wsn + (size_t)I_W2B_HI * IMG + (size_t)ka * 16384, 64 * q4, 0);
+                store_transposed<C2, 64>(scratch, phi, plo, trow, cb2, et, wsn + (size_t)I_W2B_HI * IMG + (size_t)ka * 16384, 64 * q4, 0);
             }
             // ---- S(b): h1 tiles [64 rows][32 columns of block b].  The CTAs that own a W2 tile are busy with its Adam
             // step and images, so the other half of the grid (CTAs 0-15: a in {0, 1}) computes the tiles of row
@@ -449,28 +476,28 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (is_g2) {
                 for (int rep = 0; rep < 2; ++rep) {
                     const int aa = a + 2 * rep;
-                    const int r = et & 63, kh = et >> 6;        // row, 16-column half
+                    const int r = et & 63, kc = C1 * (et >> 6);  // row, first of C1 columns
                     const float* x = u.obs + (row0 + 64 * aa + r) * D;
-                    float acc[16], hi[16], lo[16];
+                    float acc[C1], hi[C1], lo[C1];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = sp_p[sm.w1 + D * 32 + 16 * kh + j];      // b1
+                    for (int j = 0; j < C1; ++j) acc[j] = sp_p[sm.w1 + D * 32 + kc + j];      // b1
                     for (int d = 0; d < D; ++d) {
                         const float xv = __ldg(x + d);
-                        const float* w = sp_p + sm.w1 + d * 32 + 16 * kh;
+                        const float* w = sp_p + sm.w1 + d * 32 + kc;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, w[j], acc[j]);
+                        for (int j = 0; j < C1; ++j) acc[j] = fmaf(xv, w[j], acc[j]);
                     }
                     float* a_hi = wsn + (size_t)I_H1A_HI * IMG + (size_t)aa * 16384 + (size_t)r * 4;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < C1 / 4; ++q) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) tf32_split(fmaxf(acc[4 * q + e], 0.f), hi[4 * q + e], lo[4 * q + e]);
-                        const size_t plane = (size_t)(8 * b + 4 * kh + q) * 256;
+                        const size_t plane = (size_t)(8 * b + (kc >> 2) + q) * 256;
                         *reinterpret_cast<float4*>(a_hi + plane) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
                         *reinterpret_cast<float4*>(a_hi + IMG + plane) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
                     }
                     // H1T (MN = k, K = r): block b / 2, columns 32 (b & 1) ..
-                    store_transposed<16>(scratch, hi, lo, r, 16 * kh, et, wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384, 64 * aa, 32 * (b & 1));
+                    store_transposed<C1, 32>(scratch, hi, lo, r, kc, et, wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384, 64 * aa, 32 * (b & 1));
                 }
             }
             epi_bar();
@@ -507,21 +534,35 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             ++acc_phase;
             tc_fence_after();
             if (et == 0) STAMP(2);
-            float h2[16];
-            acc_ld_split16(tm_lane, lane, h2);
+            float h2[C1];
+            acc_ld_split<C1>(tm_lane, lane, C1 * wq, 16 + C1 * wq, h2);
             float hp[OUTP];
 #pragma unroll
             for (int j = 0; j < OUTP; ++j) hp[j] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                h2[j] = fmaxf(h2[j] + sp_p[sm.b2 + 16 * half + j], 0.f);
-                const float* w = sp_p + sm.w3 + (16 * half + j) * OUTP;
+            for (int j = 0; j < C1; ++j) {
+                h2[j] = fmaxf(h2[j] + sp_p[sm.b2 + cb1 + j], 0.f);
+                const float* w = sp_p + sm.w3 + (cb1 + j) * OUTP;
 #pragma unroll
                 for (int jj = 0; jj < OUTP; ++jj) hp[jj] = fmaf(h2[j], w[jj], hp[jj]);
             }
 #pragma unroll
             for (int jj = 0; jj < OUTP; ++jj) hp[jj] += __shfl_xor_sync(0xffffffffu, hp[jj], 16);
-            if (half == 0) {
+            if (WQ > 1) {                                       // the WQ warps of a subpartition hold different columns of the same rows
+                float* xh = &s_red[0][0];
+                if (half == 0 && wq > 0) {
+#pragma unroll
+                    for (int jj = 0; jj < OUTP; ++jj) xh[((wq - 1) * 64 + trow) * OUTP + jj] = hp[jj];
+                }
+                epi_bar();
+                if (half == 0 && wq == 0) {
+#pragma unroll
+                    for (int w2 = 1; w2 < WQ; ++w2)
+#pragma unroll
+                        for (int jj = 0; jj < OUTP; ++jj) hp[jj] += xh[((w2 - 1) * 64 + trow) * OUTP + jj];
+                }
+            }
+            if (half == 0 && wq == 0) {
                 float* dst = wsn + HEADP_OFF + ((size_t)(a * 8 + b) * 64 + trow) * OUTP;
                 *reinterpret_cast<float4*>(dst) = make_float4(hp[0], hp[1], hp[2], hp[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(hp[4], hp[5], hp[6], hp[7]);
@@ -619,28 +660,28 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (et == 0) STAMP(26);
             // ---- dz2 tile = (dOut W3^T) * relu'(h2): images DZA / DZT; partial db2, dW3, db3 ----------------
             const int nfeed = (net == 0) ? A : 1;              // head columns that feed W3 (mu only)
-            float dz[16];
+            float dz[C1];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float* w = sp_p + sm.w3 + (16 * half + j) * OUTP;
+            for (int j = 0; j < C1; ++j) {
+                const float* w = sp_p + sm.w3 + (cb1 + j) * OUTP;
                 float g = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < OUTP; ++jj) if (jj < nfeed) g = fmaf(dd[jj], w[jj], g);
                 dz[j] = h2[j] > 0.f ? g : 0.f;
             }
             {
-                float hi[16], lo[16];
+                float hi[C1], lo[C1];
                 float* a_hi = wsn + (size_t)I_DZA_HI * IMG + (size_t)a * 16384 + (size_t)trow * 4;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < C1 / 4; ++q) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) tf32_split(dz[4 * q + e], hi[4 * q + e], lo[4 * q + e]);
-                    const size_t plane = (size_t)(8 * b + 4 * half + q) * 256;
+                    const size_t plane = (size_t)(8 * b + (cb1 >> 2) + q) * 256;
                     *reinterpret_cast<float4*>(a_hi + plane) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
                     *reinterpret_cast<float4*>(a_hi + IMG + plane) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
                 }
                 // DZT (MN = o, K = r): block b / 2, columns 32 (b & 1) ..
-                store_transposed<16>(scratch, hi, lo, trow, 16 * half, et, wsn + (size_t)I_DZT_HI * IMG + (size_t)(b >> 1) * 16384, 64 * a, 32 * (b & 1));
+                store_transposed<C1, 32>(scratch, hi, lo, trow, cb1, et, wsn + (size_t)I_DZT_HI * IMG + (size_t)(b >> 1) * 16384, 64 * a, 32 * (b & 1));
             }
             if (et == 0) STAMP(27);
             // partial sums over this tile's 64 rows: half-warp butterflies (16 rows of a subpartition), one shared
@@ -648,21 +689,21 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             {
                 float* row = &s_red[sp][0];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < C1; ++j) {
                     const float sdz = half_sum(dz[j]);
-                    if (r16 == 0) row[16 * half + j] = sdz;
+                    if (r16 == 0) row[cb1 + j] = sdz;
                 }
 #pragma unroll
                 for (int jj = 0; jj < OUTP; ++jj) {
                     if (jj < nfeed) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < C1; ++j) {
                             const float sv = half_sum(h2[j] * dd[jj]);
-                            if (r16 == 0) row[32 + 32 * jj + 16 * half + j] = sv;
+                            if (r16 == 0) row[32 + 32 * jj + cb1 + j] = sv;
                         }
                     }
                 }
-                if (b == 0) {
+                if (b == 0 && wq == 0) {                            // per-row quantities: one warp of each subpartition
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float sv = half_sum(dd[j]);
@@ -703,14 +744,14 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             // G2: what does not depend on the accumulators is requested BEFORE waiting for them -- the ReLU mask of
             // this lane's h1 entries (image H1A, complete since flag A) and this thread's share of the 64 x D
             // observation block of row block q4
-            float mreg[32];
+            float mreg[C2];
             float xr[(64 * MAXD + NEPI - 1) / NEPI];
             const int nx = (64 * D + NEPI - 1) / NEPI;
             if (is_g2) {
                 const int k = 64 * ka + trow;
                 const float* msk = wsn + (size_t)I_H1A_HI * IMG + (size_t)q4 * 16384 + (size_t)(k >> 2) * 256 + (k & 3);
 #pragma unroll
-                for (int jq = 0; jq < 32; ++jq) mreg[jq] = __ldcg(msk + (size_t)(32 * half + jq) * 4);
+                for (int jq = 0; jq < C2; ++jq) mreg[jq] = __ldcg(msk + (size_t)(cb2 + jq) * 4);
                 const float* xb = u.obs + (row0 + 64 * q4) * D;
 #pragma unroll
                 for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q)
@@ -730,26 +771,26 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     const int e = et + q * NEPI;
                     if (q < nx && e < 64 * D) { const int r = e / D; xs[e + (r >> 5)] = xr[q]; }
                 }
-                // lane: k = 64 ka + trow ; rows 32 half + j of row block q4
-                float v[32];
-                acc_ld_split32(tm_lane, lane, v);
+                // lane: k = 64 ka + trow ; rows cb2 + j of row block q4; partial set 2 q4 + wq (WQ sets per row block)
+                float v[C2];
+                acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, v);
                 const int k = 64 * ka + trow;
 #pragma unroll
-                for (int jq = 0; jq < 32; ++jq) v[jq] = (mreg[jq] > 0.f) ? v[jq] : 0.f;
+                for (int jq = 0; jq < C2; ++jq) v[jq] = (mreg[jq] > 0.f) ? v[jq] : 0.f;
                 epi_bar();
                 if (et == 0) STAMP(22);
-                const float* xh = xs + (size_t)(32 * half) * D + half;
-                float* dst = wsn + DW1P_OFF + (size_t)q4 * (MAXD + 1) * H + k;
+                const float* xh = xs + (size_t)cb2 * D + half;
+                float* dst = wsn + DW1P_OFF + (size_t)(WQ * q4 + wq) * (MAXD + 1) * H + k;
                 for (int d = 0; d < D; ++d) {
                     float sacc = 0.f;
 #pragma unroll
-                    for (int jq = 0; jq < 32; ++jq) sacc = fmaf(xh[jq * D + d], v[jq], sacc);
+                    for (int jq = 0; jq < C2; ++jq) sacc = fmaf(xh[jq * D + d], v[jq], sacc);
                     sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
                     if (half == 0) dst[(size_t)d * H] = sacc;
                 }
                 float sb1 = 0.f;
 #pragma unroll
-                for (int jq = 0; jq < 32; ++jq) sb1 += v[jq];
+                for (int jq = 0; jq < C2; ++jq) sb1 += v[jq];
                 sb1 += __shfl_xor_sync(0xffffffffu, sb1, 16);
                 if (half == 0) dst[(size_t)D * H] = sb1;          // db1
                 if (et == 0) STAMP(23);
@@ -757,50 +798,52 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                 epi_bar();
                 if (et == 0) flag_add_release(fl_net + F_D1 * FLAG_LINE);
             } else {
-                float g[32];
-                acc_ld_split32(tm_lane, lane, g);
+                float g[C2];
+                acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
                 if (world > 1) {
                     const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
                     const int par = (int)(id & 1ULL);
-                    const size_t off = ((size_t)(net * 16 + (c - 16)) * NEPI + et) * 32;
+                    const size_t off = ((size_t)(net * 16 + (c - 16)) * NEPI + et) * C2;
                     float* mine = const_cast<float*>(u.p2p_xg[par][u.p2p_rank]) + off;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(mine + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                    for (int q = 0; q < C2 / 4; ++q) *reinterpret_cast<float4*>(mine + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
                     __threadfence_system();
                     epi_bar();
                     if (et == 0) { dp_signal(blockIdx.x, id); dp_wait(blockIdx.x, id); }
                     epi_bar();
 #pragma unroll
-                    for (int jq = 0; jq < 32; ++jq) g[jq] = 0.f;
+                    for (int jq = 0; jq < C2; ++jq) g[jq] = 0.f;
                     for (int r = 0; r < world; ++r) {
                         const float* src = u.p2p_xg[par][r] + off;
-                        float4 v[8];
+                        float4 v[C2 / 4];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = ld_peer4(src + 4 * q);
+                        for (int q = 0; q < C2 / 4; ++q) v[q] = ld_peer4(src + 4 * q);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) { g[4 * q] += v[q].x; g[4 * q + 1] += v[q].y; g[4 * q + 2] += v[q].z; g[4 * q + 3] += v[q].w; }
+                        for (int q = 0; q < C2 / 4; ++q) { g[4 * q] += v[q].x; g[4 * q + 1] += v[q].y; g[4 * q + 2] += v[q].z; g[4 * q + 3] += v[q].w; }
                     }
 #pragma unroll
-                    for (int jq = 0; jq < 32; ++jq) g[jq] *= inv_world;
-                    tmem_st32(tm_lane + TM_G, g);
+                    for (int jq = 0; jq < C2; ++jq) g[jq] *= inv_world;
+                    tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
                 }
 #pragma unroll
-                for (int jq = 0; jq < 32; ++jq) sq = fmaf(g[jq], g[jq], sq);
+                for (int jq = 0; jq < C2; ++jq) sq = fmaf(g[jq], g[jq], sq);
             }
             // ---- small-parameter gradients: fixed-order sums of the row-block partials.  The b2 / W3 / b3 partials
             // are complete since flag C: they are summed while flag D1 (the dW1 partials) is still on its way.
             auto reduce_slices = [&](int lo, int hi) {
                 for (int i0 = lo + et; i0 < hi; i0 += 4 * NEPI) {    // 4 elements x 4 partials in flight per thread
-                    float pv[4][4];
+                    float pv[4][4 * WQ];
                     bool real[4];
+                    int np[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int i = i0 + e * NEPI;
                         const float* src = wsn;
                         size_t stride = 0;
                         real[e] = false;
+                        np[e] = 4;
                         if (i < hi) {
-                            if (i < sm.b2) { src = wsn + DW1P_OFF + (size_t)(i / 32) * H + 32 * b + (i % 32); stride = (size_t)(MAXD + 1) * H; real[e] = true; }
+                            if (i < sm.b2) { src = wsn + DW1P_OFF + (size_t)(i / 32) * H + 32 * b + (i % 32); stride = (size_t)(MAXD + 1) * H; real[e] = true; np[e] = 4 * WQ; }
                             else if (i < sm.w3) { src = wsn + DB2P_OFF + 32 * b + (i - sm.b2); stride = H; real[e] = true; }
                             else if (i < sm.b3) {
                                 const int oo = (i - sm.w3) / OUTP, jj = (i - sm.w3) % OUTP;
@@ -813,13 +856,15 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                             }
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) pv[e][q] = real[e] ? __ldcg(src + q * stride) : 0.f;
+                        for (int q = 0; q < 4 * WQ; ++q) pv[e][q] = (real[e] && q < np[e]) ? __ldcg(src + q * stride) : 0.f;
                     }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int i = i0 + e * NEPI;
                         if (i < hi) {
-                            const float gsum = ((pv[e][0] + pv[e][1]) + pv[e][2]) + pv[e][3];
+                            float gsum = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 4 * WQ; ++q) gsum += pv[e][q];          // fixed order
                             sp_g[i] = gsum;
                         }
                     }
@@ -860,10 +905,13 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             }
             // ---- global gradient norm: per-CTA partial -> device-wide hop -> same summation order everywhere --
             sq = warp_sum(sq);
-            if (lane == 0) s_misc[sp] = sq;
+            if (lane == 0) s_misc[warp - 2] = sq;
             epi_bar();
             if (et == 0) {
-                sumsq_g[blockIdx.x] = s_misc[0] + s_misc[1] + s_misc[2] + s_misc[3];
+                float tot = 0.f;
+#pragma unroll
+                for (int w2 = 0; w2 < NEPI / 32; ++w2) tot += s_misc[w2];
+                sumsq_g[blockIdx.x] = tot;
                 STAMP(9);
                 flag_add_release(fl_d2);
                 if (!flag_wait_ge(fl_d2, (unsigned)n_cta * (t + 1), WAIT_CYCLES)) fail(P.err, 34);
@@ -888,13 +936,13 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             }
             if (et == 0) STAMP(25);
             if (!is_g2) {
-                float g[32], pv[32], mv[32], vv[32];
-                if (world > 1) tmem_ld32(tm_lane + TM_G, g);
-                else acc_ld_split32(tm_lane, lane, g);
-                tmem_ld32(tm_lane + TM_P, pv); tmem_ld32(tm_lane + TM_M, mv); tmem_ld32(tm_lane + TM_V, vv);
+                float g[C2], pv[C2], mv[C2], vv[C2];
+                if (world > 1) tmem_ldn<C2>(tm_lane + TM_G + C2 * wq, g);
+                else acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
+                tmem_ldn<C2>(tm_lane + TM_P + C2 * wq, pv); tmem_ldn<C2>(tm_lane + TM_M + C2 * wq, mv); tmem_ldn<C2>(tm_lane + TM_V + C2 * wq, vv);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) pv[j] = adam_one(pv[j], g[j] * gscale, mv[j], vv[j], ad);
-                tmem_st32(tm_lane + TM_P, pv); tmem_st32(tm_lane + TM_M, mv); tmem_st32(tm_lane + TM_V, vv);
+                for (int j = 0; j < C2; ++j) pv[j] = adam_one(pv[j], g[j] * gscale, mv[j], vv[j], ad);
+                tmem_stn<C2>(tm_lane + TM_P + C2 * wq, pv); tmem_stn<C2>(tm_lane + TM_M + C2 * wq, mv); tmem_stn<C2>(tm_lane + TM_V + C2 * wq, vv);
             }
             tc_fence_before();
             epi_bar();     // slices final before the next h1 tile / head reads them; s_adam may be rewritten
@@ -913,12 +961,12 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             }
         }
         if (!is_g2) {
-            float pv[32], mv[32], vv[32];
-            tmem_ld32(tm_lane + TM_P, pv); tmem_ld32(tm_lane + TM_M, mv); tmem_ld32(tm_lane + TM_V, vv);
+            float pv[C2], mv[C2], vv[C2];
+            tmem_ldn<C2>(tm_lane + TM_P + C2 * wq, pv); tmem_ldn<C2>(tm_lane + TM_M + C2 * wq, mv); tmem_ldn<C2>(tm_lane + TM_V + C2 * wq, vv);
             const int o = 64 * q4 + trow;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const long long idx = o_w2 + (long long)(64 * ka + 32 * half + j) * H + o;
+            for (int j = 0; j < C2; ++j) {
+                const long long idx = o_w2 + (long long)(64 * ka + cb2 + j) * H + o;
                 u.theta[idx] = pv[j]; u.adam_m[idx] = mv[j]; u.adam_v[idx] = vv[j];
             }
         }
