@@ -83,6 +83,7 @@ struct Args {
     const float* adam_tab;   // [n_mb][2]: 1 / sqrt(1 - beta2^t), -(lr / (1 - beta1^t)) of every step (host doubles -> f32)
     long long* dbg;          // optional [n_cta][DBG_N] clock stamps of step dbg_step
     int dbg_step;
+    int cluster;             // launched as clusters of 8 CTAs (one row block): hop B runs over distributed shared memory
 };
 constexpr int DBG_N = 32;
 #define STAMP(i) do { if (P.dbg && t == P.dbg_step) P.dbg[(size_t)blockIdx.x * DBG_N + (i)] = clock64(); } while (0)
@@ -122,6 +123,38 @@ __device__ __forceinline__ float ld_peer(const float* p) {
     float v;
     asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
+}
+
+// ---- thread-block cluster: distributed shared memory pushes + remote mbarrier arrivals (hop B) ------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster4(uint32_t raddr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// asynchronous remote store that completes 16 transaction bytes on the destination CTA's mbarrier: the data signals
+// its own arrival, so no release fence / arrival round trip follows the push
+__device__ __forceinline__ void st_async4(uint32_t raddr, float4 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, long long timeout_cycles) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > timeout_cycles) return false;
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // one thread of a converged warp (CUTLASS elect_one_sync): lets the compiler issue the uniform-datapath
@@ -245,7 +278,7 @@ struct SliceMap {
 
 __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_acc;
+    __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_acc, bar_b;
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[4][320];          // cross-subpartition partial sums
     __shared__ float s_misc[32];
@@ -269,10 +302,12 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     float* sp_m = small + sm.n;          // Adam first moment
     float* sp_v = small + 2 * sm.n;      // Adam second moment
     float* sp_g = small + 3 * sm.n;      // reduced gradient of the current step
+    float* land = small + 4 * sm.n;      // cluster mode: head partials pushed by the 8 CTAs of this row block [b][64][OUTP]
 
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         mbar_init(&bar_acc, 1);
+        mbar_init(&bar_b, 1);                // per step: one local expect_tx arrival + 16 KB of remote st.async bytes
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<TM_COLS>(&s_tmem);
@@ -280,6 +315,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    if (P.cluster) cluster_sync_all();       // every CTA's barriers exist before a peer may arrive on them
 
     // parameter offsets of this network inside the flat arena
     const long long pbase = u.net_off[net];
@@ -438,6 +474,11 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                 s_adam.rbc2s = __ldg(P.adam_tab + 2 * t); s_adam.eps = (float)u.adam_eps; s_adam.neg_step = __ldg(P.adam_tab + 2 * t + 1);
                 STAMP(0);
                 if (P.dbg && t == P.dbg_step) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.dbg[(size_t)blockIdx.x * DBG_N + 30] = gt; }
+                if (P.dbg && t == P.dbg_step + 64) {     // 64 steps later: average cycles and ns per step
+                    long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    P.dbg[(size_t)blockIdx.x * DBG_N + 31] = gt;
+                    P.dbg[(size_t)blockIdx.x * DBG_N + 29] = clock64();
+                }
             }
             // rows of the NEXT minibatch towards L2 while this one is processed
             if (t + 1 < P.n_mb && et < 64) {
@@ -562,30 +603,59 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                         for (int jj = 0; jj < OUTP; ++jj) hp[jj] += xh[((w2 - 1) * 64 + trow) * OUTP + jj];
                 }
             }
-            if (half == 0 && wq == 0) {
-                float* dst = wsn + HEADP_OFF + ((size_t)(a * 8 + b) * 64 + trow) * OUTP;
-                *reinterpret_cast<float4*>(dst) = make_float4(hp[0], hp[1], hp[2], hp[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(hp[4], hp[5], hp[6], hp[7]);
-            }
-            tc_fence_before();
-            epi_bar();
-            if (et == 0) {
-                STAMP(3);
-                flag_add_release(fl_net + (F_B + a) * FLAG_LINE);
-                if (!flag_wait_ge(fl_net + (F_B + a) * FLAG_LINE, 8u * (t + 1), WAIT_CYCLES)) fail(P.err, 31);
-                STAMP(4);
-            }
-            epi_bar();
             float outv[OUTP];
 #pragma unroll
             for (int jj = 0; jj < OUTP; ++jj) outv[jj] = sp_p[sm.b3 + jj];
+            if (P.cluster) {
+                // hop B inside the cluster (8 CTAs = the column blocks of this row block): push the partial rows into every
+                // peer's landing zone, one remote mbarrier arrival per peer, then wait for the 8 arrivals on the own barrier
+                if (et == 0) {
+                    STAMP(3);
+                    mbar_expect_tx(&bar_b, 8u * 64u * OUTP * (uint32_t)sizeof(float));
+                }
+                if (half == 0 && wq == 0) {
+                    const uint32_t mine = smem_u32(land + ((size_t)b * 64 + trow) * OUTP);
+                    const uint32_t bb_ = smem_u32(&bar_b);
 #pragma unroll
-            for (int bb = 0; bb < 8; ++bb) {
-                const float* src = wsn + HEADP_OFF + ((size_t)(a * 8 + bb) * 64 + trow) * OUTP;
-                const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src));
-                const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + 4));
-                outv[0] += v0.x; outv[1] += v0.y; outv[2] += v0.z; outv[3] += v0.w;
-                outv[4] += v1.x; outv[5] += v1.y; outv[6] += v1.z; outv[7] += v1.w;
+                    for (int r = 0; r < 8; ++r) {
+                        const uint32_t ra = mapa_u32(mine, r), rb = mapa_u32(bb_, r);
+                        st_async4(ra, make_float4(hp[0], hp[1], hp[2], hp[3]), rb);
+                        st_async4(ra + 16, make_float4(hp[4], hp[5], hp[6], hp[7]), rb);
+                    }
+                }
+                if (!mbar_wait_cluster(&bar_b, t & 1, WAIT_CYCLES)) fail(P.err, 31);
+                if (et == 0) STAMP(4);
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) {
+                    const float* src = land + ((size_t)bb * 64 + trow) * OUTP;
+                    const float4 v0 = *reinterpret_cast<const float4*>(src);
+                    const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+                    outv[0] += v0.x; outv[1] += v0.y; outv[2] += v0.z; outv[3] += v0.w;
+                    outv[4] += v1.x; outv[5] += v1.y; outv[6] += v1.z; outv[7] += v1.w;
+                }
+            } else {
+                if (half == 0 && wq == 0) {
+                    float* dst = wsn + HEADP_OFF + ((size_t)(a * 8 + b) * 64 + trow) * OUTP;
+                    *reinterpret_cast<float4*>(dst) = make_float4(hp[0], hp[1], hp[2], hp[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(hp[4], hp[5], hp[6], hp[7]);
+                }
+                tc_fence_before();
+                epi_bar();
+                if (et == 0) {
+                    STAMP(3);
+                    flag_add_release(fl_net + (F_B + a) * FLAG_LINE);
+                    if (!flag_wait_ge(fl_net + (F_B + a) * FLAG_LINE, 8u * (t + 1), WAIT_CYCLES)) fail(P.err, 31);
+                    STAMP(4);
+                }
+                epi_bar();
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) {
+                    const float* src = wsn + HEADP_OFF + ((size_t)(a * 8 + bb) * 64 + trow) * OUTP;
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src));
+                    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                    outv[0] += v0.x; outv[1] += v0.y; outv[2] += v0.z; outv[3] += v0.w;
+                    outv[4] += v1.x; outv[5] += v1.y; outv[6] += v1.z; outv[7] += v1.w;
+                }
             }
             // ---- loss gradient at the head (ppo_lag.py:152-212): dd[j] = d loss / d head_j --------------
             float dd[16];
@@ -973,10 +1043,13 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         tc_fence_before();
     }
     __syncthreads();
+    if (P.cluster) cluster_sync_all();
     if (warp == 1) { tc_fence_after(); tmem_dealloc<TM_COLS>(tmem); }
 }
 
-static size_t smem_bytes(int D) { return (size_t)NSLOT * SLOT_BYTES + 4 * sizeof(float) * SliceMap(D).n; }
+static size_t smem_bytes(int D, bool cluster = false) {
+    return (size_t)NSLOT * SLOT_BYTES + 4 * sizeof(float) * SliceMap(D).n + (cluster ? sizeof(float) * 8 * 64 * OUTP : 0);
+}
 
 }  // namespace pp
 
@@ -1032,14 +1105,40 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
         a.dbg = reinterpret_cast<long long*>(tab_dev + 2 * (size_t)pp::MAX_MB);
         a.dbg_step = atoi(e);
     }
-    const size_t smem = pp::smem_bytes(ug.D);
+    // clusters of 8 CTAs (the column blocks of one row block) when the landing zone fits and all clusters can be
+    // co-resident; otherwise hop B goes through global memory like the other hops
+    static int smem_optin = -1;
+    if (smem_optin < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    bool cluster = !getenv("FSRL_PPO_NO_CLUSTER") && pp::smem_bytes(ug.D, true) + 8192 <= (size_t)smem_optin;
+    size_t smem = pp::smem_bytes(ug.D, cluster);
     static size_t set = 0;
     if (smem > set) {
         FSRL_CUDA(cudaFuncSetAttribute(pp::ppo_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
     }
-    pp::ppo_persist_kernel<<<32 * ug.n_nets, pp::TPB, smem, s>>>(a);
-    FSRL_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(32 * ug.n_nets); cfg.blockDim = dim3(pp::TPB); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    if (cluster) {
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, pp::ppo_persist_kernel, &cfg) != cudaSuccess || n_clusters < 4 * ug.n_nets) {
+            cudaGetLastError();
+            cluster = false;
+            smem = pp::smem_bytes(ug.D, false);
+            cfg.dynamicSmemBytes = smem;
+        }
+    }
+    if (!cluster) { cfg.attrs = nullptr; cfg.numAttrs = 0; }
+    a.cluster = cluster ? 1 : 0;
+    FSRL_CUDA(cudaLaunchKernelEx(&cfg, pp::ppo_persist_kernel, a));
+    ++g_launches;
     return FSRL_OK;
 }
 

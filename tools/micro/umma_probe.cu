@@ -87,6 +87,117 @@ static float rtf32(float x) { uint32_t b; memcpy(&b, &x, 4); b = (b + 0x1000u) &
 static size_t off_kmajor(int mn, int k, int MNx) { return (size_t)(k / 4) * MNx * 4 + (size_t)mn * 4 + k % 4; }
 static size_t off_mnmajor(int mn, int k, int Kx) { return (size_t)(mn / 4) * Kx * 4 + (size_t)k * 4 + mn % 4; }
 
+
+// ---- accuracy study: how should the K = 256 accumulation be organised? ------------------------------------------
+// nacc accumulators (K split into nacc consecutive chunks, each accumulated from zero in its own tensor-memory columns
+// and summed with fp32 round-to-nearest adds afterwards); sepcorr: the two correction products (a_lo b_hi, a_hi b_lo)
+// go to their own accumulators.
+__global__ void __launch_bounds__(128) acc_probe(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                                                 int K, int nacc, int sepcorr, float* dout, int* err) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar_full, bar_done;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t a_bytes = 64 * K * 4, b_bytes = 32 * K * 4;
+    float* sa_hi = reinterpret_cast<float*>(smem);
+    float* sa_lo = reinterpret_cast<float*>(smem + a_bytes);
+    float* sb_hi = reinterpret_cast<float*>(smem + 2 * a_bytes);
+    float* sb_lo = reinterpret_cast<float*>(smem + 2 * a_bytes + b_bytes);
+    if (tid == 0) { mbar_init(&bar_full, 1); mbar_init(&bar_done, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<512>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base;
+    if (tid == 0) {
+        mbar_expect_tx(&bar_full, 2 * a_bytes + 2 * b_bytes);
+        bulk_g2s(sa_hi, a_hi, a_bytes, &bar_full); bulk_g2s(sa_lo, a_lo, a_bytes, &bar_full);
+        bulk_g2s(sb_hi, b_hi, b_bytes, &bar_full); bulk_g2s(sb_lo, b_lo, b_bytes, &bar_full);
+        if (!mbar_wait(&bar_full, 0)) *err = 1;
+        tc_fence_after();
+        const uint32_t idesc = idesc_tf32(64, 32, 0, 0);
+        const int ksteps = K / 8, per = ksteps / nacc;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int acc = ks / per;
+            const bool first = (ks % per) == 0;
+            const uint64_t ah = smem_desc(smem_u32(sa_hi) + ks * 2048, 1024, 128), al = smem_desc(smem_u32(sa_lo) + ks * 2048, 1024, 128);
+            const uint64_t bh = smem_desc(smem_u32(sb_hi) + ks * 1024, 512, 128), bl = smem_desc(smem_u32(sb_lo) + ks * 1024, 512, 128);
+            const uint32_t dmain = tb + 32 * acc, dcorr = sepcorr ? tb + 32 * (nacc + acc) : dmain;
+            if (sepcorr) {
+                mma_tf32_ss(dcorr, al, bh, idesc, !first);
+                mma_tf32_ss(dcorr, ah, bl, idesc, true);
+                mma_tf32_ss(dmain, ah, bh, idesc, !first);
+            } else {
+                mma_tf32_ss(dmain, al, bh, idesc, !first);
+                mma_tf32_ss(dmain, ah, bl, idesc, true);
+                mma_tf32_ss(dmain, ah, bh, idesc, true);
+            }
+        }
+        mma_commit(&bar_done);
+    }
+    __syncwarp();
+    if (!mbar_wait(&bar_done, 0)) { if ((tid & 31) == 0) *err = 2; }
+    tc_fence_after();
+    float sum[32], corr[32], v[32];
+    for (int j = 0; j < 32; ++j) { sum[j] = 0.f; corr[j] = 0.f; }
+    for (int acc = 0; acc < nacc; ++acc) {
+        tmem_ld32(tb + ((uint32_t)(32 * warp) << 16) + 32 * acc, v);
+        for (int j = 0; j < 32; ++j) sum[j] += v[j];
+        if (sepcorr) {
+            tmem_ld32(tb + ((uint32_t)(32 * warp) << 16) + 32 * (nacc + acc), v);
+            for (int j = 0; j < 32; ++j) corr[j] += v[j];
+        }
+    }
+    for (int j = 0; j < 32; ++j) dout[(size_t)tid * 32 + j] = sum[j] + corr[j];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tb);
+}
+
+static void accuracy_study() {
+    const int M = 64, N = 32, K = 256;
+    std::vector<float> A((size_t)M * K), B((size_t)N * K);
+    // activations-like A (non-negative, as after a ReLU), weights-like B
+    for (auto& x : A) { x = frand(); if (x < 0) x = 0; }
+    for (auto& x : B) x = 0.1f * frand();
+    std::vector<float> ah(A.size()), al(A.size()), bh(B.size()), bl(B.size());
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { float x = A[(size_t)m * K + k], h = rtf32(x), l = rtf32(x - h); size_t o = off_kmajor(m, k, M); ah[o] = h; al[o] = l; }
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) { float x = B[(size_t)n * K + k], h = rtf32(x), l = rtf32(x - h); size_t o = off_kmajor(n, k, N); bh[o] = h; bl[o] = l; }
+    std::vector<double> ref((size_t)M * N); std::vector<float> f32((size_t)M * N);
+    double rms = 0;
+    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+        double r = 0; float f = 0.f;
+        for (int k = 0; k < K; ++k) { r += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k]; f = fmaf(A[(size_t)m * K + k], B[(size_t)n * K + k], f); }
+        ref[(size_t)m * N + n] = r; f32[(size_t)m * N + n] = f; rms += r * r;
+    }
+    rms = sqrt(rms / (M * N));
+    double e32 = 0;
+    for (size_t i = 0; i < ref.size(); ++i) e32 += (f32[i] - ref[i]) * (f32[i] - ref[i]);
+    printf("[accuracy] fp32 FMA chain (CPU)             : rms err / rms ref = %.3e\n", sqrt(e32 / ref.size()) / rms);
+    float *dah, *dal, *dbh, *dbl, *dd; int* derr;
+    CK(cudaMalloc(&dah, A.size() * 4)); CK(cudaMalloc(&dal, A.size() * 4)); CK(cudaMalloc(&dbh, B.size() * 4)); CK(cudaMalloc(&dbl, B.size() * 4));
+    CK(cudaMalloc(&dd, 128 * 32 * 4)); CK(cudaMalloc(&derr, 4)); CK(cudaMemset(derr, 0, 4));
+    CK(cudaMemcpy(dah, ah.data(), A.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dal, al.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbh, bh.data(), B.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dbl, bl.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    const size_t smem = 2 * A.size() * 4 + 2 * B.size() * 4;
+    CK(cudaFuncSetAttribute(acc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int cfgs[6][2] = {{1, 0}, {1, 1}, {2, 0}, {4, 0}, {4, 1}, {8, 0}};
+    for (auto& c : cfgs) {
+        acc_probe<<<1, 128, smem>>>(dah, dal, dbh, dbl, K, c[0], c[1], dd, derr);
+        CK(cudaDeviceSynchronize());
+        std::vector<float> D(128 * 32);
+        CK(cudaMemcpy(D.data(), dd, D.size() * 4, cudaMemcpyDeviceToHost));
+        double e = 0, bias = 0;
+        for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+            const int lane = (m % 16) + 32 * (m / 16);
+            const double d = D[(size_t)lane * 32 + n] - ref[(size_t)m * N + n];
+            e += d * d; bias += d;
+        }
+        printf("[accuracy] tcgen05 3xTF32, %d accumulator(s)%s : rms err / rms ref = %.3e   mean err / rms ref = %+.3e\n", c[0],
+               c[1] ? ", corrections separate" : "                      ", sqrt(e / (M * N)) / rms, bias / (M * N) / rms);
+    }
+}
+
 static int run_gemm(const char* name, int M, int N, int K, int a_mn, int b_mn, int interleave) {
     std::vector<float> A((size_t)M * K), B((size_t)N * K);
     for (auto& x : A) x = frand();
@@ -197,6 +308,7 @@ int main() {
     fails += run_gemm("M128 K x K", 128, 32, 128, 0, 0, 0);
     fails += run_gemm("M128 MN x MN", 128, 64, 64, 1, 1, 0);
 
+    accuracy_study();
     // ingest: every CTA pulls 3 x 64 KB per iteration from an L2-resident region
     int* derr; CK(cudaMalloc(&derr, 4)); CK(cudaMemset(derr, 0, 4));
     const int chunk = 64 * 1024, nch = 3;

@@ -167,6 +167,9 @@ def main():
                 rel[b0, i].mean() for i in (4, 26, 27, 28, 5)))
         gt = dbg[:, 30]
         print("  step start skew across CTAs (globaltimer ns): %d" % (gt.max() - gt.min()))
+        cyc = (dbg[:, 29] - dbg[:, 0]) / 64.0
+        ns = (dbg[:, 31] - dbg[:, 30]) / 64.0
+        print("  over the next 64 steps: %.0f cycles / step, %.0f ns / step -> SM clock %.0f MHz" % (cyc.mean(), ns.mean(), 1e3 * cyc.mean() / ns.mean()))
 
 
 if __name__ == "__main__":
