@@ -174,9 +174,22 @@ def ppo_rooflines(cfg, agent, col, buf, T, device, pk, how):
     pol._ensure_update_state(cfg["batch"], n, 1)
     u = pol._descriptor(batch, torch.zeros(n, dtype=torch.int32, device=device))
     persistent = bool(_lib.lib.fsrl_ppo_persist_active(ctypes.byref(u), n, cfg["batch"]))
-    np.random.seed(SEED)
+    # one repeat = one fsrl_ppo_lag_epoch call (gather + advantage statistics + the update launch(es)); the permutation is
+    # uploaded before the timed region so that the host's draw of it is not counted as kernel time
+    perm = torch.randperm(n, device=device).to(torch.int32)
+    pol._dp_batch = int(cfg["batch"])
+    u = pol._descriptor(batch, perm)
+    pol._stats_dev.zero_()
+    n_mb_c = ctypes.c_int(0)
+    stream = pol._stream()
+
+    def one_repeat():
+        _lib.check(_lib.lib.fsrl_ppo_lag_epoch(ctypes.byref(u), n, int(cfg["batch"]), 0, pol.optim.step_count,
+                                               ctypes.byref(n_mb_c), stream))
+        pol.optim.step_count += n_mb_c.value
+    one_repeat()                                                   # warm
     l0 = int(_lib.lib.fsrl_launch_count())
-    ms_rep, _ = ev_time(lambda: pol.learn(batch, batch_size=cfg["batch"], repeat=1))
+    ms_rep, _ = ev_time(one_repeat)
     launches_rep = int(_lib.lib.fsrl_launch_count()) - l0
     n_mb = max(n // cfg["batch"], 1)
     fl = net_flops(D, H, A, cfg["batch"]) * n_mb
@@ -326,6 +339,9 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if world > 1:
+        # the other ranks are gone: the per-kernel measurements below run on this GPU alone, without the exchange
+        agent.policy._dp = None
     if algo == "ppol":
         roof, hbm = ppo_rooflines(cfg, agent, col, buf, T, device, pk, how)
         out["roofline"], out["roofline_hbm"] = roof, hbm

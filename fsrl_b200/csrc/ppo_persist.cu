@@ -62,11 +62,18 @@ constexpr int FLAG_LINE = 32;
 constexpr int F_A = 0, F_C = 1, F_D1 = 2, F_B = 3, F_PER_NET = 7;
 constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,64) accumulators, Adam state
 constexpr int TM_G = 160;                                        // reduced gradient tile (data-parallel runs)
-// peer-mapped exchange buffer of one step parity (floats): per net 16 gradient tiles [tile][thread 128][32] and the
-// locally reduced small-parameter slices [b 8][NSMAX]; behind them (parity 0 only) the flags [src rank 8][CTA 128] u64
+// peer-mapped exchange buffer of one step parity (floats): one region per SOURCE rank [8], each holding per net 16
+// gradient tiles and the locally reduced small-parameter slices of the 8 column blocks.  Ranks PUSH their pieces into
+// every peer's buffer as 16-byte packets {3 floats, tag}: the tag (launch sequence number | step) travels with the data,
+// so the receiver polls its own memory until every packet carries the tag -- one NVLink one-way latency per exchange,
+// no system-scope fence (measured: ~6 us each with posted peer writes outstanding), no flag round trip, no remote loads.
+// (A 16-byte aligned vector store is one write transaction; NCCL's LL128 protocol relies on 128-byte ones over NVLink.)
 constexpr int NSMAX = (MAXD + 1) * 32 + 32 + 32 * OUTP + 16;
-constexpr int XG_PER_NET = 16 * 4096 + 8 * NSMAX;
-constexpr int XG_FLAG_FLOATS = 8 * 128 * 2;
+constexpr int TILE_PK = (64 * 64 / NEPI + 2) / 3;                // packets per thread of a 64 x 64 tile (16 floats -> 6)
+constexpr int TILE_FLOATS = TILE_PK * NEPI * 4;                  // [packet][thread][4]
+constexpr int SLICE_PK = (NSMAX + 2) / 3;
+constexpr int XG_PER_NET = 16 * TILE_FLOATS + 8 * SLICE_PK * 4;
+constexpr int XG_FLAG_FLOATS = 8 * 128 * 2;                      // (reserved: flag lines of the fenced protocol)
 constexpr int MAX_MB = 16384;                                    // minibatches per launch (Adam scalar table)
 constexpr long long WAIT_CYCLES = 6000000000LL;                  // ~3 s: a lost partner must not hang the GPU
 
@@ -84,8 +91,9 @@ struct Args {
     long long* dbg;          // optional [n_cta][DBG_N] clock stamps of step dbg_step
     int dbg_step;
     int cluster;             // launched as clusters of 8 CTAs (one row block): hop B runs over distributed shared memory
+    unsigned dp_seq;         // data-parallel runs: launch sequence number (same on every rank), upper half of the packet tags
 };
-constexpr int DBG_N = 32;
+constexpr int DBG_N = 48;
 #define STAMP(i) do { if (P.dbg && t == P.dbg_step) P.dbg[(size_t)blockIdx.x * DBG_N + (i)] = clock64(); } while (0)
 
 struct AdamS { float w1, b2, w2, rbc2s, eps, neg_step; };
@@ -106,22 +114,13 @@ __device__ __forceinline__ void fail(int* err, int code) {
     __threadfence_system();
     asm volatile("trap;");
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// one 16-byte packet {x, y, z, tag}: a single vector store into peer memory / a single vector load from local memory
+__device__ __forceinline__ void st_packet(float* p, float x, float y, float z, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(tag)) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float4 ld_peer4(const float* p) {      // peer memory is cached in L1 only: bypass it
+__device__ __forceinline__ float4 ld_packet(const float* p) {
     float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_peer(const float* p) {
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
 
@@ -422,24 +421,15 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         const int cb2 = 32 * half + C2 * wq;        // first of this thread's C2 columns of a 64-column tile
         const uint32_t tm_lane = tmem + ((uint32_t)(32 * sp) << 16);
         float* stat_base = u.stats;
-        // ---- data-parallel exchange over peer memory (NVLink): every CTA publishes its local gradient piece in this
-        // rank's exchange buffer, release-stores the step id into the same slot of every rank's flag array and sums the
-        // ranks' pieces in rank order once their flags arrived -- point-to-point between equal CTAs, no local barrier,
+        // ---- data-parallel exchange over peer memory (NVLink): every CTA pushes its local gradient piece into its
+        // rank's region of EVERY rank's exchange buffer, one thread fences and release-stores the step id into the same
+        // slot of every rank's flag array; the receiver waits for the ranks' flags and sums their pieces from its own
+        // memory in rank order -- point-to-point between equal CTAs, one NVLink one-way latency, no remote loads,
         // bit-identical sums on every rank.
         const int world = u.world > 1 ? u.world : 1;
         const float inv_world = 1.0f / (float)world;
-        const long long xg_total = (long long)u.n_nets * XG_PER_NET;
-        auto dp_flags = [&](int r) { return reinterpret_cast<unsigned long long*>(const_cast<float*>(u.p2p_xg[0][r]) + xg_total); };
-        auto dp_signal = [&](int slot_cta, unsigned long long id) {
-            for (int r = 0; r < world; ++r) st_release_sys(dp_flags(r) + (size_t)u.p2p_rank * 128 + slot_cta, id);
-        };
-        auto dp_wait = [&](int slot_cta, unsigned long long id) {
-            const unsigned long long* f = dp_flags(u.p2p_rank);
-            const long long t0 = clock64();
-            for (int r = 0; r < world; ++r)
-                while (ld_acquire_sys(f + (size_t)r * 128 + slot_cta) < id)
-                    if (clock64() - t0 > 4 * WAIT_CYCLES) fail(P.err, 40);
-        };
+        const long long xg_total = (long long)u.n_nets * XG_PER_NET;          // one source rank's region
+        const int me = u.p2p_rank;
 
         // ---- initial state: small slices from the arena, the W2 tile (p, m, v) into tensor memory ----
         for (int i = et; i < sm.n; i += NEPI) {
@@ -871,32 +861,23 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                 float g[C2];
                 acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
                 if (world > 1) {
+                    // push the local tile now; it is summed after the small slices went out as well (below)
                     const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
                     const int par = (int)(id & 1ULL);
-                    const size_t off = ((size_t)(net * 16 + (c - 16)) * NEPI + et) * C2;
-                    float* mine = const_cast<float*>(u.p2p_xg[par][u.p2p_rank]) + off;
-#pragma unroll
-                    for (int q = 0; q < C2 / 4; ++q) *reinterpret_cast<float4*>(mine + 4 * q) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
-                    __threadfence_system();
-                    epi_bar();
-                    if (et == 0) { dp_signal(blockIdx.x, id); dp_wait(blockIdx.x, id); }
-                    epi_bar();
-#pragma unroll
-                    for (int jq = 0; jq < C2; ++jq) g[jq] = 0.f;
+                    const uint32_t tag = (P.dp_seq << 16) | (uint32_t)((t + 1) & 0xffff);
+                    const size_t off = (size_t)me * xg_total + (size_t)(net * 16 + (c - 16)) * TILE_FLOATS + (size_t)et * 4;
                     for (int r = 0; r < world; ++r) {
-                        const float* src = u.p2p_xg[par][r] + off;
-                        float4 v[C2 / 4];
+                        if (r == me) continue;
+                        float* dst = const_cast<float*>(u.p2p_xg[par][r]) + off;
 #pragma unroll
-                        for (int q = 0; q < C2 / 4; ++q) v[q] = ld_peer4(src + 4 * q);
-#pragma unroll
-                        for (int q = 0; q < C2 / 4; ++q) { g[4 * q] += v[q].x; g[4 * q + 1] += v[q].y; g[4 * q + 2] += v[q].z; g[4 * q + 3] += v[q].w; }
+                        for (int q = 0; q < TILE_PK; ++q)
+                            st_packet(dst + (size_t)q * NEPI * 4, g[3 * q], 3 * q + 1 < C2 ? g[3 * q + 1] : 0.f, 3 * q + 2 < C2 ? g[3 * q + 2] : 0.f, tag);
                     }
+                    if (et == 0) STAMP(32);
+                } else {
 #pragma unroll
-                    for (int jq = 0; jq < C2; ++jq) g[jq] *= inv_world;
-                    tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
+                    for (int jq = 0; jq < C2; ++jq) sq = fmaf(g[jq], g[jq], sq);
                 }
-#pragma unroll
-                for (int jq = 0; jq < C2; ++jq) sq = fmaf(g[jq], g[jq], sq);
             }
             // ---- small-parameter gradients: fixed-order sums of the row-block partials.  The b2 / W3 / b3 partials
             // are complete since flag C: they are summed while flag D1 (the dW1 partials) is still on its way.
@@ -947,21 +928,80 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (world > 1) {
                 const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
                 const int par = (int)(id & 1ULL);
-                const size_t off = (size_t)u.n_nets * 16 * 4096 + (size_t)(net * 8 + b) * NSMAX;
+                const uint32_t tag = (P.dp_seq << 16) | (uint32_t)((t + 1) & 0xffff);
+                const size_t off_s = (size_t)u.n_nets * 16 * TILE_FLOATS + (size_t)(net * 8 + b) * SLICE_PK * 4;
+                const int n3 = (sm.n + 2) / 3;
+                const float* loc = u.p2p_xg[par][me];
+                const long long t0w = clock64();
                 epi_bar();                                    // sp_g complete
                 if (a == 0) {
-                    float* mine = const_cast<float*>(u.p2p_xg[par][u.p2p_rank]) + off;
-                    for (int i = et; i < sm.n; i += NEPI) mine[i] = sp_g[i];
-                    __threadfence_system();
+                    for (int r = 0; r < world; ++r) {
+                        if (r == me) continue;
+                        float* dst = const_cast<float*>(u.p2p_xg[par][r]) + (size_t)me * xg_total + off_s;
+                        for (int i = et; i < n3; i += NEPI)
+                            st_packet(dst + 4 * (size_t)i, sp_g[3 * i], 3 * i + 1 < sm.n ? sp_g[3 * i + 1] : 0.f, 3 * i + 2 < sm.n ? sp_g[3 * i + 2] : 0.f, tag);
+                    }
+                    if (et == 0) STAMP(35);
                 }
-                epi_bar();
-                if (et == 0) { if (a == 0) dp_signal(net * 32 + b, id); dp_wait(net * 32 + b, id); }
-                epi_bar();
-                for (int i = et; i < sm.n; i += NEPI) {
-                    float acc = 0.f;
-                    for (int r = 0; r < world; ++r) acc += ld_peer(u.p2p_xg[par][r] + off + i);
-                    sp_g[i] = acc * inv_world;
+                // rank-ordered sums (own piece from shared memory); every thread waits for its own packets only
+                for (int i = et; i < n3; i += NEPI) {
+                    float ax = 0.f, ay = 0.f, az = 0.f;
+                    for (int r = 0; r < world; ++r) {
+                        float4 v;
+                        if (r == me) {
+                            v = make_float4(sp_g[3 * i], 3 * i + 1 < sm.n ? sp_g[3 * i + 1] : 0.f, 3 * i + 2 < sm.n ? sp_g[3 * i + 2] : 0.f, 0.f);
+                        } else {
+                            const float* src = loc + (size_t)r * xg_total + off_s + 4 * (size_t)i;
+                            v = ld_packet(src);
+                            while (__float_as_uint(v.w) != tag) {
+                                if (clock64() - t0w > 4 * WAIT_CYCLES) fail(P.err, 40);
+                                v = ld_packet(src);
+                            }
+                        }
+                        ax += v.x; ay += v.y; az += v.z;
+                    }
+                    sp_g[3 * i] = ax * inv_world;
+                    if (3 * i + 1 < sm.n) sp_g[3 * i + 1] = ay * inv_world;
+                    if (3 * i + 2 < sm.n) sp_g[3 * i + 2] = az * inv_world;
                 }
+                if (et == 0) STAMP(38);
+                if (!is_g2) {
+                    // the W2 tiles went out before the dW1 hop: by now the peers' packets have usually landed
+                    const size_t off = (size_t)(net * 16 + (c - 16)) * TILE_FLOATS + (size_t)et * 4;
+                    float own[C2], g[C2];
+                    acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, own);
+#pragma unroll
+                    for (int jq = 0; jq < C2; ++jq) g[jq] = 0.f;
+                    for (int r = 0; r < world; ++r) {
+                        if (r == me) {
+#pragma unroll
+                            for (int jq = 0; jq < C2; ++jq) g[jq] += own[jq];
+                            continue;
+                        }
+                        const float* src = loc + (size_t)r * xg_total + off;
+                        float4 v[TILE_PK];
+                        bool ok;
+                        do {
+                            ok = true;
+#pragma unroll
+                            for (int q = 0; q < TILE_PK; ++q) v[q] = ld_packet(src + (size_t)q * NEPI * 4);
+#pragma unroll
+                            for (int q = 0; q < TILE_PK; ++q) ok = ok && (__float_as_uint(v[q].w) == tag);
+                            if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(P.err, 41);
+                        } while (!ok);
+#pragma unroll
+                        for (int q = 0; q < TILE_PK; ++q) {
+                            g[3 * q] += v[q].x;
+                            if (3 * q + 1 < C2) g[3 * q + 1] += v[q].y;
+                            if (3 * q + 2 < C2) g[3 * q + 2] += v[q].z;
+                        }
+                    }
+#pragma unroll
+                    for (int jq = 0; jq < C2; ++jq) { g[jq] *= inv_world; sq = fmaf(g[jq], g[jq], sq); }
+                    tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
+                    if (et == 0) STAMP(41);
+                }
+                epi_bar();                                    // sp_g holds the global mean before the norm / Adam read it
             }
             // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3 / log sigma by CTA 0.
             // (each thread re-reads only elements it wrote itself: same i = et + k NEPI mapping)
@@ -1059,7 +1099,7 @@ size_t ppo_persist_ws_floats(int n_nets, int D, int H) {
            2 * (size_t)pp::MAX_MB + 2 * (size_t)32 * n_nets * pp::DBG_N;
 }
 
-size_t ppo_persist_p2p_floats(int n_nets) { return (size_t)n_nets * pp::XG_PER_NET + pp::XG_FLAG_FLOATS + 64; }
+size_t ppo_persist_p2p_floats(int n_nets) { return (size_t)FSRL_P2P_MAX_RANKS * n_nets * pp::XG_PER_NET + pp::XG_FLAG_FLOATS + 64; }
 
 bool ppo_persist_supported(const fsrl_ppo_update_t& u, long long n_total, int batch_size) {
     if (u.H != 256 || batch_size != pp::MB || n_total % pp::MB != 0 || n_total < pp::MB || n_total / pp::MB > pp::MAX_MB) return false;
@@ -1100,6 +1140,10 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
     }
     FSRL_CUDA(cudaMemcpyAsync(tab_dev, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     a.adam_tab = tab_dev;
+    // tag of the exchange packets: ranks run their persistent launches in lock step, so the count agrees everywhere
+    static unsigned dp_seq = 0;
+    if (ug.world > 1) dp_seq = (dp_seq % 65535u) + 1u;
+    a.dp_seq = dp_seq;
     a.dbg = nullptr; a.dbg_step = -1;
     if (const char* e = getenv("FSRL_PPO_PERSIST_DBG")) {
         a.dbg = reinterpret_cast<long long*>(tab_dev + 2 * (size_t)pp::MAX_MB);

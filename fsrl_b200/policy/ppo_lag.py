@@ -195,7 +195,7 @@ class PPOLagrangian(LagrangianPolicy):
                     perm_host.numpy()[:] = next_perm
                     next_perm = None
                 else:
-                    perm_host.numpy()[:] = np.random.permutation(n)
+                    perm_host.numpy()[:] = self._first_permutation(n)
                 perm_dev.copy_(perm_host, non_blocking=True)
                 u = self._descriptor(batch, perm_dev)
                 n_mb = ctypes.c_int(0)
@@ -210,6 +210,8 @@ class PPOLagrangian(LagrangianPolicy):
                 if step + 1 < repeat:
                     rng_state = np.random.get_state()
                     next_perm = np.random.permutation(n)
+                else:
+                    self._prefetch_permutation(n)
                 st = self._stats_dev[slot * _lib.PPO_STATS:(slot + n_mb.value) * _lib.PPO_STATS] \
                     .view(n_mb.value, _lib.PPO_STATS).cpu().numpy()                    # sync point
                 rows.append(st)
@@ -226,6 +228,28 @@ class PPOLagrangian(LagrangianPolicy):
             self._dp.p2p_check()             # raises if a peer rank never joined a gradient exchange
         self._log_stats(np.concatenate(rows, axis=0), u)
         self.logger.store(gradient_steps=self.gradient_steps, tab="update")
+
+    # ---- first permutation of the NEXT learn call, drawn while the last repeat's launch is still running -----------
+    # The global NumPy stream must be consumed exactly as in the reference (one permutation per executed repeat, nothing
+    # else), so the draw is speculative: the generator is put back to where it was, and the result is used only if the
+    # next learn call finds the generator in that very state (nobody drew from it in between) -- then the generator is
+    # advanced to where the draw had left it.
+    @staticmethod
+    def _same_rng_state(a, b) -> bool:
+        return a[0] == b[0] and a[2:] == b[2:] and np.array_equal(a[1], b[1])
+
+    def _prefetch_permutation(self, n: int) -> None:
+        before = np.random.get_state()
+        perm = np.random.permutation(n)
+        self._spec_perm = (n, before, perm, np.random.get_state())
+        np.random.set_state(before)
+
+    def _first_permutation(self, n: int) -> np.ndarray:
+        spec, self._spec_perm = getattr(self, "_spec_perm", None), None
+        if spec is not None and spec[0] == n and self._same_rng_state(np.random.get_state(), spec[1]):
+            np.random.set_state(spec[3])
+            return spec[2]
+        return np.random.permutation(n)
 
     # ---- the reference's per-piece loss hooks (ppo_lag.py:152-212) ------------------------------------------------
     # ``learn`` never calls these: the persistent launch / kernel chain evaluates both losses, their gradients and the

@@ -206,3 +206,36 @@ def test_oracle_offpolicy_step_equals_targets_plus_update():
                         torch.optim.Adam([p for q in c for p in q.parameters()], lr=1e-3), buf, idx, gamma=0.97, n_step=2,
                         tau=0.05, lagrangian=0.4)
     assert np.isfinite(list(st.values())).all() and {"loss/q0", "loss/q1", "loss/actor_total"} <= set(st)
+
+
+def test_speculative_permutation_keeps_the_numpy_stream():
+    """ppo_lag.learn draws the next learn call's first permutation early (while the last launch runs): the global NumPy
+    stream must look untouched to everybody else, and the draw must be dropped if someone consumed the stream in between."""
+    from fsrl_b200.policy.ppo_lag import PPOLagrangian as P
+
+    class Host:
+        _same_rng_state = staticmethod(P._same_rng_state)
+
+    h = Host()
+    np.random.seed(11)
+    ref = [np.random.permutation(50) for _ in range(3)]
+    np.random.seed(11)
+    first = np.random.permutation(50)
+    P._prefetch_permutation(h, 50)
+    second = P._first_permutation(h, 50)
+    third = np.random.permutation(50)
+    assert (first == ref[0]).all() and (second == ref[1]).all() and (third == ref[2]).all()
+    # somebody else draws between the two learn calls: the reference order is (their draw, then the permutation)
+    np.random.seed(11)
+    r_ref = np.random.rand(); p_ref = np.random.permutation(50)
+    np.random.seed(11)
+    P._prefetch_permutation(h, 50)
+    r = np.random.rand()
+    p = P._first_permutation(h, 50)
+    assert r == r_ref and (p == p_ref).all()
+    # a different row count invalidates the draw
+    np.random.seed(11)
+    P._prefetch_permutation(h, 50)
+    q = P._first_permutation(h, 40)
+    np.random.seed(11)
+    assert (q == np.random.permutation(40)).all()

@@ -141,7 +141,7 @@ def main():
         run(policy2, batch2, 256, True, seed=5)
         del os.environ["FSRL_PPO_PERSIST_DBG"]
         ws = policy2._persist_ws.detach().cpu().numpy()
-        dbg = ws[-2 * 96 * 32:].view(np.int64).reshape(96, 32)
+        dbg = ws[-2 * 96 * 48:].view(np.int64).reshape(96, 48)
         names = {1: "S done (h1 tile + W2 images)", 2: "G1 accumulators ready", 3: "head partial written", 4: "flag B passed",
                  5: "dz2 + partials written", 6: "G2/G3 accumulators ready", 7: "G2/G3 epilogue done", 8: "flag D1 passed",
                  9: "slices reduced, sumsq out", 10: "flag D2 passed", 11: "Adam done (step end)", 12: "[producer] flag A passed",
