@@ -305,6 +305,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    ranks_identical = None
+    if dist is not None:
+        # lock-step check: every rank must hold bit-identical parameters after the K + K cycles
+        th = agent.policy.arena.theta.detach()
+        sig = torch.stack([th.double().sum(), th.double().abs().sum(), th.view(torch.int32).long().sum().double()])
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        ranks_identical = all(bool(torch.equal(sigs[0], x)) for x in sigs)
 
     if rank != 0:
         if dist is not None:
@@ -339,6 +347,8 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if ranks_identical is not None:
+        out["ranks_bit_identical_parameters"] = ranks_identical
     if world > 1:
         # the other ranks are gone: the per-kernel measurements below run on this GPU alone, without the exchange
         agent.policy._dp = None

@@ -62,8 +62,9 @@ constexpr int FLAG_LINE = 32;
 constexpr int F_A = 0, F_C = 1, F_D1 = 2, F_B = 3, F_PER_NET = 7;
 constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,64) accumulators, Adam state
 constexpr int TM_G = 160;                                        // reduced gradient tile (data-parallel runs)
-// peer-mapped exchange buffer of one step parity (floats): one region per SOURCE rank [8], each holding per net 16
-// gradient tiles and the locally reduced small-parameter slices of the 8 column blocks.  Ranks PUSH their pieces into
+// peer-mapped exchange buffer of one step parity (floats): one region per SOURCE rank [8] plus one for the W2 means
+// (written by the packets' owners), each holding per net 16 gradient tiles and the locally reduced small-parameter
+// slices of the 8 column blocks.  Ranks PUSH their pieces into
 // every peer's buffer as 16-byte packets {3 floats, tag}: the tag (launch sequence number | step) travels with the data,
 // so the receiver polls its own memory until every packet carries the tag -- one NVLink one-way latency per exchange,
 // no system-scope fence (measured: ~6 us each with posted peer writes outstanding), no flag round trip, no remote loads.
@@ -92,6 +93,7 @@ struct Args {
     int dbg_step;
     int cluster;             // launched as clusters of 8 CTAs (one row block): hop B runs over distributed shared memory
     unsigned dp_seq;         // data-parallel runs: launch sequence number (same on every rank), upper half of the packet tags
+    int dp_direct;           // W2 gradient tiles exchanged in one hop (2 ranks) instead of the two-hop owner scheme
 };
 constexpr int DBG_N = 48;
 #define STAMP(i) do { if (P.dbg && t == P.dbg_step) P.dbg[(size_t)blockIdx.x * DBG_N + (i)] = clock64(); } while (0)
@@ -122,6 +124,41 @@ __device__ __forceinline__ float4 ld_packet(const float* p) {
     float4 v;
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
+}
+
+// Wait for the packets of all ranks but `me` at src + r * stride (local memory, pushed by the peers) and add them to the
+// own piece (ox, oy, oz) in rank order.  Deliberately not inlined: the exchange code runs once per step and the kernel's
+// instruction footprint matters (measured: the step slows down by ~10 % when the exchange is unrolled into the epilogue).
+__device__ __noinline__ float3 dp_gather(const float* src, long long stride, int me, int world, uint32_t tag,
+                                        float ox, float oy, float oz, int* err, int code) {
+    const long long t0w = clock64();
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int r0 = 0; r0 < world; r0 += 4) {                // four ranks' packets in flight, rank order kept
+        float4 v[4];
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r0 + k < world && r0 + k != me) v[k] = ld_packet(src + (size_t)(r0 + k) * stride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r0 + k < world && r0 + k != me) ok = ok && (__float_as_uint(v[k].w) == tag);
+            if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(err, code);
+        } while (!ok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (r0 + k >= world) continue;
+            if (r0 + k == me) { ax += ox; ay += oy; az += oz; }
+            else { ax += v[k].x; ay += v[k].y; az += v[k].z; }
+        }
+    }
+    return make_float3(ax, ay, az);
+}
+// one packet to every rank but `me`: dst_r = xg[r] + off
+__device__ __noinline__ void dp_push_all(const float* const* xg, size_t off, int me, int world, float x, float y, float z, uint32_t tag) {
+    for (int r = 0; r < world; ++r)
+        if (r != me) st_packet(const_cast<float*>(xg[r]) + off, x, y, z, tag);
 }
 
 // ---- thread-block cluster: distributed shared memory pushes + remote mbarrier arrivals (hop B) ------------------------
@@ -275,6 +312,146 @@ struct SliceMap {
     __device__ __host__ SliceMap(int D) { w1 = 0; b2 = (D + 1) * 32; w3 = b2 + 32; b3 = w3 + 32 * OUTP; n = b3 + 16; }
 };
 
+// ---- data-parallel exchange, out of line ---------------------------------------------------------------------------------
+// All of it lives in functions the kernel CALLS: inlined into the epilogue, the mere presence of this code slowed every
+// phase of the step down by ~9 % (measured with the exchange compiled in but world = 1) -- register allocation and the
+// instruction footprint of the ~7k-instruction epilogue are that tight.
+struct DpCtx {
+    const float* const* xg;   // [rank] exchange buffers of this step's parity (shared-memory table)
+    long long region;         // floats per source-rank region
+    int me, world;
+    uint32_t tag;
+    int* err;
+    int direct;               // W2 tiles in ONE hop (every rank sums all ranks' tiles itself): less latency, W - 1 tile
+                              // volumes per rank -- the choice for 2 ranks; the two-hop owner scheme beyond
+};
+__device__ __forceinline__ int dp_owner(int et, int q, int world) { return (int)((unsigned)((et >> 5) * TILE_PK + q) % (unsigned)world); }
+
+// hop 1 of a W2 gradient tile: every packet of the local tile (tensor-memory accumulators) to its owner
+__device__ __noinline__ void dp_tile_send(DpCtx d, size_t off, uint32_t tm_lane, int lane, int wq, int et) {
+    float g[C2];
+    acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
+#pragma unroll
+    for (int q = 0; q < TILE_PK; ++q) {
+        const size_t o_q = (size_t)d.me * d.region + off + (size_t)q * NEPI * 4;
+        const float x = g[3 * q], y = 3 * q + 1 < C2 ? g[3 * q + 1] : 0.f, z = 3 * q + 2 < C2 ? g[3 * q + 2] : 0.f;
+        if (d.direct) {
+            dp_push_all(d.xg, o_q, d.me, d.world, x, y, z, d.tag);
+        } else {
+            const int o = dp_owner(et, q, d.world);
+            if (o != d.me) st_packet(const_cast<float*>(d.xg[o]) + o_q, x, y, z, d.tag);
+        }
+    }
+}
+// hop 2: owned packets -- rank-ordered mean of the ranks' contributions, pushed into everybody's result region; the tile
+// (owned entries final, the others still local) goes to tensor-memory columns TM_G
+__device__ __noinline__ void dp_tile_reduce(DpCtx d, size_t off, uint32_t tm_lane, int lane, int wq, int et) {
+    float g[C2];
+    acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
+    const float inv_world = 1.0f / (float)d.world;
+    const float* loc = d.xg[d.me];
+#pragma unroll
+    for (int q = 0; q < TILE_PK; ++q) {
+        if (dp_owner(et, q, d.world) != d.me) continue;
+        const float3 s3 = dp_gather(loc + off + (size_t)q * NEPI * 4, d.region, d.me, d.world, d.tag, g[3 * q],
+                                    3 * q + 1 < C2 ? g[3 * q + 1] : 0.f, 3 * q + 2 < C2 ? g[3 * q + 2] : 0.f, d.err, 41);
+        const float ax = s3.x * inv_world, ay = s3.y * inv_world, az = s3.z * inv_world;
+        dp_push_all(d.xg, (size_t)FSRL_P2P_MAX_RANKS * d.region + off + (size_t)q * NEPI * 4, d.me, d.world, ax, ay, az, d.tag);
+        g[3 * q] = ax;
+        if (3 * q + 1 < C2) g[3 * q + 1] = ay;
+        if (3 * q + 2 < C2) g[3 * q + 2] = az;
+    }
+    tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
+}
+// the other owners' means: wait for them in the local result region, complete the tile in TM_G, return its sum of squares
+__device__ __noinline__ float dp_tile_finish(DpCtx d, size_t off, uint32_t tm_lane, int lane, int wq, int et) {
+    float g[C2];
+    const long long t0w = clock64();
+    if (d.direct) {
+        // one hop: all ranks' tiles are (or will be) in the local contribution regions -- rank-ordered mean, rank by rank
+        float own[C2];
+        acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, own);
+#pragma unroll
+        for (int jq = 0; jq < C2; ++jq) g[jq] = 0.f;
+        for (int r = 0; r < d.world; ++r) {
+            if (r == d.me) {
+#pragma unroll
+                for (int jq = 0; jq < C2; ++jq) g[jq] += own[jq];
+                continue;
+            }
+            const float* src = d.xg[d.me] + (size_t)r * d.region + off;
+            float4 v[TILE_PK];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int q = 0; q < TILE_PK; ++q) v[q] = ld_packet(src + (size_t)q * NEPI * 4);
+#pragma unroll
+                for (int q = 0; q < TILE_PK; ++q) ok = ok && (__float_as_uint(v[q].w) == d.tag);
+                if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(d.err, 42);
+            } while (!ok);
+#pragma unroll
+            for (int q = 0; q < TILE_PK; ++q) {
+                g[3 * q] += v[q].x;
+                if (3 * q + 1 < C2) g[3 * q + 1] += v[q].y;
+                if (3 * q + 2 < C2) g[3 * q + 2] += v[q].z;
+            }
+        }
+        const float inv_world = 1.0f / (float)d.world;
+        float sq = 0.f;
+#pragma unroll
+        for (int jq = 0; jq < C2; ++jq) { g[jq] *= inv_world; sq = fmaf(g[jq], g[jq], sq); }
+        tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
+        return sq;
+    }
+    const float* res = d.xg[d.me] + (size_t)FSRL_P2P_MAX_RANKS * d.region + off;
+    tmem_ldn<C2>(tm_lane + TM_G + C2 * wq, g);
+    float4 v[TILE_PK];
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int q = 0; q < TILE_PK; ++q)
+            if (dp_owner(et, q, d.world) != d.me) v[q] = ld_packet(res + (size_t)q * NEPI * 4);
+#pragma unroll
+        for (int q = 0; q < TILE_PK; ++q)
+            if (dp_owner(et, q, d.world) != d.me) ok = ok && (__float_as_uint(v[q].w) == d.tag);
+        if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(d.err, 42);
+    } while (!ok);
+    float sq = 0.f;
+#pragma unroll
+    for (int q = 0; q < TILE_PK; ++q) {
+        if (dp_owner(et, q, d.world) == d.me) continue;
+        g[3 * q] = v[q].x;
+        if (3 * q + 1 < C2) g[3 * q + 1] = v[q].y;
+        if (3 * q + 2 < C2) g[3 * q + 2] = v[q].z;
+    }
+#pragma unroll
+    for (int jq = 0; jq < C2; ++jq) sq = fmaf(g[jq], g[jq], sq);
+    tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
+    return sq;
+}
+// small-parameter slices of one column block (n floats in shared memory): row block 0 pushes them to every rank, every
+// CTA of the column block replaces them by the rank-ordered mean (one hop: this exchange is on the step's critical path)
+__device__ __noinline__ void dp_slices(DpCtx d, size_t off_s, float* sp_g, int n, int et, bool push) {
+    const int n3 = (n + 2) / 3;
+    const float inv_world = 1.0f / (float)d.world;
+    if (push)
+        for (int i = et; i < n3; i += NEPI)
+            dp_push_all(d.xg, (size_t)d.me * d.region + off_s + 4 * (size_t)i, d.me, d.world,
+                        sp_g[3 * i], 3 * i + 1 < n ? sp_g[3 * i + 1] : 0.f, 3 * i + 2 < n ? sp_g[3 * i + 2] : 0.f, d.tag);
+    const float* loc = d.xg[d.me];
+    for (int i = et; i < n3; i += NEPI) {
+        const float3 s3 = dp_gather(loc + off_s + 4 * (size_t)i, d.region, d.me, d.world, d.tag, sp_g[3 * i],
+                                    3 * i + 1 < n ? sp_g[3 * i + 1] : 0.f, 3 * i + 2 < n ? sp_g[3 * i + 2] : 0.f, d.err, 40);
+        sp_g[3 * i] = s3.x * inv_world;
+        if (3 * i + 1 < n) sp_g[3 * i + 1] = s3.y * inv_world;
+        if (3 * i + 2 < n) sp_g[3 * i + 2] = s3.z * inv_world;
+    }
+}
+
+// DP = false: single-GPU instantiation without any of the exchange code (smaller instruction footprint)
+template <bool DP>
 __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_acc, bar_b;
@@ -282,6 +459,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     __shared__ float s_red[4][320];          // cross-subpartition partial sums
     __shared__ float s_misc[32];
     __shared__ AdamS s_adam;
+    __shared__ const float* s_xg[2][FSRL_P2P_MAX_RANKS];   // peers' exchange buffers (a table the exchange helpers can index)
     const fsrl_ppo_update_t& u = P.u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int net = blockIdx.x >> 5, c = blockIdx.x & 31, a = c >> 3, b = c & 7;
@@ -289,7 +467,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     const int ka = (c & 15) >> 2, q4 = c & 3;      // G2: (k block, row block) ; G3: (k block, o block)
     const int D = u.D, A = u.A, C = u.C, H = H_;
     const int out = (net == 0) ? A : 1;
-    const int n_cta = gridDim.x;
+    const int n_cta = 32 * u.n_nets;
     float* wsn = P.ws + (size_t)net * NET_WS;
     float* sumsq_g = P.ws + (size_t)u.n_nets * NET_WS;
     unsigned* fl_net = P.flags + (size_t)net * F_PER_NET * FLAG_LINE;
@@ -314,6 +492,8 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    if (DP && threadIdx.x < 2 * FSRL_P2P_MAX_RANKS) s_xg[threadIdx.x / FSRL_P2P_MAX_RANKS][threadIdx.x % FSRL_P2P_MAX_RANKS] = P.u.p2p_xg[threadIdx.x / FSRL_P2P_MAX_RANKS][threadIdx.x % FSRL_P2P_MAX_RANKS];
+    if (DP) __syncthreads();
     if (P.cluster) cluster_sync_all();       // every CTA's barriers exist before a peer may arrive on them
 
     // parameter offsets of this network inside the flat arena
@@ -426,10 +606,23 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
         // slot of every rank's flag array; the receiver waits for the ranks' flags and sums their pieces from its own
         // memory in rank order -- point-to-point between equal CTAs, one NVLink one-way latency, no remote loads,
         // bit-identical sums on every rank.
-        const int world = u.world > 1 ? u.world : 1;
+        const int world = (DP && u.world > 1) ? u.world : 1;
         const float inv_world = 1.0f / (float)world;
-        const long long xg_total = (long long)u.n_nets * XG_PER_NET;          // one source rank's region
-        const int me = u.p2p_rank;
+        // W2 tiles travel in two hops (reduce-scatter + all-gather, 2 (W - 1) / W tile volumes per rank instead of W - 1):
+        // packet q of epilogue warp w is OWNED by rank (6 w + q) mod W -- every rank sends it there, the owner sums the
+        // ranks' packets in rank order and pushes the mean into everybody's result region (region 8).  Both hops are
+        // hidden behind the dW1 hop / slice reduction of the same step; the result is bit-identical on every rank.
+        auto dp_ctx = [&](int t_) {
+            DpCtx d;
+            const unsigned long long id = (unsigned long long)(P.adam_t0 + t_ + 1);
+            d.xg = s_xg[(int)(id & 1ULL)];
+            d.region = (long long)u.n_nets * XG_PER_NET;
+            d.me = u.p2p_rank; d.world = world;
+            d.tag = (P.dp_seq << 16) | (uint32_t)((t_ + 1) & 0xffff);
+            d.err = P.err;
+            d.direct = P.dp_direct;
+            return d;
+        };
 
         // ---- initial state: small slices from the arena, the W2 tile (p, m, v) into tensor memory ----
         for (int i = et; i < sm.n; i += NEPI) {
@@ -860,19 +1053,8 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             } else {
                 float g[C2];
                 acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
-                if (world > 1) {
-                    // push the local tile now; it is summed after the small slices went out as well (below)
-                    const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
-                    const int par = (int)(id & 1ULL);
-                    const uint32_t tag = (P.dp_seq << 16) | (uint32_t)((t + 1) & 0xffff);
-                    const size_t off = (size_t)me * xg_total + (size_t)(net * 16 + (c - 16)) * TILE_FLOATS + (size_t)et * 4;
-                    for (int r = 0; r < world; ++r) {
-                        if (r == me) continue;
-                        float* dst = const_cast<float*>(u.p2p_xg[par][r]) + off;
-#pragma unroll
-                        for (int q = 0; q < TILE_PK; ++q)
-                            st_packet(dst + (size_t)q * NEPI * 4, g[3 * q], 3 * q + 1 < C2 ? g[3 * q + 1] : 0.f, 3 * q + 2 < C2 ? g[3 * q + 2] : 0.f, tag);
-                    }
+                if (DP && world > 1) {
+                    dp_tile_send(dp_ctx(t), (size_t)(net * 16 + (c - 16)) * TILE_FLOATS + (size_t)et * 4, tm_lane, lane, wq, et);
                     if (et == 0) STAMP(32);
                 } else {
 #pragma unroll
@@ -925,82 +1107,14 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (et == 0) { STAMP(7); if (!flag_wait_ge(fl_net + F_D1 * FLAG_LINE, 16u * (t + 1), WAIT_CYCLES)) fail(P.err, 33); STAMP(8); }
             epi_bar();
             reduce_slices(0, sm.b2);
-            if (world > 1) {
-                const unsigned long long id = (unsigned long long)(P.adam_t0 + t + 1);
-                const int par = (int)(id & 1ULL);
-                const uint32_t tag = (P.dp_seq << 16) | (uint32_t)((t + 1) & 0xffff);
-                const size_t off_s = (size_t)u.n_nets * 16 * TILE_FLOATS + (size_t)(net * 8 + b) * SLICE_PK * 4;
-                const int n3 = (sm.n + 2) / 3;
-                const float* loc = u.p2p_xg[par][me];
-                const long long t0w = clock64();
+            if (DP && world > 1) {
+                const DpCtx d = dp_ctx(t);
+                const size_t off_t = (size_t)(net * 16 + (c - 16)) * TILE_FLOATS + (size_t)et * 4;
                 epi_bar();                                    // sp_g complete
-                if (a == 0) {
-                    for (int r = 0; r < world; ++r) {
-                        if (r == me) continue;
-                        float* dst = const_cast<float*>(u.p2p_xg[par][r]) + (size_t)me * xg_total + off_s;
-                        for (int i = et; i < n3; i += NEPI)
-                            st_packet(dst + 4 * (size_t)i, sp_g[3 * i], 3 * i + 1 < sm.n ? sp_g[3 * i + 1] : 0.f, 3 * i + 2 < sm.n ? sp_g[3 * i + 2] : 0.f, tag);
-                    }
-                    if (et == 0) STAMP(35);
-                }
-                // rank-ordered sums (own piece from shared memory); every thread waits for its own packets only
-                for (int i = et; i < n3; i += NEPI) {
-                    float ax = 0.f, ay = 0.f, az = 0.f;
-                    for (int r = 0; r < world; ++r) {
-                        float4 v;
-                        if (r == me) {
-                            v = make_float4(sp_g[3 * i], 3 * i + 1 < sm.n ? sp_g[3 * i + 1] : 0.f, 3 * i + 2 < sm.n ? sp_g[3 * i + 2] : 0.f, 0.f);
-                        } else {
-                            const float* src = loc + (size_t)r * xg_total + off_s + 4 * (size_t)i;
-                            v = ld_packet(src);
-                            while (__float_as_uint(v.w) != tag) {
-                                if (clock64() - t0w > 4 * WAIT_CYCLES) fail(P.err, 40);
-                                v = ld_packet(src);
-                            }
-                        }
-                        ax += v.x; ay += v.y; az += v.z;
-                    }
-                    sp_g[3 * i] = ax * inv_world;
-                    if (3 * i + 1 < sm.n) sp_g[3 * i + 1] = ay * inv_world;
-                    if (3 * i + 2 < sm.n) sp_g[3 * i + 2] = az * inv_world;
-                }
+                if (!is_g2 && !d.direct) { dp_tile_reduce(d, off_t, tm_lane, lane, wq, et); if (et == 0) STAMP(33); }
+                dp_slices(d, (size_t)u.n_nets * 16 * TILE_FLOATS + (size_t)(net * 8 + b) * SLICE_PK * 4, sp_g, sm.n, et, a == 0);
                 if (et == 0) STAMP(38);
-                if (!is_g2) {
-                    // the W2 tiles went out before the dW1 hop: by now the peers' packets have usually landed
-                    const size_t off = (size_t)(net * 16 + (c - 16)) * TILE_FLOATS + (size_t)et * 4;
-                    float own[C2], g[C2];
-                    acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, own);
-#pragma unroll
-                    for (int jq = 0; jq < C2; ++jq) g[jq] = 0.f;
-                    for (int r = 0; r < world; ++r) {
-                        if (r == me) {
-#pragma unroll
-                            for (int jq = 0; jq < C2; ++jq) g[jq] += own[jq];
-                            continue;
-                        }
-                        const float* src = loc + (size_t)r * xg_total + off;
-                        float4 v[TILE_PK];
-                        bool ok;
-                        do {
-                            ok = true;
-#pragma unroll
-                            for (int q = 0; q < TILE_PK; ++q) v[q] = ld_packet(src + (size_t)q * NEPI * 4);
-#pragma unroll
-                            for (int q = 0; q < TILE_PK; ++q) ok = ok && (__float_as_uint(v[q].w) == tag);
-                            if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(P.err, 41);
-                        } while (!ok);
-#pragma unroll
-                        for (int q = 0; q < TILE_PK; ++q) {
-                            g[3 * q] += v[q].x;
-                            if (3 * q + 1 < C2) g[3 * q + 1] += v[q].y;
-                            if (3 * q + 2 < C2) g[3 * q + 2] += v[q].z;
-                        }
-                    }
-#pragma unroll
-                    for (int jq = 0; jq < C2; ++jq) { g[jq] *= inv_world; sq = fmaf(g[jq], g[jq], sq); }
-                    tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
-                    if (et == 0) STAMP(41);
-                }
+                if (!is_g2) { sq += dp_tile_finish(d, off_t, tm_lane, lane, wq, et); if (et == 0) STAMP(41); }
                 epi_bar();                                    // sp_g holds the global mean before the norm / Adam read it
             }
             // every small parameter is counted once in the norm: W1/b1/b2/W3 slices by row block 0, b3 / log sigma by CTA 0.
@@ -1047,7 +1161,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (et == 0) STAMP(25);
             if (!is_g2) {
                 float g[C2], pv[C2], mv[C2], vv[C2];
-                if (world > 1) tmem_ldn<C2>(tm_lane + TM_G + C2 * wq, g);
+                if (DP && world > 1) tmem_ldn<C2>(tm_lane + TM_G + C2 * wq, g);
                 else acc_ld_split<C2>(tm_lane, lane, C2 * wq, 32 + C2 * wq, g);
                 tmem_ldn<C2>(tm_lane + TM_P + C2 * wq, pv); tmem_ldn<C2>(tm_lane + TM_M + C2 * wq, mv); tmem_ldn<C2>(tm_lane + TM_V + C2 * wq, vv);
 #pragma unroll
@@ -1099,7 +1213,7 @@ size_t ppo_persist_ws_floats(int n_nets, int D, int H) {
            2 * (size_t)pp::MAX_MB + 2 * (size_t)32 * n_nets * pp::DBG_N;
 }
 
-size_t ppo_persist_p2p_floats(int n_nets) { return (size_t)FSRL_P2P_MAX_RANKS * n_nets * pp::XG_PER_NET + pp::XG_FLAG_FLOATS + 64; }
+size_t ppo_persist_p2p_floats(int n_nets) { return (size_t)(FSRL_P2P_MAX_RANKS + 1) * n_nets * pp::XG_PER_NET + pp::XG_FLAG_FLOATS + 64; }
 
 bool ppo_persist_supported(const fsrl_ppo_update_t& u, long long n_total, int batch_size) {
     if (u.H != 256 || batch_size != pp::MB || n_total % pp::MB != 0 || n_total < pp::MB || n_total / pp::MB > pp::MAX_MB) return false;
@@ -1144,6 +1258,8 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
     static unsigned dp_seq = 0;
     if (ug.world > 1) dp_seq = (dp_seq % 65535u) + 1u;
     a.dp_seq = dp_seq;
+    a.dp_direct = ug.world <= 2;
+    if (const char* e = getenv("FSRL_PPO_DP_DIRECT")) a.dp_direct = atoi(e) != 0;      // (experiments; must agree on all ranks)
     a.dbg = nullptr; a.dbg_step = -1;
     if (const char* e = getenv("FSRL_PPO_PERSIST_DBG")) {
         a.dbg = reinterpret_cast<long long*>(tab_dev + 2 * (size_t)pp::MAX_MB);
@@ -1159,10 +1275,12 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
     }
     bool cluster = !getenv("FSRL_PPO_NO_CLUSTER") && pp::smem_bytes(ug.D, true) + 8192 <= (size_t)smem_optin;
     size_t smem = pp::smem_bytes(ug.D, cluster);
-    static size_t set = 0;
-    if (smem > set) {
-        FSRL_CUDA(cudaFuncSetAttribute(pp::ppo_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set = smem;
+    const bool dp = ug.world > 1 || getenv("FSRL_PPO_FORCE_DP_KERNEL") != nullptr;   // (the env switch: code-generation experiments)
+    void (*kern)(const pp::Args) = dp ? pp::ppo_persist_kernel<true> : pp::ppo_persist_kernel<false>;
+    static size_t set[2] = {0, 0};
+    if (smem > set[dp]) {
+        FSRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set[dp] = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(32 * ug.n_nets); cfg.blockDim = dim3(pp::TPB); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1172,7 +1290,7 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
     if (cluster) {
         cfg.attrs = at; cfg.numAttrs = 1;
         int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, pp::ppo_persist_kernel, &cfg) != cudaSuccess || n_clusters < 4 * ug.n_nets) {
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess || n_clusters < 4 * ug.n_nets) {
             cudaGetLastError();
             cluster = false;
             smem = pp::smem_bytes(ug.D, false);
@@ -1181,7 +1299,7 @@ int ppo_persist_run(const fsrl_ppo_update_t& ug, int n_mb, int stats_slot0, long
     }
     if (!cluster) { cfg.attrs = nullptr; cfg.numAttrs = 0; }
     a.cluster = cluster ? 1 : 0;
-    FSRL_CUDA(cudaLaunchKernelEx(&cfg, pp::ppo_persist_kernel, a));
+    FSRL_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     ++g_launches;
     return FSRL_OK;
 }

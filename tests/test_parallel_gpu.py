@@ -120,7 +120,10 @@ def _worker_persistent(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_persistent_update_matches_chain_exchange():
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_two_rank_persistent_update_matches_chain_exchange(direct, monkeypatch):
+    # direct = 1: W2 gradient tiles in one hop (the default for 2 ranks); 0: the two-hop owner scheme used beyond 2 ranks
+    monkeypatch.setenv("FSRL_PPO_DP_DIRECT", direct)
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
