@@ -308,11 +308,17 @@ def run_ours(args):
     ranks_identical = None
     if dist is not None:
         # lock-step check: every rank must hold bit-identical parameters after the K + K cycles
-        th = agent.policy.arena.theta.detach()
-        sig = torch.stack([th.double().sum(), th.double().abs().sum(), th.view(torch.int32).long().sum().double()])
-        sigs = [torch.zeros_like(sig) for _ in range(world)]
-        dist.all_gather(sigs, sig)
-        ranks_identical = all(bool(torch.equal(sigs[0], x)) for x in sigs)
+        th = agent.policy.arena.theta.detach().contiguous()
+        allth = [torch.empty_like(th) for _ in range(world)]
+        dist.all_gather(allth, th)
+        ranks_identical = all(bool(torch.equal(allth[0].view(torch.int32), x.view(torch.int32))) for x in allth)
+        if not ranks_identical and rank == 0:
+            for r in range(1, world):
+                bad = (allth[0].view(torch.int32) != allth[r].view(torch.int32)).nonzero().flatten()
+                if bad.numel():
+                    print("rank 0 vs rank %d: %d of %d parameters differ, max |diff| %.3e, first offsets %s; slots %s" % (
+                        r, bad.numel(), th.numel(), float((allth[0] - allth[r]).abs().max()), bad[:8].tolist(),
+                        [(sl.offset, sl.D, sl.H, sl.out) for sl in agent.policy.arena.slots]), file=sys.stderr, flush=True)
 
     if rank != 0:
         if dist is not None:

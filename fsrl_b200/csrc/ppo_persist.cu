@@ -60,7 +60,12 @@ constexpr int SUMSQ_FLOATS = 128;                               // global tail: 
 // flag lines (32 unsigned each): per net A, C, D1, B[4]; global D2
 constexpr int FLAG_LINE = 32;
 constexpr int F_A = 0, F_C = 1, F_D1 = 2, F_B = 3, F_PER_NET = 7;
-constexpr int TM_COLS = 256, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,64) accumulators, Adam state
+constexpr int TM_COLS = 512, TM_P = 64, TM_M = 96, TM_V = 128;  // tensor-memory columns: [0,64) accumulators, Adam state
+// The two cross terms a_lo b_hi + a_hi b_lo accumulate in their OWN tensor-memory columns [TM_C, TM_C + 64) and meet the
+// a_hi b_hi sum only in the epilogue: the tensor core's accumulator add drops the low bits of a small addend, and the
+// cross terms are 2^-11 of the main ones (tools/micro/umma_probe.cu accuracy study, K = 256: rms error vs fp64 1.7e-6 with
+// one accumulator, 5.7e-7 with the corrections apart; an fp32 FMA chain: 1.9e-7).  Same MMA count, one more tcgen05.ld.
+constexpr int TM_C = 256;
 constexpr int TM_G = 160;                                        // reduced gradient tile (data-parallel runs)
 // peer-mapped exchange buffer of one step parity (floats): one region per SOURCE rank [8] plus one for the W2 means
 // (written by the packets' owners), each holding per net 16 gradient tiles and the locally reduced small-parameter
@@ -68,7 +73,10 @@ constexpr int TM_G = 160;                                        // reduced grad
 // every peer's buffer as 16-byte packets {3 floats, tag}: the tag (launch sequence number | step) travels with the data,
 // so the receiver polls its own memory until every packet carries the tag -- one NVLink one-way latency per exchange,
 // no system-scope fence (measured: ~6 us each with posted peer writes outstanding), no flag round trip, no remote loads.
-// (A 16-byte aligned vector store is one write transaction; NCCL's LL128 protocol relies on 128-byte ones over NVLink.)
+// The tag word is XORed with a hash of the three payload words: a 16-byte vector store does NOT become visible atomically
+// to a concurrent 16-byte load on the receiving GPU (measured on 2 x B200: about one packet in 1e9 showed the new tag
+// next to a stale payload word, i.e. one diverging parameter update per ~10k optimiser steps; tools/dp_identity_check.py),
+// so the receiver accepts a packet only if tag AND payload agree and simply polls again otherwise.
 constexpr int NSMAX = (MAXD + 1) * 32 + 32 + 32 * OUTP + 16;
 constexpr int TILE_PK = (64 * 64 / NEPI + 2) / 3;                // packets per thread of a 64 x 64 tile (16 floats -> 6)
 constexpr int TILE_FLOATS = TILE_PK * NEPI * 4;                  // [packet][thread][4]
@@ -116,9 +124,17 @@ __device__ __forceinline__ void fail(int* err, int code) {
     __threadfence_system();
     asm volatile("trap;");
 }
-// one 16-byte packet {x, y, z, tag}: a single vector store into peer memory / a single vector load from local memory
+// one 16-byte packet {x, y, z, tag ^ hash(x, y, z)}: a single vector store into peer memory / a single vector load from
+// local memory.  The fourth word vouches for the other three: a packet is accepted only if it carries the expected tag
+// AND its payload hashes to what the sender hashed, so a reader can never combine a fresh tag with stale payload words
+// (whatever the granularity at which the fabric / L2 make a 16-byte write visible).
+__device__ __forceinline__ uint32_t pk_hash(float x, float y, float z) {
+    const uint32_t a = __float_as_uint(x), b = __float_as_uint(y), c = __float_as_uint(z);
+    return a ^ __funnelshift_l(b, b, 11) ^ __funnelshift_l(c, c, 22);
+}
+__device__ __forceinline__ bool pk_ok(const float4& v, uint32_t tag) { return (__float_as_uint(v.w) ^ pk_hash(v.x, v.y, v.z)) == tag; }
 __device__ __forceinline__ void st_packet(float* p, float x, float y, float z, uint32_t tag) {
-    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(tag)) : "memory");
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(tag ^ pk_hash(x, y, z))) : "memory");
 }
 __device__ __forceinline__ float4 ld_packet(const float* p) {
     float4 v;
@@ -143,7 +159,7 @@ __device__ __noinline__ float3 dp_gather(const float* src, long long stride, int
                 if (r0 + k < world && r0 + k != me) v[k] = ld_packet(src + (size_t)(r0 + k) * stride);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (r0 + k < world && r0 + k != me) ok = ok && (__float_as_uint(v[k].w) == tag);
+                if (r0 + k < world && r0 + k != me) ok = ok && pk_ok(v[k], tag);
             if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(err, code);
         } while (!ok);
 #pragma unroll
@@ -240,6 +256,27 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two loads in flight, one wait (NC = 8 / 16): the accumulator columns and their correction columns
+template <int NC> __device__ __forceinline__ void tmem_ld_pair(uint32_t ta, uint32_t tb, float (&x)[NC], float (&y)[NC]) {
+    static_assert(NC == 8 || NC == 16, "pair loads in use");
+    uint32_t r[NC], q[NC];
+    if constexpr (NC == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(ta));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "r"(tb));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+                       "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]) : "r"(tb));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { x[i] = __uint_as_float(r[i]); y[i] = __uint_as_float(q[i]); }
+}
 // NC = 8 / 16 / 32 consecutive columns of this thread's tensor-memory lane
 template <int NC> __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[NC]) {
     if constexpr (NC == 8) tmem_ld8(taddr, v);
@@ -259,8 +296,15 @@ template <int NC> __device__ __forceinline__ void tmem_stn(uint32_t taddr, const
 template <int NC>
 __device__ __forceinline__ void acc_ld_split(uint32_t taddr, int lane, int col_lo, int col_hi, float (&v)[NC]) {
     float w[NC];
-    tmem_ldn<NC>(taddr + col_hi, w);
-    tmem_ldn<NC>(taddr + col_lo, v);
+    {
+        float c[NC];
+        tmem_ld_pair<NC>(taddr + col_hi, taddr + TM_C + col_hi, w, c);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) w[j] += c[j];
+        tmem_ld_pair<NC>(taddr + col_lo, taddr + TM_C + col_lo, v, c);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] += c[j];
+    }
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
         const float x = __shfl_sync(0xffffffffu, w[j], lane & 15);
@@ -361,6 +405,7 @@ __device__ __noinline__ void dp_tile_reduce(DpCtx d, size_t off, uint32_t tm_lan
         if (3 * q + 1 < C2) g[3 * q + 1] = ay;
         if (3 * q + 2 < C2) g[3 * q + 2] = az;
     }
+    __syncwarp();      // the lanes left their poll loops at different times: tcgen05.st is .sync.aligned
     tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
 }
 // the other owners' means: wait for them in the local result region, complete the tile in TM_G, return its sum of squares
@@ -387,7 +432,7 @@ __device__ __noinline__ float dp_tile_finish(DpCtx d, size_t off, uint32_t tm_la
 #pragma unroll
                 for (int q = 0; q < TILE_PK; ++q) v[q] = ld_packet(src + (size_t)q * NEPI * 4);
 #pragma unroll
-                for (int q = 0; q < TILE_PK; ++q) ok = ok && (__float_as_uint(v[q].w) == d.tag);
+                for (int q = 0; q < TILE_PK; ++q) ok = ok && pk_ok(v[q], d.tag);
                 if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(d.err, 42);
             } while (!ok);
 #pragma unroll
@@ -401,6 +446,7 @@ __device__ __noinline__ float dp_tile_finish(DpCtx d, size_t off, uint32_t tm_la
         float sq = 0.f;
 #pragma unroll
         for (int jq = 0; jq < C2; ++jq) { g[jq] *= inv_world; sq = fmaf(g[jq], g[jq], sq); }
+        __syncwarp();  // the lanes left their poll loops at different times: tcgen05.st is .sync.aligned
         tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
         return sq;
     }
@@ -415,7 +461,7 @@ __device__ __noinline__ float dp_tile_finish(DpCtx d, size_t off, uint32_t tm_la
             if (dp_owner(et, q, d.world) != d.me) v[q] = ld_packet(res + (size_t)q * NEPI * 4);
 #pragma unroll
         for (int q = 0; q < TILE_PK; ++q)
-            if (dp_owner(et, q, d.world) != d.me) ok = ok && (__float_as_uint(v[q].w) == d.tag);
+            if (dp_owner(et, q, d.world) != d.me) ok = ok && pk_ok(v[q], d.tag);
         if (!ok && clock64() - t0w > 4 * WAIT_CYCLES) fail(d.err, 42);
     } while (!ok);
     float sq = 0.f;
@@ -428,6 +474,7 @@ __device__ __noinline__ float dp_tile_finish(DpCtx d, size_t off, uint32_t tm_la
     }
 #pragma unroll
     for (int jq = 0; jq < C2; ++jq) sq = fmaf(g[jq], g[jq], sq);
+    __syncwarp();
     tmem_stn<C2>(tm_lane + TM_G + C2 * wq, g);
     return sq;
 }
@@ -559,9 +606,9 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                         const uint64_t al = smem_desc(base + 16384 + ks * 2048, 1024, 128);
                         const uint64_t bh = smem_desc(base + 32768 + ks * 1024, 512, 128);
                         const uint64_t bl = smem_desc(base + 40960 + ks * 1024, 512, 128);
-                        mma_tf32_ss(tmem, al, bh, id32, (j | ks) != 0);
-                        mma_tf32_ss(tmem, ah, bl, id32, true);
-                        mma_tf32_ss(tmem, ah, bh, id32, true);
+                        mma_tf32_ss(tmem + TM_C, al, bh, id32, (j | ks) != 0);
+                        mma_tf32_ss(tmem + TM_C, ah, bl, id32, true);
+                        mma_tf32_ss(tmem, ah, bh, id32, (j | ks) != 0);
                     }
                     mma_commit(&bar_empty[s]);
                 }
@@ -580,9 +627,9 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                         const uint64_t al = smem_desc(base + 16384 + ks * 2048, 1024, 128);
                         const uint64_t bh = smem_desc(base + 32768 + ks * 2048, 1024, 128);
                         const uint64_t bl = smem_desc(base + 49152 + ks * 2048, 1024, 128);
-                        mma_tf32_ss(tmem, al, bh, id64, (j | ks) != 0);
-                        mma_tf32_ss(tmem, ah, bl, id64, true);
-                        mma_tf32_ss(tmem, ah, bh, id64, true);
+                        mma_tf32_ss(tmem + TM_C, al, bh, id64, (j | ks) != 0);
+                        mma_tf32_ss(tmem + TM_C, ah, bl, id64, true);
+                        mma_tf32_ss(tmem, ah, bh, id64, (j | ks) != 0);
                     }
                     mma_commit(&bar_empty[s]);
                 }
@@ -755,6 +802,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
 
             // ---- G1 epilogue: h2 = relu(acc + b2), head partial over this tile's 32 columns -------------
             if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 30);
+            __syncwarp();      // every thread polled on its own: reconverge before the .sync.aligned tensor-memory loads
             ++acc_phase;
             tc_fence_after();
             if (et == 0) STAMP(2);
@@ -807,6 +855,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     }
                 }
                 if (!mbar_wait_cluster(&bar_b, t & 1, WAIT_CYCLES)) fail(P.err, 31);
+                __syncwarp();
                 if (et == 0) STAMP(4);
 #pragma unroll
                 for (int bb = 0; bb < 8; ++bb) {
@@ -1011,6 +1060,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                     xr[q] = (q < nx && et + q * NEPI < 64 * D) ? __ldg(xb + et + q * NEPI) : 0.f;
             }
             if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 32);
+            __syncwarp();      // every thread polled on its own: reconverge before the .sync.aligned tensor-memory loads
             ++acc_phase;
             tc_fence_after();
             if (et == 0) STAMP(6);
@@ -1113,6 +1163,7 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
                 epi_bar();                                    // sp_g complete
                 if (!is_g2 && !d.direct) { dp_tile_reduce(d, off_t, tm_lane, lane, wq, et); if (et == 0) STAMP(33); }
                 dp_slices(d, (size_t)u.n_nets * 16 * TILE_FLOATS + (size_t)(net * 8 + b) * SLICE_PK * 4, sp_g, sm.n, et, a == 0);
+                __syncwarp();
                 if (et == 0) STAMP(38);
                 if (!is_g2) { sq += dp_tile_finish(d, off_t, tm_lane, lane, wq, et); if (et == 0) STAMP(41); }
                 epi_bar();                                    // sp_g holds the global mean before the norm / Adam read it
