@@ -206,8 +206,6 @@ def test_offpolicy_rollout_heads_match_oracle(algo, head):
     np.testing.assert_allclose(b["rew"], obuf.rew, rtol=0, atol=5e-3)
 
 
-@pytest.mark.xfail(strict=False, reason="API wrapper added after the round's GPU budget was spent: not yet run on a B200 "
-                                        "(the kernel underneath is covered by test_nstep_prepare_matches_oracle)")
 def test_compute_nstep_returns_api_matches_oracle():
     """BasePolicy.compute_nstep_returns (base_policy.py:453-512) as a public call: user-supplied target_q_fn,
     batch.rets of shape (B, 1, C) like the reference's (target_q keeps its trailing axis)."""

@@ -245,11 +245,12 @@ def test_gradients_against_fp64_autograd(hidden, task, lag):
     for r in rows:
         print("%-18s %12.3e %12.3e" % r)
     for name, e_dev, e_32 in rows:
-        # Measured (B200): the fp32 autograd reference sits 1e-7..6e-7 from fp64, the device 4e-7..2e-6 -- the 3xTF32
-        # products are ~8x coarser than an fp32 FMA chain -- and up to 1e-5 where the value loss
-        # gradient 2 (v - ret) cancels (|v - ret| << |v| amplifies the forward error of v into every group of that
-        # critic alike).  A wrong term in a kernel shows up at 1e-2 and above.
-        assert e_dev <= 2e-5, (name, e_dev, e_32)
+        # Measured (B200): the fp32 autograd reference sits 1e-7..6e-7 from fp64.  The persistent tcgen05 launch
+        # (H = 256 case; 3xTF32 with the cross terms in their own tensor-memory accumulator) sits at
+        # 4e-7..1e-6; the three-launch chain (H = 512 cases, mma.sync 3xTF32, one accumulator) at 4e-7..4e-6 and up
+        # to 1e-5 where the value loss gradient 2 (v - ret) cancels (|v - ret| << |v| amplifies the forward error of
+        # v into every group of that critic alike).  A wrong term in a kernel shows up at 1e-2 and above.
+        assert e_dev <= (3e-6 if hidden == (256, 256) else 2e-5), (name, e_dev, e_32)
 
 
 @pytest.mark.parametrize("hidden,task,lag", [((512, 512), "SafetyPointGoal1Gymnasium-v0", 0.4),

@@ -85,7 +85,7 @@ def main():
     # decode the images (they hold the operands of the LAST step = the only step)
     ws = policy._persist_ws.detach().cpu().numpy()
     from fsrl_b200 import _lib as _fl
-    lib_net_ws = int(_fl.lib.fsrl_ppo_persist_ws_floats(2, 8, 256)) - int(_fl.lib.fsrl_ppo_persist_ws_floats(1, 8, 256)) - 7 * 32 - 2 * 32 * 32
+    lib_net_ws = int(_fl.lib.fsrl_ppo_persist_ws_floats(2, 8, 256)) - int(_fl.lib.fsrl_ppo_persist_ws_floats(1, 8, 256)) - 7 * 32 - 2 * 32 * 48
     x = sub.obs.cpu().double().numpy()
     perm = None
     for net in range(3):
