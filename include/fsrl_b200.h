@@ -189,9 +189,12 @@ typedef struct fsrl_ppo_update {
     float* p2p_part;               /* local [FSRL_P2P_PARTIALS]: per-CTA sums of g^2 (summed in a fixed
                                     * order by the Adam kernel: atomics would break rank lock-step) */
     int p2p_rank, p2p_on;
-    /* persistent tcgen05 path (csrc/ppo_persist.cu; H = 256, batch 256, single GPU): workspace of
+    /* persistent tcgen05 path (csrc/ppo_persist.cu; H = 256, batch 256): workspace of
      * fsrl_ppo_persist_ws_floats() floats for the operand images / partials / flags; NULL or
-     * persist_off != 0 selects the three-launch chain */
+     * persist_off != 0 selects the three-launch chain.  With world > 1 the launch exchanges gradients
+     * itself: it treats every p2p_xg[b][r] as fsrl_ppo_persist_p2p_floats() floats of packet regions
+     * (one per source rank + one for reduced tiles; ranks push, receivers poll their own buffer) and
+     * needs p2p_on, p2p_rank and p2p_stride >= that size; p2p_flags / p2p_part stay with the chain */
     float* persist_ws;
     long long persist_ws_floats;
     int persist_off, pad1;
