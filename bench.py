@@ -196,7 +196,8 @@ def ppo_rooflines(cfg, agent, col, buf, T, device, pk, how):
     ach = fl / (ms_rep * 1e-3) / 1e12
     peak = pk["bf16_tflops_sustained"]
     traffic_file = os.path.join(ROOT, "profiles", "r2_ppo_persist_traffic.json")
-    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else None
+    # the captured DRAM traffic belongs to the persistent launch; the chain's (H != 256) is in profiles/r1_ppo_update_ncu_summary.txt
+    traffic = json.load(open(traffic_file)) if (persistent and os.path.exists(traffic_file)) else None
     roof = {"kernel": "ppo_persist_kernel (one launch per repeat: tcgen05 kind::tf32 3-term split, TMEM accumulators, bulk-copy "
                       "operand images)" if persistent else "ppo_fwd/bwd/wgrad_adam chain (three launches per minibatch)",
             "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
