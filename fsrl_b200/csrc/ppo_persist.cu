@@ -320,15 +320,17 @@ __device__ __forceinline__ void acc_ld_split(uint32_t taddr, int lane, int col_l
 // instruction); staged through `scr` (an idle operand-ring slot, row stride 65: conflict-free) it becomes
 // float4 stores, 512 contiguous bytes per warp instruction.
 template <int NC, int W>
-__device__ __forceinline__ void store_transposed(float* scr, const float (&hi)[NC], const float (&lo)[NC], int row, int c0,
-                                                 int et, float* img_hi, int row_base, int col_base) {
+__device__ __forceinline__ void transposed_stage(float* scr, const float (&hi)[NC], const float (&lo)[NC], int row, int c0) {
     constexpr int LO = W * 65;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
         scr[(c0 + j) * 65 + row] = hi[j];
         scr[LO + (c0 + j) * 65 + row] = lo[j];
     }
-    epi_bar();
+}
+template <int W>
+__device__ __forceinline__ void transposed_flush(const float* scr, int et, float* img_hi, int row_base, int col_base) {
+    constexpr int LO = W * 65;
     const int col = et % W;
     constexpr int GPT = 16 / (NEPI / W);                       // row groups (of 4 rows) per thread
     const int g0 = (et / W) * GPT;
@@ -340,6 +342,13 @@ __device__ __forceinline__ void store_transposed(float* scr, const float (&hi)[N
         *reinterpret_cast<float4*>(dst + (size_t)g * 256) = make_float4(sh[0], sh[1], sh[2], sh[3]);
         *reinterpret_cast<float4*>(dst + IMG + (size_t)g * 256) = make_float4(sh[LO], sh[LO + 1], sh[LO + 2], sh[LO + 3]);
     }
+}
+template <int NC, int W>
+__device__ __forceinline__ void store_transposed(float* scr, const float (&hi)[NC], const float (&lo)[NC], int row, int c0,
+                                                 int et, float* img_hi, int row_base, int col_base) {
+    transposed_stage<NC, W>(scr, hi, lo, row, c0);
+    epi_bar();
+    transposed_flush<W>(scr, et, img_hi, row_base, col_base);
     epi_bar();                                                 // scratch may be reused
 }
 
@@ -745,31 +754,40 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             // step and images, so the other half of the grid (CTAs 0-15: a in {0, 1}) computes the tiles of row
             // blocks a and a + 2 -- same column block, hence the same W1 slice.
             if (is_g2) {
+                const int r = et & 63, kc = C1 * (et >> 6);  // row, first of C1 columns
+                // both row blocks' observation rows are in flight before anything is stored
+                const float* x0 = u.obs + (row0 + 64 * a + r) * D;
+                const float* x1 = u.obs + (row0 + 64 * (a + 2) + r) * D;
+                float acc2[2][C1];
+#pragma unroll
+                for (int j = 0; j < C1; ++j) acc2[0][j] = acc2[1][j] = sp_p[sm.w1 + D * 32 + kc + j];      // b1
+                for (int d = 0; d < D; ++d) {
+                    const float xv0 = __ldg(x0 + d), xv1 = __ldg(x1 + d);
+                    const float* w = sp_p + sm.w1 + d * 32 + kc;
+#pragma unroll
+                    for (int j = 0; j < C1; ++j) { acc2[0][j] = fmaf(xv0, w[j], acc2[0][j]); acc2[1][j] = fmaf(xv1, w[j], acc2[1][j]); }
+                }
+                constexpr int TSCR = 2 * 32 * 65;                  // staging floats of one [64 x 32] tile (hi + lo)
+#pragma unroll
                 for (int rep = 0; rep < 2; ++rep) {
                     const int aa = a + 2 * rep;
-                    const int r = et & 63, kc = C1 * (et >> 6);  // row, first of C1 columns
-                    const float* x = u.obs + (row0 + 64 * aa + r) * D;
-                    float acc[C1], hi[C1], lo[C1];
-#pragma unroll
-                    for (int j = 0; j < C1; ++j) acc[j] = sp_p[sm.w1 + D * 32 + kc + j];      // b1
-                    for (int d = 0; d < D; ++d) {
-                        const float xv = __ldg(x + d);
-                        const float* w = sp_p + sm.w1 + d * 32 + kc;
-#pragma unroll
-                        for (int j = 0; j < C1; ++j) acc[j] = fmaf(xv, w[j], acc[j]);
-                    }
+                    float hi[C1], lo[C1];
                     float* a_hi = wsn + (size_t)I_H1A_HI * IMG + (size_t)aa * 16384 + (size_t)r * 4;
 #pragma unroll
                     for (int q = 0; q < C1 / 4; ++q) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) tf32_split(fmaxf(acc[4 * q + e], 0.f), hi[4 * q + e], lo[4 * q + e]);
+                        for (int e = 0; e < 4; ++e) tf32_split(fmaxf(acc2[rep][4 * q + e], 0.f), hi[4 * q + e], lo[4 * q + e]);
                         const size_t plane = (size_t)(8 * b + (kc >> 2) + q) * 256;
                         *reinterpret_cast<float4*>(a_hi + plane) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
                         *reinterpret_cast<float4*>(a_hi + IMG + plane) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
                     }
-                    // H1T (MN = k, K = r): block b / 2, columns 32 (b & 1) ..
-                    store_transposed<C1, 32>(scratch, hi, lo, r, kc, et, wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384, 64 * aa, 32 * (b & 1));
+                    transposed_stage<C1, 32>(scratch + rep * TSCR, hi, lo, r, kc);
                 }
+                epi_bar();
+                // H1T (MN = k, K = r): block b / 2, columns 32 (b & 1) .. -- both tiles behind ONE pair of barriers
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep)
+                    transposed_flush<32>(scratch + rep * TSCR, et, wsn + (size_t)I_H1T_HI * IMG + (size_t)(b >> 1) * 16384, 64 * (a + 2 * rep), 32 * (b & 1));
             }
             epi_bar();
             if (et == 0) { STAMP(1); flag_add_release(fl_net + F_A * FLAG_LINE); }
