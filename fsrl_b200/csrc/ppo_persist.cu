@@ -1076,6 +1076,15 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
 #pragma unroll
                 for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q)
                     xr[q] = (q < nx && et + q * NEPI < 64 * D) ? __ldg(xb + et + q * NEPI) : 0.f;
+                // cluster launches: the hop-B landing zone is idle until the next step -- the observation block is staged
+                // there NOW, while the GEMM still runs (row r at r * D + (r >> 5): the two half-warps read different banks)
+                if (P.cluster) {
+#pragma unroll
+                    for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q) {
+                        const int e = et + q * NEPI;
+                        if (q < nx && e < 64 * D) { const int r = e / D; land[e + (r >> 5)] = xr[q]; }
+                    }
+                }
             }
             if (!mbar_wait(&bar_acc, acc_phase & 1, WAIT_CYCLES)) fail(P.err, 32);
             __syncwarp();      // every thread polled on its own: reconverge before the .sync.aligned tensor-memory loads
@@ -1084,13 +1093,15 @@ __global__ void __launch_bounds__(TPB, 1) ppo_persist_kernel(const Args P) {
             if (et == 0) STAMP(6);
             float sq = 0.f;
             if (is_g2) {
-                // the operand ring is idle from here until the next step's flag A: slot 0 serves as scratch for the
-                // observation block (row r at r * D + (r >> 5): the two half-warps read different banks)
-                float* xs = reinterpret_cast<float*>(ring);
+                // without clusters the observation block goes to slot 0 of the operand ring, idle from here until the
+                // next step's flag A
+                float* xs = P.cluster ? land : reinterpret_cast<float*>(ring);
+                if (!P.cluster) {
 #pragma unroll
-                for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q) {
-                    const int e = et + q * NEPI;
-                    if (q < nx && e < 64 * D) { const int r = e / D; xs[e + (r >> 5)] = xr[q]; }
+                    for (int q = 0; q < (64 * MAXD + NEPI - 1) / NEPI; ++q) {
+                        const int e = et + q * NEPI;
+                        if (q < nx && e < 64 * D) { const int r = e / D; xs[e + (r >> 5)] = xr[q]; }
+                    }
                 }
                 // lane: k = 64 ka + trow ; rows cb2 + j of row block q4; partial set 2 q4 + wq (WQ sets per row block)
                 float v[C2];
