@@ -75,3 +75,21 @@ def test_header_is_plain_c99(tmp_path):
     sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     from fsrl_b200 import _lib
     assert sizes == [int(_lib.lib.fsrl_abi_sizeof(i)) for i in range(10)]
+
+
+def test_persistent_exchange_buffers_fit_the_peer_block():
+    """Host-side sizing of the persistent PPO launch (no device call): the packet regions of the data-parallel exchange
+    (8 source-rank regions + 1 result region per parity) must fit the peer block `parallel.enable_p2p` is
+    willing to allocate, and the workspace must grow with the number of networks."""
+    from fsrl_b200 import _lib
+    lib = _lib.lib
+    sizes = [int(lib.fsrl_ppo_persist_p2p_floats(n)) for n in (1, 2, 3)]
+    assert sizes[0] < sizes[1] < sizes[2]
+    assert sizes[2] <= 4096 * 1024                      # the bound enable_p2p applies to one parity buffer
+    per_net = sizes[1] - sizes[0]
+    assert per_net % 9 == 0 and sizes[2] - sizes[1] == per_net
+    stride = int(lib.fsrl_p2p_stride(sizes[2]))
+    assert stride >= sizes[2] and stride % 64 == 0
+    assert int(lib.fsrl_p2p_block_bytes(sizes[2])) >= 2 * 4 * stride
+    ws = [int(lib.fsrl_ppo_persist_ws_floats(n, 8, 256)) for n in (1, 2, 3)]
+    assert ws[0] < ws[1] < ws[2] and ws[2] - ws[1] == ws[1] - ws[0]
