@@ -25,6 +25,13 @@
 //       96 partials in the same order.
 // All operand images are K-major SWIZZLE_NONE plane images (umma.cuh); transposed copies are written
 // by the producer (MN-major tf32 operands would need the 128B_BASE32B swizzle).
+//
+// CTA = 320 threads: warp 0 bulk-copy producer, warp 1 MMA issuer, warps 2-9 epilogue (two per tensor-memory
+// subpartition).  The 8 CTAs of a row block form a thread-block cluster: their head partials travel over distributed
+// shared memory (st.async + mbarrier complete_tx); all other hops are flag lines in L2.  The cross terms of the 3-term
+// split accumulate in their own tensor-memory columns (TM_C).  With world > 1 the <DP = true> instantiation exchanges
+// gradients itself over peer memory (dp_* functions below: tagged + hashed 16-byte packets pushed into the peers' buffers).
+// DESIGN.md 3a / 6 hold the measurements behind these choices.
 #include "ppo_persist.cuh"
 #include "umma.cuh"
 #include <cstdlib>
