@@ -110,3 +110,60 @@ def test_trust_region_combiners_equal_union_batch():
         np.testing.assert_allclose(x, want_x, rtol=2e-5, atol=2e-6)
         assert mismatch_raises
     np.testing.assert_array_equal(res[0][2], res[1][2])      # identical reduced vector on both ranks
+
+
+def _trainer_worker(rank, world, port, q):
+    """BaseTrainer's cycle loop with ranks that collect DIFFERENT step counts per cycle (early terminations on one rank):
+    every rank must leave the loop after the same number of cycles and size its updates from the same agreed count."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fsrl_b200.parallel import DataParallel
+    from fsrl_b200.trainer.base_trainer import BaseTrainer
+    from fsrl_b200.utils.logger import DummyLogger
+
+    dp = DataParallel(dist, with_nccl=False)
+
+    class Policy:
+        _dp = dp
+        def train(self): pass
+        def eval(self): pass
+
+    class Collector:
+        collect_time, collect_step = 1e-3, 0
+        def reset_stat(self): pass
+        def collect(self, n_episode):
+            n_st = 300 if rank == 0 else 240          # rank 1's episodes end early
+            self.collect_step += n_st
+            local = {"n/ep": 1, "n/st": n_st, "rew": 1.0, "len": float(n_st), "total_cost": 2.0, "cost": 2.0,
+                     "truncated": 1.0, "terminated": 0.0}
+            return dp.reduce_collect_stats(local)     # what parallel.attach's pre_update_fn hook feeds the policy
+
+    class Trainer(BaseTrainer):
+        cycles, sizes = 0, []
+        def policy_update_fn(self, stats_train):
+            self.cycles += 1
+            self.sizes.append(self._cycle_steps)
+
+    tr = Trainer("onpolicy", Policy(), Collector(), None, max_epoch=2, step_per_epoch=1000, episode_per_test=1,
+                 episode_per_collect=1, logger=DummyLogger(), verbose=False, show_progress=False)
+    tr.run()
+    q.put((rank, tr.cycles, tuple(tr.sizes), tr.env_step))
+    dist.destroy_process_group()
+
+
+def test_trainer_cycles_agree_when_ranks_collect_different_step_counts():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, c0, s0, e0), (_, c1, s1, e1) = res
+    assert c0 == c1 == 8                                  # 2 epochs x ceil(1000 / 300): the quota advances by the agreed count
+    assert s0 == s1 == (300,) * 8                         # the larger rank's count, on both ranks
+    assert e0 == e1 == 8 * 540                            # env_step counts the GLOBAL steps the reduced statistics report
